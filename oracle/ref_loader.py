@@ -1,0 +1,235 @@
+"""TEST INFRASTRUCTURE ONLY.  Loads the reference's OWN hot-path functions,
+read-only, from ``/root/reference`` under a stub importer.
+
+The reference package cannot be imported as a whole (``mmengine`` / ``mmcv`` /
+``matplotlib`` are not installed and there is no network), but the three files
+that carry the hot-path arithmetic only need those packages for decorators,
+base classes and logging.  We fabricate empty stand-ins for exactly those roots
+and then load the three files by path.  Nothing is copied into this repo.
+
+Available only in the build container: ``/root/reference`` does not exist on the
+GPU box, so nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` may call this
+module - they use ``oracle.restated`` (pinned against fixtures produced here by
+``oracle/make_golden.py``).
+"""
+from __future__ import annotations
+
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+from collections import defaultdict
+from types import SimpleNamespace
+
+REFERENCE_ROOT = os.environ.get("NSGP_REFERENCE_ROOT", "/root/reference")
+
+_STUB_ROOTS = ("mmengine", "mmcv", "matplotlib", "mmdet")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(
+        REFERENCE_ROOT, "mmdet/engine/optimizers/SGD_NSCL.py"))
+
+
+class _Registry:
+    """Stand-in for an mmengine Registry: ``register_module()`` is identity."""
+
+    def register_module(self, *a, **k):
+        def deco(obj):
+            return obj
+        return deco
+
+
+class _StubModule(types.ModuleType):
+    """Empty package whose attributes are fabricated on demand."""
+
+    def __init__(self, name):
+        super().__init__(name)
+        self.__path__ = []          # mark as package so sub-imports resolve
+        self.__file__ = "<stub %s>" % name
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        if item.isupper():                       # registries: RUNNERS, MODELS ...
+            val = _Registry()
+        elif item == "is_model_wrapper":
+            val = lambda m: False
+        elif item == "get_rank":
+            val = lambda *a, **k: 0
+        elif item == "get_world_size":
+            val = lambda *a, **k: 1
+        elif item in ("print_log",):
+            val = lambda *a, **k: None
+        elif item in ("barrier", "all_reduce", "all_reduce_dict", "broadcast"):
+            val = lambda *a, **k: None
+        else:                                    # base classes / type hints
+            val = type(item, (), {})
+        setattr(self, item, val)
+        return val
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in _STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        return None
+
+
+_finder = None
+
+
+def _install_stubs():
+    global _finder
+    if _finder is None:
+        for root in _STUB_ROOTS:
+            if root in sys.modules and not isinstance(sys.modules[root], _StubModule):
+                raise RuntimeError(
+                    "real %s is importable; use it instead of the stub loader" % root)
+        _finder = _StubFinder()
+        sys.meta_path.insert(0, _finder)
+
+
+def _load_by_path(modname: str, relpath: str, package: str | None = None):
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    if package is not None:
+        mod.__package__ = package
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_cache: dict = {}
+
+
+def load_sgd_nscl():
+    """The reference ``SGDNSCL`` class (mmdet/engine/optimizers/SGD_NSCL.py:15)."""
+    if "sgd" not in _cache:
+        _install_stubs()
+        mod = _load_by_path("_ref_sgd_nscl", "mmdet/engine/optimizers/SGD_NSCL.py")
+        _cache["sgd"] = mod.SGDNSCL
+    return _cache["sgd"]
+
+
+def load_runner():
+    """The reference ``BRNullSpaceRunner`` class
+    (mmdet/engine/runner/nsrunner_roi_replay.py:111); only its unbound
+    ``compute_cov`` / ``update_cov`` are ever called."""
+    if "runner" not in _cache:
+        _install_stubs()
+        mod = _load_by_path("_ref_nsrunner",
+                            "mmdet/engine/runner/nsrunner_roi_replay.py")
+        _cache["runner"] = mod.BRNullSpaceRunner
+    return _cache["runner"]
+
+
+def load_multi_prototype_head():
+    """The reference ``StandardMultiPrototypeReplayHead`` class
+    (mmdet/models/roi_heads/standard_roi_replay_head.py:375) with
+    ``StandardRoIHead`` replaced by a trivial ``nn.Module``."""
+    if "head" not in _cache:
+        _install_stubs()
+        import torch
+        import torch.nn as nn
+
+        pkg = "_ref_models"
+        for name in (pkg, pkg + ".roi_heads", pkg + ".task_modules",
+                     pkg + ".task_modules.samplers", pkg + ".utils",
+                     pkg + ".roi_heads.base_roi_head",
+                     pkg + ".roi_heads.standard_roi_head"):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+
+        class StandardRoIHead(nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+                self._dummy = nn.Parameter(torch.zeros(1))
+                self.with_shared_head = False
+
+        sys.modules[pkg + ".roi_heads.standard_roi_head"].StandardRoIHead = StandardRoIHead
+        sys.modules[pkg + ".roi_heads.base_roi_head"].BaseRoIHead = type("BaseRoIHead", (), {})
+        sys.modules[pkg + ".task_modules.samplers"].SamplingResult = type("SamplingResult", (), {})
+        sys.modules[pkg + ".utils"].empty_instances = None
+        sys.modules[pkg + ".utils"].unpack_gt_instances = None
+        mod = _load_by_path(pkg + ".roi_heads.standard_roi_replay_head",
+                            "mmdet/models/roi_heads/standard_roi_replay_head.py",
+                            package=pkg + ".roi_heads")
+        _cache["head"] = mod.StandardMultiPrototypeReplayHead
+        _cache["head_mod"] = mod
+    return _cache["head"]
+
+
+# --------------------------------------------------------------------------- #
+# Thin drivers around the reference's own functions
+# --------------------------------------------------------------------------- #
+
+def ref_covariances(model, batches, mode_call=None):
+    """Run the reference ``compute_cov`` / ``update_cov`` as real forward hooks.
+
+    ``model`` is any ``nn.Module``; ``batches`` an iterable of input tensors.
+    Returns the reference's ``fea_in`` dict  {"<module path>.weight": (d,d)}.
+    Follows the hook registration of nsrunner_roi_replay.py:731-744.
+    """
+    import torch
+    Runner = load_runner()
+    fake = SimpleNamespace(model=model, fea_in=defaultdict(dict))
+    fake.update_cov = lambda fea, k: Runner.update_cov(fake, fea, k)
+    hook = lambda m, i, o: Runner.compute_cov(fake, m, i, o)
+    handles = [m.register_forward_hook(hook)
+               for n, m in model.named_modules() if hasattr(m, "weight")]
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        for x in batches:
+            (mode_call or model)(x)
+    for h in handles:
+        h.remove()
+    model.train(was_training)
+    return dict(fake.fea_in)
+
+
+def ref_optimizer(named_params, **kw):
+    """Build the reference SGDNSCL with the runner's ``names`` convention
+    (nsrunner_roi_replay.py:473-484)."""
+    SGDNSCL = load_sgd_nscl()
+    names = [n for n, _ in named_params]
+    params = [p for _, p in named_params]
+    opt = SGDNSCL(params, **kw)
+    opt.param_groups[0]["names"] = names
+    return opt
+
+
+def ref_prototypes(feats, cls_targets, task_split, task_id, max_prototype, tmpdir,
+                   saved_masks=None):
+    """Run the reference StandardMultiPrototypeReplayHead.__init__ prototype build
+    (standard_roi_replay_head.py:397-452) on a synthetic rois_etc.pth.
+
+    Returns (bbox_featss (P,D), tmp_label (P,), mask list as saved to mask.pth).
+    """
+    import torch
+    Head = load_multi_prototype_head()
+    prev = os.path.join(tmpdir, "x_%d" % (task_id - 1))
+    cur = os.path.join(tmpdir, "x_%d" % task_id)
+    os.makedirs(prev, exist_ok=True)
+    os.makedirs(cur, exist_ok=True)
+    M = feats.shape[0]
+    torch.save([feats, cls_targets, torch.ones(M), torch.zeros(M, 4),
+                torch.zeros(M, 4), torch.zeros(M, 5)],
+               os.path.join(prev, "rois_etc.pth"))
+    if saved_masks is not None:
+        torch.save(saved_masks, os.path.join(prev, "mask.pth"))
+    head = Head(previous_path=prev, task_id=task_id, task_split=list(task_split),
+                max_prototype=max_prototype)
+    masks = torch.load(os.path.join(cur, "mask.pth"), map_location="cpu")
+    return head.bbox_featss, head.tmp_label, masks

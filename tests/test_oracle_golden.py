@@ -1,0 +1,122 @@
+"""The CPU restatement (oracle/restated.py) against the fixtures produced by the
+reference's OWN functions (oracle/make_golden.py -> tests/golden/*.pt).
+CPU only; this is what pins the oracle (the reference itself has
+no tests for this path)."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_fro
+from oracle import restated as O
+from oracle import synth
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), map_location="cpu", weights_only=False)
+
+
+def test_covariance_hooks_match_reference(golden_dir):
+    g = _load(golden_dir, "cov_toy.pt")
+    net = synth.ToyDetector()
+    net.load_state_dict(g["state_dict"])
+    batches = synth.toy_batches(seed=g["seed"])
+    assert abs(float(sum(b.double().sum() for b in batches)) - g["batch_checksum"]) < 1e-6
+    fea = O.covariances_of_model(net, batches)
+    assert set(fea) == set(g["fea_in"])
+    for k, ref in g["fea_in"].items():
+        assert fea[k].shape == ref.shape
+        assert rel_fro(fea[k], ref) < 2e-6, k
+
+
+def test_conv_rows_column_order_is_cin_kh_kw():
+    x = torch.arange(2 * 3 * 5 * 6, dtype=torch.float32).reshape(2, 3, 5, 6)
+    rows = O.conv_rows(x, (3, 3), (1, 1), (1, 1))
+    assert rows.shape == (30, 27)
+    m = x.mean(0)
+    # output pixel (oy=2, ox=3), channel 1, tap (0,2) -> input (1, 4)
+    assert rows[2 * 6 + 3, 1 * 9 + 0 * 3 + 2] == m[1, 1, 4]
+    # zero padding at the border
+    assert rows[0, 0] == 0
+
+
+@pytest.mark.parametrize("offset", [0.0, 0.5, -0.5, 3.0])
+def test_threshold_and_transform_match_reference(golden_dir, offset):
+    g = _load(golden_dir, "projector.pt")
+    for name, ent in g["proj"][offset].items():
+        d, seed, rank = g["seeds"][name]
+        cov = synth.decaying_cov(d, seed, rank=rank)
+        s, v = O.eigens(cov)
+        assert rel_fro(s, ent["svals"]) < 1e-5
+        # the reference's own spectrum -> identical cut index
+        assert O.threshold_index(ent["svals"].numpy(), offset) == ent["i_thres"]
+        assert O.threshold_index(s.numpy(), offset) == ent["i_thres"]
+        p = O.transform(s, v, name, offset)
+        assert rel_fro(p, ent["transform"]) < 1e-4, name
+        if "backbone" in name:
+            assert abs(float(torch.norm(p)) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["mom_wd", "plain", "nesterov_damp"])
+def test_sgd_nscl_steps_match_reference(golden_dir, tag):
+    g = _load(golden_dir, "sgd_steps.pt")
+    proj = _load(golden_dir, "projector.pt")["proj"][0.0]
+    transforms = {n: e["transform"] for n, e in proj.items()}
+    run = g["steps"][tag]
+    params = {n: v.clone() for n, v in g["init"].items()}
+    states = {}
+    for step, want in zip(g["grads"], run["traj"]):
+        grads = {n: v.clone() for n, v in step.items()}
+        O.sgd_nscl_step(params, grads, states, transforms, svd=True, **run["kw"])
+        for n in params:
+            assert rel_fro(params[n], want["w"][n]) < 1e-6, (tag, n)
+            assert rel_fro(states[n].previous_grad, want["buf"][n]) < 1e-6 or \
+                float(want["buf"][n].abs().max()) == 0.0
+            # in-place weight-decay side effect on .grad (SGD_NSCL.py:399-400)
+            assert rel_fro(grads[n], want["grad_after"][n]) < 1e-6, (tag, n)
+
+
+def test_prototypes_match_reference(golden_dir):
+    g = _load(golden_dir, "prototypes.pt")
+    feats, lab = synth.proto_features()
+    assert abs(float(feats.double().sum()) - g["feat_checksum"]) < 1e-3
+    assert torch.equal(lab, g["labels"])
+    protos, tmp_label, masks = O.build_prototypes(feats, lab, range(0, 3), max_proto=10)
+    assert torch.equal(tmp_label, g["tmp_label"])
+    assert [len(m) for m in masks] == [len(m) for m in g["masks"]]
+    for mine, ref in zip(masks, g["masks"]):
+        for a, b in zip(mine, ref):
+            assert torch.equal(a, b)
+    assert rel_fro(protos, g["protos"]) < 1e-6
+
+    # next task: saved masks are replayed for old classes, class 3 is new
+    feats2, lab2 = synth.proto_features(seed=1, classes=4, per_class=60, bg=20)
+    feats2 = torch.cat([feats, feats2[lab2 == 3]])
+    lab2 = torch.cat([lab, lab2[lab2 == 3]])
+    assert torch.equal(lab2, g["labels2"])
+    protos2, tmp_label2, masks2 = O.build_prototypes(
+        feats2, lab2, range(0, 4), max_proto=10, saved_masks=[list(m) for m in masks])
+    assert torch.equal(tmp_label2, g["tmp_label2"])
+    assert [len(m) for m in masks2] == [len(m) for m in g["masks2"]]
+    assert rel_fro(protos2, g["protos2"]) < 1e-6
+
+
+def test_replay_loss_double_softmax():
+    torch.manual_seed(0)
+    score = torch.randn(7, 21)
+    label = torch.randint(0, 10, (7,))
+    want = torch.nn.functional.cross_entropy(
+        torch.cat([score[:, :19], score[:, -1:]], -1).softmax(-1), label)
+    assert torch.allclose(O.replay_loss(score, label, 19), want)
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors from the Random123 distribution
+    (kat_vectors: zero counter/key and the pi-digits vector)."""
+    import numpy as np
+    out = O.philox4x32_10(np.zeros((1, 4), np.uint32), np.zeros(2, np.uint32))[0]
+    assert [hex(int(v)) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    ctr = np.array([[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], np.uint32)
+    key = np.array([0xa4093822, 0x299f31d0], np.uint32)
+    out = O.philox4x32_10(ctr, key)[0]
+    assert [hex(int(v)) for v in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
