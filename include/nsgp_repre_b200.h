@@ -1,0 +1,181 @@
+/* nsgp_repre_b200.h - C ABI of the B200-native NSGP-RePRE hot path.
+ *
+ * The reference (yyl404/NSGP-RePRE, a pure-Python MMDetection fork) has no FFI
+ * of its own: its plug-in surface is the mmengine registries.  This header is the
+ * boundary a maintainer binds UNDER those Python classes (ctypes stubs in
+ * INTEGRATION.md).  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked host;
+ *   - fp32, row-major, contiguous unless a pitch is given;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered,
+ *     nothing synchronises the device;
+ *   - return 0 on success, <0 invalid argument, >0 a cudaError_t value;
+ *     nsgp_last_error() returns the message of the last failure on this thread;
+ *   - no internal device allocation: scratch comes from the caller through the
+ *     *_workspace_bytes queries;
+ *   - sm_100a only.  There is no CPU fallback.
+ */
+#ifndef NSGP_REPRE_B200_H_
+#define NSGP_REPRE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSGP_ABI_VERSION 1
+
+int nsgp_abi_version(void);
+const char* nsgp_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports
+ * the delta over the timed region as "gpu_launches") */
+unsigned long long nsgp_launch_count(void);
+/* contraction engine: 0 = tcgen05/TMA 3xTF32 (product), 1 = SIMT fp32 FFMA
+ * (bring-up / on-device cross-check).  Returns the previous value. */
+int nsgp_set_engine(int engine);
+int nsgp_get_engine(void);
+
+/* ------------------------------------------------------------------------- *
+ * a1/a2  per-layer input covariance
+ *   replaces BRNullSpaceRunner.compute_cov + update_cov
+ *   (mmdet/engine/runner/nsrunner_roi_replay.py:876-916, 923-934)
+ * ------------------------------------------------------------------------- */
+
+/* Geometry of the internal accumulator for one hooked Conv2d.
+ *   d      = Cin*kh*kw, the covariance dimension of the reference
+ *   d_int  = rows/cols of the internal accumulator (>= d)
+ *   taps   = 1 or kh*kw: internal row order is (tap, channel) when taps > 1
+ *   ld     = leading dimension (elements) of the accumulator, = round_up(d_int,4) */
+typedef struct {
+  int d, d_int, taps, ld;
+  size_t acc_bytes;        /* ld * d_int * 4: zero it once before the first call */
+  size_t workspace_bytes;  /* scratch for one accumulate call */
+} nsgp_cov_layout_t;
+
+int nsgp_cov_conv2d_layout(int Cin, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                           int pw, nsgp_cov_layout_t* out /* host */);
+int nsgp_cov_linear_layout(int d, nsgp_cov_layout_t* out /* host */);
+
+/* acc += X^T X with X = unfold(mean_b(x)) - the batch mean is taken first, exactly
+ * like nsrunner_roi_replay.py:908.  x: (B,Cin,H,W).  Only the upper block-
+ * triangle of acc (internal row order) is maintained; nsgp_cov_finalize expands
+ * it.  Fuses torch.mean (:908), F.unfold+permute+reshape (:908-912), torch.mm
+ * (:930) and the running add (:931-934). */
+int nsgp_cov_conv2d_accumulate(const float* x, int B, int Cin, int H, int W, int kh, int kw,
+                               int sh, int sw, int ph, int pw, float* acc, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* Linear: acc += m^T m with m = mean over the R rows of x (R,d)
+ * (nsrunner_roi_replay.py:900-901, 930-934). */
+int nsgp_cov_linear_accumulate(const float* x, int R, int d, float* acc, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* cov_out (d x d, dense, symmetric, reference (Cin,kh,kw) order) = expand(acc),
+ * or += when accumulate != 0 (the "+ old covariance.pth" merge of :750-753). */
+int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* layout /* host */,
+                      float* cov_out, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * a7/a8  SGD update + null-space projection
+ *   replaces SGDNSCL.get_update + the projection loop of SGDNSCL.step
+ *   (mmdet/engine/optimizers/SGD_NSCL.py:387-415, 59-96)
+ * ------------------------------------------------------------------------- */
+
+/* dst_hi/dst_lo (d x d) = tf32 hi/lo split of P^T, the K-major operand of
+ * update @ P (SGD_NSCL.py:85-90).  Done once per task after get_transforms. */
+int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, void* stream);
+
+typedef struct {
+  float* w;          /* parameter, updated in place (:95) */
+  float* g;          /* p.grad, modified in place by weight decay (:399-400) */
+  float* buf;        /* state['previous_grad'] (:394) */
+  long long numel;
+  int first_step;    /* 1 when state['step'] becomes 1: buf = grad (:405-406) */
+  int layer;         /* index into layers[] when the name is in transforms, else -1 */
+} nsgp_sgd_tensor_t;
+
+typedef struct {
+  int cout, d;             /* update.view(cout, d) @ P(d,d) */
+  const float* pt_hi;      /* from nsgp_projector_prepare */
+  const float* pt_lo;
+  float* u_hi;             /* scratch (cout x d) each: staged update */
+  float* u_lo;
+} nsgp_proj_layer_t;
+
+size_t nsgp_sgd_step_workspace_bytes(int n_tensors, int n_layers);
+
+/* One optimizer step over all tensors: a fused multi-tensor prologue (weight
+ * decay, momentum, -lr) followed by the projection GEMMs W += update @ P for the
+ * protected layers.  tensors/layers are HOST arrays. */
+int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                       const nsgp_proj_layer_t* layers, int n_layers, double lr,
+                       double momentum, double dampening, double weight_decay, int nesterov,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * a9/a10/a11  RePRE prototypes
+ *   replaces the prototype build of StandardMultiPrototypeReplayHead.__init__
+ *   and the per-step staging of .loss
+ *   (mmdet/models/roi_heads/standard_roi_replay_head.py:411-449, 458-463)
+ * ------------------------------------------------------------------------- */
+
+/* Stable class index of labels (M,) int64 over classes [0,C): counts[C],
+ * offsets[C+1], rows[M] (rows of class c = rows[offsets[c]:offsets[c+1]],
+ * ascending) - the boolean-mask gather of :412. Labels outside [0,C) (background)
+ * are skipped. */
+int repre_class_index(const int64_t* labels, int M, int C, int32_t* counts, int32_t* offsets,
+                      int32_t* rows, void* stream);
+
+/* out[s][:] = mean over rows[seg_offsets[s]:seg_offsets[s+1]] of F (M,D):
+ * coarse class means (:412-414) and masked fine-grained means (:443).
+ * max_seg_rows: upper bound of the segment lengths (host hint for the grid). */
+int repre_segment_mean(const float* F, int D, const int32_t* seg_offsets,
+                       const int32_t* rows, int n_segments, int max_seg_rows, float* out,
+                       void* stream);
+
+/* extension (no reference counterpart): out[s][:] = mean((F[row]-mu[s])^2) */
+int repre_segment_var(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
+                      int n_segments, int max_seg_rows, const float* mu, float* out,
+                      void* stream);
+
+size_t repre_cosine_count_workspace_bytes(int n, int D);
+
+/* For the n gathered rows F[rows[i]]: L2-normalise, Gram, mask = Gram >= thresh,
+ * counts = row sums (:417-421).  mask: (n,n) uint8; counts: (n,) int32;
+ * sim_out: optional (n,n) fp32 copy of the Gram (may be NULL). */
+int repre_cosine_count(const float* F, int D, const int32_t* rows, int n, float thresh,
+                       uint8_t* mask, int32_t* counts, float* sim_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* out[p][:] = protos[idx[p]][:] (idx NULL: identity, the reference stages every
+ * prototype every step, :458-463; idx = randperm()[:64] is :58-59).  Extension:
+ * sigma != NULL adds sigma[idx[p]] * N(0,1) noise from Philox4x32-10 keyed by
+ * (seed, p, column/4). */
+int repre_replay_gather(const float* protos, const float* sigma, const int64_t* idx, int P,
+                        int D, uint64_t seed, float* out, void* stream);
+
+/* extension (no reference counterpart; sklearn KMeans is imported at
+ * standard_roi_replay_head.py:18 and never called): Lloyd assignment
+ * labels[i] = argmin_k |x_i - c_k|^2, ties -> lowest k. X (n,D), centres (k,D). */
+size_t repre_kmeans_assign_workspace_bytes(int n, int k, int D);
+int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int k,
+                        int64_t* labels, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
+int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
+
+/* test hook: C (M x ldc) += A (M x K) * B^T (B is N x K), 3xTF32 on the selected
+ * engine; a_/b_ are hi/lo pairs with pitch K. */
+int nsgp_debug_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
+                       const float* b_lo, int M, int N, int K, float* C, int ldc,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSGP_REPRE_B200_H_ */

@@ -1,0 +1,24 @@
+"""B200-native NSGP-RePRE hot path behind the reference's plug-in surface.
+
+Host layer (Python/PyTorch) mirroring the reference classes, over hand-written
+sm_100a kernels reached through the C ABI of ``include/nsgp_repre_b200.h``:
+
+* ``covariance.CovarianceHooks``   - BRNullSpaceRunner.compute_cov / update_cov /
+  fea_in and the reduce / merge / save tail of cal_fea_in
+  (mmdet/engine/runner/nsrunner_roi_replay.py:704-763, 876-934)
+* ``optim.SGDNSCL``                - mmdet/engine/optimizers/SGD_NSCL.py:15
+* ``prototypes.MultiPrototypeReplay`` / ``StandardMultiPrototypeReplayHead``
+  - mmdet/models/roi_heads/standard_roi_replay_head.py:375
+* ``registry``                     - registers the above into mmengine / mmdet
+  when those packages are importable.
+
+There is no CPU fallback: importing ``_lib`` raises if the CUDA library has not
+been built (``python -c "import __graft_entry__ as g; g.build()"``).
+"""
+__version__ = "0.1.0"
+
+from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
+from .covariance import CovarianceHooks, BRNullSpaceCovariance  # noqa: F401
+from .optim import SGDNSCL  # noqa: F401
+from .prototypes import MultiPrototypeReplay, StandardMultiPrototypeReplayHead  # noqa: F401
+from . import registry  # noqa: F401

@@ -1,0 +1,108 @@
+"""ctypes binding of ``lib/libnsgp_repre_b200.so`` (C ABI: include/nsgp_repre_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnsgp_repre_b200.so")
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        "nsgp_repre_b200: %s is missing - build it with "
+        "`make -C nsgp-repre_b200/csrc` (or __graft_entry__.build()). "
+        "There is no CPU fallback." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+c_void_p, c_int, c_size_t, c_float, c_double = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
+
+
+class CovLayout(C.Structure):
+    _fields_ = [("d", c_int), ("d_int", c_int), ("taps", c_int), ("ld", c_int),
+                ("acc_bytes", c_size_t), ("workspace_bytes", c_size_t)]
+
+
+class SgdTensor(C.Structure):
+    _fields_ = [("w", c_void_p), ("g", c_void_p), ("buf", c_void_p),
+                ("numel", C.c_longlong), ("first_step", c_int), ("layer", c_int)]
+
+
+class ProjLayer(C.Structure):
+    _fields_ = [("cout", c_int), ("d", c_int), ("pt_hi", c_void_p), ("pt_lo", c_void_p),
+                ("u_hi", c_void_p), ("u_lo", c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol of include/nsgp_repre_b200.h
+SIGNATURES = {
+    "nsgp_abi_version": (c_int, []),
+    "nsgp_last_error": (C.c_char_p, []),
+    "nsgp_launch_count": (C.c_ulonglong, []),
+    "nsgp_set_engine": (c_int, [c_int]),
+    "nsgp_get_engine": (c_int, []),
+    "nsgp_cov_conv2d_layout": (c_int, [c_int] * 9 + [C.POINTER(CovLayout)]),
+    "nsgp_cov_linear_layout": (c_int, [c_int, C.POINTER(CovLayout)]),
+    "nsgp_cov_conv2d_accumulate": (c_int, [c_void_p] + [c_int] * 10 +
+                                   [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nsgp_cov_linear_accumulate": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]),
+    "nsgp_cov_finalize": (c_int, [c_void_p, C.POINTER(CovLayout), c_void_p, c_int, c_void_p]),
+    "nsgp_projector_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "nsgp_sgd_step_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nsgp_sgd_nscl_step": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
+                                   c_double, c_double, c_double, c_double, c_int,
+                                   c_void_p, c_size_t, c_void_p]),
+    "repre_class_index": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "repre_segment_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p]),
+    "repre_segment_var": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p]),
+    "repre_cosine_count_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "repre_cosine_count": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    C.c_uint64, c_void_p, c_void_p]),
+    "repre_kmeans_assign_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "repre_kmeans_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = ABI mismatch, fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.nsgp_abi_version() != 1:
+    raise ImportError("nsgp_repre_b200: ABI version mismatch")
+
+
+class NsgpError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.nsgp_last_error().decode("utf-8", "replace")
+        raise NsgpError("%s failed (rc=%d): %s" % (what, rc, msg))
+
+
+def ptr(t) -> int:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device=None) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise NsgpError("%s must live on a CUDA device (there is no CPU fallback)" % name)
+
+
+def launch_count() -> int:
+    return int(lib.nsgp_launch_count())

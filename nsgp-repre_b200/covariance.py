@@ -1,0 +1,237 @@
+"""Per-layer input covariance for NSGP - drop-in for the covariance part of
+``BRNullSpaceRunner`` (mmdet/engine/runner/nsrunner_roi_replay.py).
+
+Mirrored surface (same names, argument meaning and error behaviour):
+
+* ``compute_cov(module, fea_in, fea_out)`` - forward hook (:876-916)
+* ``update_cov(fea_in, k)``                - rows (N,d) -> running X^T X (:923-934)
+* ``fea_in``                               - dict "<module path>.weight" -> (d,d)
+* ``cal_fea_in`` tail                      - all-reduce over ranks (:746-749), merge
+  with the previous task's covariance.pth (:750-753), ``torch.save`` (:757)
+
+What changed underneath: the hook makes ONE C-ABI call per layer that fuses the
+batch mean (:908), the im2col (never materialised), X^T X (:930) and the running
+add (:931-934) into the layer's persistent fp32 accumulator in HBM.  The
+accumulator lives in an internal (tap-major, upper block-triangular) layout;
+``fea_in`` expands it to the reference layout on access.
+"""
+from __future__ import annotations
+
+import re
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, ptr, CovLayout
+
+
+class _LayerAcc:
+    __slots__ = ("layout", "acc", "calls")
+
+    def __init__(self, layout, acc):
+        self.layout = layout
+        self.acc = acc
+        self.calls = 0
+
+
+class CovarianceHooks:
+    """Accumulates the un-centred input covariance of every hooked Conv2d/Linear.
+
+    Args:
+        model: the detector (unwrapped module); hooks see ``model.named_modules()``.
+        ignore_keys: regex prefixes matched with ``re.match`` like :722-726; the
+            reference appends ``roi_head.bbox_head.fc_cls|fc_reg|teacher`` (:354).
+    """
+
+    DEFAULT_IGNORE = ["roi_head.bbox_head.fc_cls", "roi_head.bbox_head.fc_reg", "teacher"]
+
+    def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True):
+        self.model = model
+        self.ignore_keys = list(ignore_keys) + (self.DEFAULT_IGNORE if add_default_ignores else [])
+        self._names = {}
+        self._layers: "OrderedDict[str, _LayerAcc]" = OrderedDict()
+        self._workspace = None
+        self._handles = []
+        self._merged = {}           # key -> dense tensor added at finalize (old tasks)
+
+    # ------------------------------------------------------------------ hooks
+    def check_if_ignore(self, n: str) -> bool:
+        return any(re.match(k, n) for k in self.ignore_keys)
+
+    def hooked_modules(self):
+        """Same selection as :731-732: every module with a ``weight`` attribute
+        whose path is not ignored (BatchNorm hooks fire and do nothing)."""
+        return [(n, m) for n, m in self.model.named_modules()
+                if hasattr(m, "weight") and not self.check_if_ignore(n)]
+
+    def register(self):
+        self._names = {m: n for n, m in self.model.named_modules()}
+        for _, m in self.hooked_modules():
+            self._handles.append(m.register_forward_hook(self.compute_cov))
+        return self
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _ws(self, nbytes: int, device) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or \
+                self._workspace.device != device:
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self._workspace
+
+    def _layer(self, key: str, layout: CovLayout, device) -> _LayerAcc:
+        la = self._layers.get(key)
+        if la is None:
+            acc = torch.zeros(layout.acc_bytes // 4, dtype=torch.float32, device=device)
+            la = _LayerAcc(layout, acc)
+            self._layers[key] = la
+        elif la.layout.d != layout.d or la.layout.d_int != layout.d_int:
+            raise _lib.NsgpError("covariance dimension of %s changed (%d -> %d)" %
+                                 (key, la.layout.d, layout.d))
+        return la
+
+    @torch.no_grad()
+    def compute_cov(self, module, fea_in, fea_out):
+        """Forward hook, same signature and return value (None) as :876-916."""
+        if not self._names:
+            self._names = {m: n for n, m in self.model.named_modules()}
+        name = self._names[module] + ".weight"
+        x = fea_in[0]
+        if isinstance(module, nn.Linear):
+            self._accumulate_linear(x, name)
+        elif isinstance(module, nn.Conv2d):
+            self._accumulate_conv(x, name, module.kernel_size, module.stride, module.padding)
+        return None
+
+    def _accumulate_conv(self, x, key, kernel_size, stride, padding):
+        _lib.require_cuda(x, "layer input")
+        if x.dim() != 4:
+            raise _lib.NsgpError("Conv2d input must be (B,C,H,W)")
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        B, Cin, H, W = x.shape
+        kh, kw = kernel_size
+        sh, sw = stride
+        ph, pw = padding
+        layout = CovLayout()
+        check(lib.nsgp_cov_conv2d_layout(Cin, H, W, kh, kw, sh, sw, ph, pw, layout),
+              "nsgp_cov_conv2d_layout")
+        la = self._layer(key, layout, x.device)
+        ws = self._ws(layout.workspace_bytes, x.device)
+        check(lib.nsgp_cov_conv2d_accumulate(
+            ptr(x), B, Cin, H, W, kh, kw, sh, sw, ph, pw, ptr(la.acc), ptr(ws), ws.numel(),
+            _lib.current_stream(x.device)), "nsgp_cov_conv2d_accumulate")
+        la.calls += 1
+
+    def _accumulate_linear(self, x, key):
+        _lib.require_cuda(x, "layer input")
+        x = x.detach()
+        d = x.shape[-1]
+        if x.dim() != 2:
+            # torch.mean(x, 0, True) on a (B, ..., d) input keeps the inner dims as rows
+            # (:901); the Gram of those rows is the reference result.
+            rows = x.float().mean(dim=0).reshape(-1, d)
+            return self.update_cov(rows, key)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        layout = CovLayout()
+        check(lib.nsgp_cov_linear_layout(d, layout), "nsgp_cov_linear_layout")
+        la = self._layer(key, layout, x.device)
+        ws = self._ws(layout.workspace_bytes, x.device)
+        check(lib.nsgp_cov_linear_accumulate(ptr(x), x.shape[0], d, ptr(la.acc), ptr(ws),
+                                             ws.numel(), _lib.current_stream(x.device)),
+              "nsgp_cov_linear_accumulate")
+        la.calls += 1
+
+    @torch.no_grad()
+    def update_cov(self, fea_in: torch.Tensor, k: str):
+        """Reference signature (:923): rows X (N,d) -> fea_in[k] (+)= X^T X.
+        Routed through the conv entry point as a 1x1 "image" (d, 1, N)."""
+        _lib.require_cuda(fea_in, "fea_in")
+        xt = fea_in.detach().float().t().contiguous()          # (d, N), K-major
+        d, N = xt.shape
+        self._accumulate_conv(xt.view(1, d, 1, N), k, (1, 1), (1, 1), (0, 0))
+
+    # ---------------------------------------------------------------- results
+    def _finalize(self, key: str) -> torch.Tensor:
+        la = self._layers[key]
+        d = la.layout.d
+        out = torch.empty(d, d, dtype=torch.float32, device=la.acc.device)
+        check(lib.nsgp_cov_finalize(ptr(la.acc), la.layout, ptr(out), 0,
+                                    _lib.current_stream(out.device)), "nsgp_cov_finalize")
+        if key in self._merged:
+            out += self._merged[key].to(out.device)
+        return out
+
+    @property
+    def fea_in(self) -> dict:
+        """dict "<module path>.weight" -> (d,d) fp32, reference layout (:931-934)."""
+        return {k: self._finalize(k) for k in self._layers}
+
+    def keys(self):
+        return list(self._layers.keys())
+
+    def reset(self):
+        for la in self._layers.values():
+            la.acc.zero_()
+            la.calls = 0
+        self._merged = {}
+
+    # ------------------------------------------------- cal_fea_in tail (:746-757)
+    def all_reduce(self, group=None):
+        """SUM over ranks of every accumulator, as ``all_reduce_dict(self.fea_in)``
+        (:746-749) - one flat fp32 buffer, one NCCL all-reduce over NVLink."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or \
+                dist.get_world_size(group) == 1 or not self._layers:
+            return
+        accs = [la.acc for la in self._layers.values()]
+        flat = torch.cat([a.view(-1) for a in accs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for a in accs:
+            a.copy_(flat[off:off + a.numel()])
+            off += a.numel()
+
+    def merge_previous(self, old_fea_in: dict):
+        """``fea_in[k] + old_fea_in[k]`` for task_id != 1 (:750-753); keys of the
+        current run that are ignored are dropped there, missing old keys raise
+        KeyError like the reference's dict lookup."""
+        for k in self._layers:
+            self._merged[k] = old_fea_in[k] if k not in self._merged else \
+                self._merged[k] + old_fea_in[k]
+
+    def save(self, path: str):
+        """``torch.save(self.fea_in, fea_in_save_path)`` (:757), same pickle format."""
+        torch.save(self.fea_in, path)
+
+    @torch.no_grad()
+    def cal_fea_in(self, batches, forward=None, save_path=None, previous=None, group=None):
+        """The accumulation loop + tail of ``cal_fea_in`` (:731-763) on an iterable
+        of already pre-processed input batches.  ``forward(model, batch)``
+        defaults to ``model(batch)`` (the reference calls
+        ``model(inputs, data_samples, mode='nullspace')``)."""
+        self.register()
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            for batch in batches:
+                (forward or (lambda m, b: m(b)))(self.model, batch)
+        finally:
+            self.remove()
+            self.model.train(was_training)
+        self.all_reduce(group)
+        if previous is not None:
+            self.merge_previous(previous)
+        out = self.fea_in
+        if save_path is not None:
+            torch.save(out, save_path)
+        return out
+
+
+BRNullSpaceCovariance = CovarianceHooks

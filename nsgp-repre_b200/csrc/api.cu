@@ -1,0 +1,339 @@
+// C ABI (include/nsgp_repre_b200.h) over the kernels of this directory.
+#include <cstdarg>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nsgp_repre_b200.h"
+#include "common.cuh"
+#include "geometry.h"
+#include "repre.h"
+#include "sgd.h"
+
+namespace nsgp {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+int g_engine = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int contraction(const ContractionArgs& a, cudaStream_t stream) {
+  return g_engine == 1 ? contraction_simt(a, stream) : contraction_tc(a, stream);
+}
+
+static int pick_splits(int tiles, int nkb) {
+  // enough CTAs for ~3 waves over 148 SMs, at least 8 K-blocks per CTA
+  int want = ceil_div(148 * 3, tiles);
+  int cap = nkb / 8;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  return want < 1 ? 1 : want;
+}
+
+static inline char* align_up(char* p, size_t a) {
+  return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + a - 1) / a * a);
+}
+
+}  // namespace nsgp
+
+using namespace nsgp;
+
+extern "C" {
+
+int nsgp_abi_version(void) { return NSGP_ABI_VERSION; }
+const char* nsgp_last_error(void) { return g_err; }
+unsigned long long nsgp_launch_count(void) { return g_launches; }
+int nsgp_set_engine(int engine) {
+  int prev = g_engine;
+  if (engine == 0 || engine == 1) g_engine = engine;
+  return prev;
+}
+int nsgp_get_engine(void) { return g_engine; }
+
+// ---------------------------------------------------------------- covariance
+int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                           nsgp_cov_layout_t* out) {
+  NSGP_REQUIRE(out != nullptr, "layout: out is null");
+  ConvGeom g;
+  NSGP_REQUIRE(make_conv_geom(C, H, W, kh, kw, sh, sw, ph, pw, &g) == 0,
+               "layout: invalid conv geometry C=%d H=%d W=%d k=%dx%d s=%dx%d p=%dx%d", C, H, W,
+               kh, kw, sh, sw, ph, pw);
+  out->d = g.d;
+  out->d_int = g.d_int;
+  out->taps = g.T;
+  out->ld = (int)round_up(g.d_int, 4);
+  out->acc_bytes = (size_t)out->ld * g.d_int * sizeof(float);
+  out->workspace_bytes = stage_bytes(g) + 1024;
+  return 0;
+}
+
+int nsgp_cov_linear_layout(int d, nsgp_cov_layout_t* out) {
+  NSGP_REQUIRE(out != nullptr && d > 0, "linear layout: bad arguments");
+  out->d = d;
+  out->d_int = d;
+  out->taps = 1;
+  out->ld = (int)round_up(d, 4);
+  out->acc_bytes = (size_t)out->ld * d * sizeof(float);
+  out->workspace_bytes = (size_t)round_up(d, 4) * sizeof(float) + 256;
+  return 0;
+}
+
+int nsgp_cov_conv2d_accumulate(const float* x, int B, int C, int H, int W, int kh, int kw,
+                               int sh, int sw, int ph, int pw, float* acc, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(x && acc && workspace, "cov_conv2d: null pointer");
+  NSGP_REQUIRE(B > 0, "cov_conv2d: empty batch");
+  ConvGeom g;
+  NSGP_REQUIRE(make_conv_geom(C, H, W, kh, kw, sh, sw, ph, pw, &g) == 0,
+               "cov_conv2d: invalid conv geometry");
+  char* ws = align_up((char*)workspace, 1024);
+  NSGP_REQUIRE(ws + stage_bytes(g) <= (char*)workspace + workspace_bytes,
+               "cov_conv2d: workspace too small (%zu < %zu)", workspace_bytes,
+               stage_bytes(g) + 1024);
+  float* stage = reinterpret_cast<float*>(ws);
+  int rc = launch_stage_conv(x, stage, g, B, stream);
+  if (rc) return rc;
+  ContractionArgs a{};
+  a.A = conv_operand(g, stage);
+  a.B = a.A;
+  a.out = acc;
+  a.ld = (int)round_up(g.d_int, 4);
+  a.n_cols = a.A.rows;
+  a.alpha = 1.f;
+  a.epi = kEpiGramAtomic;
+  int tiles_1d = ceil_div(a.A.rows, 128);
+  a.splits = pick_splits(tiles_1d * (tiles_1d + 1) / 2, k_blocks(a.A));
+  return contraction(a, stream);
+}
+
+int nsgp_cov_linear_accumulate(const float* x, int R, int d, float* acc, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(x && acc && workspace, "cov_linear: null pointer");
+  NSGP_REQUIRE(R > 0 && d > 0, "cov_linear: empty input");
+  char* ws = align_up((char*)workspace, 256);
+  NSGP_REQUIRE(ws + (size_t)d * 4 <= (char*)workspace + workspace_bytes,
+               "cov_linear: workspace too small");
+  return launch_linear_cov(x, R, d, acc, (int)round_up(d, 4), reinterpret_cast<float*>(ws),
+                           stream);
+}
+
+int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* L, float* cov_out,
+                      int accumulate, void* stream_) {
+  NSGP_REQUIRE(acc && L && cov_out, "cov_finalize: null pointer");
+  NSGP_REQUIRE(L->taps >= 1 && L->d % L->taps == 0, "cov_finalize: bad layout");
+  return launch_cov_finalize(acc, L->ld, cov_out, L->d / L->taps, L->taps, accumulate,
+                             (cudaStream_t)stream_);
+}
+
+// ---------------------------------------------------------------- projection
+int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, void* stream_) {
+  NSGP_REQUIRE(P && pt_hi && pt_lo && d > 0, "projector_prepare: bad arguments");
+  return launch_transpose_split(P, pt_hi, pt_lo, d, d, (cudaStream_t)stream_);
+}
+
+size_t nsgp_sgd_step_workspace_bytes(int n_tensors, int n_layers) {
+  (void)n_layers;
+  return (size_t)n_tensors * sizeof(SgdTensorDev) + (size_t)(n_tensors + 1) * sizeof(int) + 512;
+}
+
+int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                       const nsgp_proj_layer_t* layers, int n_layers, double lr,
+                       double momentum, double dampening, double weight_decay, int nesterov,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(n_tensors >= 0 && n_layers >= 0, "sgd_step: negative counts");
+  if (n_tensors == 0) return 0;
+  NSGP_REQUIRE(tensors && workspace, "sgd_step: null pointer");
+  NSGP_REQUIRE(workspace_bytes >= nsgp_sgd_step_workspace_bytes(n_tensors, n_layers),
+               "sgd_step: workspace too small");
+  std::vector<SgdTensorDev> host(n_tensors);
+  std::vector<int> chunk_start(n_tensors + 1);
+  int total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    const nsgp_sgd_tensor_t& t = tensors[i];
+    NSGP_REQUIRE(t.w && t.g, "sgd_step: tensor %d has a null weight/grad pointer", i);
+    NSGP_REQUIRE(momentum == 0.0 || t.buf, "sgd_step: tensor %d needs a momentum buffer", i);
+    SgdTensorDev d{};
+    d.w = t.w; d.g = t.g; d.buf = t.buf; d.numel = t.numel; d.first = t.first_step;
+    if (t.layer >= 0) {
+      NSGP_REQUIRE(t.layer < n_layers && layers, "sgd_step: tensor %d: bad layer index", i);
+      const nsgp_proj_layer_t& L = layers[t.layer];
+      NSGP_REQUIRE((long long)L.cout * L.d == t.numel,
+                   "sgd_step: tensor %d: cout*d != numel", i);
+      d.u_hi = L.u_hi; d.u_lo = L.u_lo;
+    }
+    host[i] = d;
+    chunk_start[i] = total;
+    total += sgd_chunks(t.numel);
+  }
+  chunk_start[n_tensors] = total;
+  char* ws = align_up((char*)workspace, 256);
+  SgdTensorDev* dev_t = reinterpret_cast<SgdTensorDev*>(ws);
+  int* dev_c = reinterpret_cast<int*>(ws + (size_t)n_tensors * sizeof(SgdTensorDev));
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_t, host.data(), host.size() * sizeof(SgdTensorDev),
+                                  cudaMemcpyHostToDevice, stream));
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_c, chunk_start.data(), chunk_start.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, stream));
+  int rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, total, (float)lr, (float)momentum,
+                               (float)(1.0 - dampening), (float)weight_decay, nesterov, stream);
+  if (rc) return rc;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (tensors[i].layer < 0) continue;
+    const nsgp_proj_layer_t& L = layers[tensors[i].layer];
+    ContractionArgs a{};
+    a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, L.d);
+    a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, L.d);
+    a.out = tensors[i].w;
+    a.ld = L.d;
+    a.n_cols = L.d;
+    a.alpha = 1.f;
+    a.epi = kEpiGemmRmw;
+    a.splits = 1;
+    rc = contraction(a, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- RePRE
+int repre_class_index(const int64_t* labels, int M, int C, int32_t* counts, int32_t* offsets,
+                      int32_t* rows, void* stream_) {
+  NSGP_REQUIRE(labels && counts && offsets && rows, "class_index: null pointer");
+  NSGP_REQUIRE(M >= 0 && C > 0, "class_index: bad sizes");
+  return launch_class_index((const long long*)labels, M, C, counts, offsets, rows,
+                            (cudaStream_t)stream_);
+}
+
+int repre_segment_mean(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
+                       int n_segments, int max_seg_rows, float* out, void* stream_) {
+  NSGP_REQUIRE(F && seg_offsets && rows && out, "segment_mean: null pointer");
+  return launch_segment_mean(F, D, seg_offsets, rows, n_segments, max_seg_rows, nullptr, 0,
+                             out, (cudaStream_t)stream_);
+}
+
+int repre_segment_var(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
+                      int n_segments, int max_seg_rows, const float* mu, float* out,
+                      void* stream_) {
+  NSGP_REQUIRE(F && seg_offsets && rows && out && mu, "segment_var: null pointer");
+  return launch_segment_mean(F, D, seg_offsets, rows, n_segments, max_seg_rows, mu, 1, out,
+                             (cudaStream_t)stream_);
+}
+
+size_t repre_cosine_count_workspace_bytes(int n, int D) {
+  size_t n8 = (size_t)round_up(n, 8);
+  return 2 * n8 * (size_t)D * 4 + n8 * (size_t)round_up(n, 4) * 4 + 2048;
+}
+
+int repre_cosine_count(const float* F, int D, const int32_t* rows, int n, float thresh,
+                       uint8_t* mask, int32_t* counts, float* sim_out, void* workspace,
+                       size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(F && rows && mask && counts && workspace, "cosine_count: null pointer");
+  NSGP_REQUIRE(n >= 0 && D > 0 && D % 4 == 0, "cosine_count: bad sizes");
+  if (n == 0) return 0;
+  NSGP_REQUIRE(workspace_bytes >= repre_cosine_count_workspace_bytes(n, D),
+               "cosine_count: workspace too small");
+  size_t n8 = (size_t)round_up(n, 8);
+  char* ws = align_up((char*)workspace, 1024);
+  float* hi = reinterpret_cast<float*>(ws);
+  float* lo = hi + n8 * D;
+  float* S = lo + n8 * D;
+  int ld = (int)round_up(n, 4);
+  int rc = launch_normalize_split(F, D, rows, n, hi, lo, stream);
+  if (rc) return rc;
+  NSGP_CHECK_CUDA(cudaMemsetAsync(S, 0, (size_t)n * ld * 4, stream));
+  ContractionArgs a{};
+  a.A = matrix_operand(hi, lo, n, D, D);
+  a.B = a.A;
+  a.out = S;
+  a.ld = ld;
+  a.n_cols = n;
+  a.alpha = 1.f;
+  a.epi = kEpiGramAtomic;
+  int t1 = ceil_div(n, 128);
+  a.splits = pick_splits(t1 * (t1 + 1) / 2, k_blocks(a.A));
+  rc = contraction(a, stream);
+  if (rc) return rc;
+  return launch_threshold_count(S, n, ld, thresh, mask, counts, sim_out, stream);
+}
+
+int repre_replay_gather(const float* protos, const float* sigma, const int64_t* idx, int P,
+                        int D, uint64_t seed, float* out, void* stream_) {
+  NSGP_REQUIRE(protos && out, "replay_gather: null pointer");
+  return launch_replay_gather(protos, sigma, (const long long*)idx, P, D, seed, out,
+                              (cudaStream_t)stream_);
+}
+
+size_t repre_kmeans_assign_workspace_bytes(int n, int k, int D) {
+  size_t n8 = (size_t)round_up(n, 8), k8 = (size_t)round_up(k, 8);
+  return 2 * (n8 + k8) * (size_t)D * 4 + n8 * (size_t)round_up(k, 4) * 4 + k8 * 4 + 4096;
+}
+
+int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int k,
+                        int64_t* labels, void* workspace, size_t workspace_bytes,
+                        void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(X && centres && labels && workspace, "kmeans_assign: null pointer");
+  NSGP_REQUIRE(n >= 0 && k > 0 && D > 0 && D % 4 == 0, "kmeans_assign: bad sizes");
+  if (n == 0) return 0;
+  NSGP_REQUIRE(workspace_bytes >= repre_kmeans_assign_workspace_bytes(n, k, D),
+               "kmeans_assign: workspace too small");
+  size_t n8 = (size_t)round_up(n, 8), k8 = (size_t)round_up(k, 8);
+  char* ws = align_up((char*)workspace, 1024);
+  float* xh = reinterpret_cast<float*>(ws);
+  float* xl = xh + n8 * D;
+  float* ch = xl + n8 * D;
+  float* cl = ch + k8 * D;
+  float* dots = cl + k8 * D;
+  int ld = (int)round_up(k, 4);
+  float* cn = dots + n8 * ld;
+  int rc = launch_split(X, xh, xl, (long long)n * D, stream);
+  if (rc) return rc;
+  rc = launch_split(centres, ch, cl, (long long)k * D, stream);
+  if (rc) return rc;
+  rc = launch_row_sqnorm(centres, k, D, D, cn, stream);
+  if (rc) return rc;
+  NSGP_CHECK_CUDA(cudaMemsetAsync(dots, 0, (size_t)n * ld * 4, stream));
+  ContractionArgs a{};
+  a.A = matrix_operand(xh, xl, n, D, D);
+  a.B = matrix_operand(ch, cl, k, D, D);
+  a.out = dots;
+  a.ld = ld;
+  a.n_cols = k;
+  a.alpha = 1.f;
+  a.epi = kEpiGemmRmw;
+  a.splits = 1;
+  rc = contraction(a, stream);
+  if (rc) return rc;
+  return launch_kmeans_argmin(dots, n, k, ld, cn, (long long*)labels, stream);
+}
+
+int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream_) {
+  NSGP_REQUIRE(src && hi && lo, "split: null pointer");
+  return launch_split(src, hi, lo, (long long)n, (cudaStream_t)stream_);
+}
+
+int nsgp_debug_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
+                       const float* b_lo, int M, int N, int K, float* C, int ldc,
+                       void* stream_) {
+  NSGP_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "debug_gemm: null pointer");
+  ContractionArgs a{};
+  a.A = matrix_operand(a_hi, a_lo, M, K, K);
+  a.B = matrix_operand(b_hi, b_lo, N, K, K);
+  a.out = C;
+  a.ld = ldc;
+  a.n_cols = N;
+  a.alpha = 1.f;
+  a.epi = kEpiGemmRmw;
+  a.splits = 1;
+  return contraction(a, (cudaStream_t)stream_);
+}
+
+}  // extern "C"

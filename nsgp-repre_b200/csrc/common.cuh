@@ -1,0 +1,105 @@
+// Shared declarations for the NSGP-RePRE B200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace nsgp {
+
+// ---- error handling / launch accounting -----------------------------------
+void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;   // kernels launched by this library
+
+#define NSGP_CHECK_CUDA(expr)                                                     \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      nsgp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                      __FILE__, __LINE__);                                        \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+#define NSGP_REQUIRE(cond, ...)                                                   \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      nsgp::set_error(__VA_ARGS__);                                               \
+      return -1;                                                                  \
+    }                                                                             \
+  } while (0)
+
+#define NSGP_LAUNCHED()                                                           \
+  do {                                                                            \
+    ++nsgp::g_launches;                                                           \
+    NSGP_CHECK_CUDA(cudaGetLastError());                                          \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---- 3xTF32 split ------------------------------------------------------------
+// hi = rna_tf32(x); lo = rna_tf32(x - hi).  x - hi is exact in fp32, so hi + lo
+// carries ~21 mantissa bits and both words have their low 13 bits clear, i.e. the
+// tensor core's tf32 truncation of the smem operand is a no-op.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
+
+// ---- K-major virtual operand ---------------------------------------------------
+// Both engines (SIMT bring-up and tcgen05) consume operands described this way.
+// A virtual matrix of `rows` = T * Cs rows and K = Kh * Kw columns is backed by
+// staged planes  stage[hl][plane][Cs][Hs][Ws]  (hl: 0 = tf32 hi part, 1 = lo part).
+// Row r = t * Cs + c (tap-major).  Column k = (krow, kx):
+//     element = stage[hl][tap_plane[t]][c][krow + tap_yoff[t]][kx + tap_xoff[t]]
+//               if kx + tap_xoff[t] < tap_ext[t] else 0
+// Plain row-major matrices are the T = 1, Kh = 1 special case.
+constexpr int kMaxTaps = 9;
+
+struct Operand {
+  const float* base;       // stage base (hi part of plane 0)
+  long long hl_stride;     // elements between the hi and the lo copy
+  long long plane_stride;  // elements between planes (= Cs*Hs*Ws)
+  int T, Cs;               // taps, rows per tap
+  int Hs, Ws;              // plane height / row pitch (elements, Ws % 4 == 0)
+  int Kh, Kw;              // K space: Kh rows of Kw valid columns
+  int rows;                // valid virtual rows (<= T*Cs)
+  int tap_plane[kMaxTaps];
+  int tap_yoff[kMaxTaps];
+  int tap_xoff[kMaxTaps];
+  int tap_ext[kMaxTaps];
+};
+
+// Epilogue of the contraction engines.
+enum EpiMode : int {
+  kEpiGramAtomic = 0,  // upper block-triangle of A*A^T, red.add into out (split-K ok)
+  kEpiGemmRmw = 1,     // full A*B^T, out[m][n] += alpha * acc (exclusive tiles, no split-K)
+};
+
+struct ContractionArgs {
+  Operand A, B;
+  float* out;       // (A.rows x ld)
+  int ld;           // leading dimension of out (elements)
+  int n_cols;       // valid output columns (= B.rows)
+  float alpha;
+  int epi;          // EpiMode
+  int splits;       // split-K factor (Gram only)
+};
+
+// engines
+int contraction_simt(const ContractionArgs& a, cudaStream_t stream);
+int contraction_tc(const ContractionArgs& a, cudaStream_t stream);      // tcgen05/TMA
+int contraction(const ContractionArgs& a, cudaStream_t stream);         // dispatch on g_engine
+extern int g_engine;   // 0 = tcgen05 (product), 1 = SIMT (bring-up / cross-check)
+
+// number of 32-wide K blocks of an operand
+static inline int k_blocks(const Operand& o) { return o.Kh * ceil_div(o.Kw, 32); }
+
+}  // namespace nsgp

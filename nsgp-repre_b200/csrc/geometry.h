@@ -1,0 +1,125 @@
+// Host-side geometry of one hooked Conv2d input and how it is staged in HBM.
+// See DESIGN.md "Data layout" for the derivation.
+#pragma once
+#include "common.cuh"
+
+namespace nsgp {
+
+enum StageMode : int {
+  kModeImplicit = 0,  // phase planes with zero halo; taps are shifted TMA windows
+  kModeFlat = 1,      // 1x1, pad 0: K = Hout*Wout flattened, no halo, no waste
+  kModeExplicit = 2,  // explicit im2col rows in reference order (fallback)
+};
+
+struct ConvGeom {
+  int C, H, W, kh, kw, sh, sw, ph, pw;
+  int Hout, Wout;
+  int mode;
+  int T;        // taps that index Gram rows (implicit: kh*kw, else 1)
+  int Cs;       // staged rows per tap (implicit/flat: C; explicit: round_up(d, 8))
+  int nphase;   // implicit: sh*sw, else 1
+  int Hs, Ws;   // staged plane height / pitch
+  int Ht, Wl;   // top / left halo in plane units
+  int d;        // true covariance dimension C*kh*kw
+  int d_int;    // internal accumulator dimension (T*Cs)
+};
+
+static inline int floor_div(int a, int b) {
+  int q = a / b, r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+static inline int pos_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+// returns 0 on success
+static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                                 int pw, ConvGeom* out) {
+  ConvGeom g{};
+  g.C = C; g.H = H; g.W = W; g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.ph = ph; g.pw = pw;
+  if (C <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || ph < 0 || pw < 0)
+    return -1;
+  g.Hout = (H + 2 * ph - kh) / sh + 1;
+  g.Wout = (W + 2 * pw - kw) / sw + 1;
+  if (g.Hout <= 0 || g.Wout <= 0) return -1;
+  g.d = C * kh * kw;
+  const bool one_by_one = (kh == 1 && kw == 1 && ph == 0 && pw == 0);
+  if (one_by_one && C % 8 == 0) {
+    g.mode = kModeFlat;
+    g.T = 1; g.Cs = C; g.nphase = 1;
+    g.Hs = 1; g.Ws = (int)round_up((long long)g.Hout * g.Wout, 4);
+    g.Ht = g.Wl = 0;
+  } else if (kh * kw <= kMaxTaps && C % 8 == 0) {
+    g.mode = kModeImplicit;
+    g.T = kh * kw; g.Cs = C; g.nphase = sh * sw;
+    g.Ht = ceil_div(ph, sh);
+    g.Wl = ceil_div(pw, sw);
+    int qy_max = floor_div(kh - 1 - ph, sh), qx_max = floor_div(kw - 1 - pw, sw);
+    g.Hs = g.Hout + qy_max + g.Ht;
+    g.Ws = (int)round_up(g.Wout + qx_max + g.Wl, 4);
+  } else {
+    g.mode = kModeExplicit;
+    g.T = 1; g.Cs = (int)round_up(g.d, 8); g.nphase = 1;
+    g.Hs = 1; g.Ws = (int)round_up((long long)g.Hout * g.Wout, 4);
+    g.Ht = g.Wl = 0;
+  }
+  g.d_int = g.T * g.Cs;
+  *out = g;
+  return 0;
+}
+
+static inline long long stage_hl_stride(const ConvGeom& g) {
+  return (long long)g.Cs * g.Hs * g.Ws * g.nphase;
+}
+static inline size_t stage_bytes(const ConvGeom& g) {
+  return (size_t)stage_hl_stride(g) * 2 * sizeof(float);
+}
+
+// Virtual K-major operand over the staged planes.
+static inline Operand conv_operand(const ConvGeom& g, const float* stage) {
+  Operand o{};
+  o.base = stage;
+  o.hl_stride = stage_hl_stride(g);
+  o.plane_stride = (long long)g.Cs * g.Hs * g.Ws;
+  o.T = g.T; o.Cs = g.Cs; o.Hs = g.Hs; o.Ws = g.Ws;
+  if (g.mode == kModeImplicit) {
+    o.Kh = g.Hout; o.Kw = g.Wout;
+    o.rows = g.T * g.Cs;
+    for (int i = 0; i < g.kh; ++i)
+      for (int j = 0; j < g.kw; ++j) {
+        int t = i * g.kw + j;
+        int ay = i - g.ph, ax = j - g.pw;
+        int qy = floor_div(ay, g.sh), py = pos_mod(ay, g.sh);
+        int qx = floor_div(ax, g.sw), px = pos_mod(ax, g.sw);
+        o.tap_plane[t] = py * g.sw + px;
+        o.tap_yoff[t] = qy + g.Ht;
+        o.tap_xoff[t] = qx + g.Wl;
+        o.tap_ext[t] = g.Wout + qx + g.Wl;   // columns past the last valid output read 0
+      }
+  } else {
+    o.Kh = 1; o.Kw = g.Hout * g.Wout;
+    o.rows = (g.mode == kModeExplicit) ? g.d : g.Cs;
+    o.tap_plane[0] = 0; o.tap_yoff[0] = 0; o.tap_xoff[0] = 0; o.tap_ext[0] = o.Kw;
+  }
+  return o;
+}
+
+// Plain row-major matrix (rows x K, pitch ld) with separate hi / lo copies.
+static inline Operand matrix_operand(const float* hi, const float* lo, int rows, int K, int ld) {
+  Operand o{};
+  o.base = hi;
+  o.hl_stride = (long long)(lo - hi);
+  o.plane_stride = 0;
+  o.T = 1; o.Cs = rows; o.Hs = 1; o.Ws = ld; o.Kh = 1; o.Kw = K; o.rows = rows;
+  o.tap_plane[0] = 0; o.tap_yoff[0] = 0; o.tap_xoff[0] = 0; o.tap_ext[0] = K;
+  return o;
+}
+
+int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B, cudaStream_t s);
+int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,
+                      cudaStream_t s);
+int launch_cov_finalize(const float* acc, int ld, float* out, int C, int T, int accumulate,
+                        cudaStream_t s);
+int launch_split(const float* src, float* hi, float* lo, long long n, cudaStream_t s);
+int launch_transpose_split(const float* src, float* hi, float* lo, int d, int ld_dst,
+                           cudaStream_t s);
+
+}  // namespace nsgp

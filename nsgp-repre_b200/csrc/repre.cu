@@ -1,0 +1,350 @@
+// RePRE prototype statistics: HBM-bound kernels (128-bit coalesced loads, warp
+// shuffles, shared-memory staging).  Reference: StandardMultiPrototypeReplayHead
+// (mmdet/models/roi_heads/standard_roi_replay_head.py:404-463).
+#include "common.cuh"
+#include "repre.h"
+
+namespace nsgp {
+
+// ---------------------------------------------------------------------------
+// Class index (stable): rows of class c in ascending row order, like the boolean
+// mask gather feats[cls_targets == c] of the reference (:412-413).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+class_count_kernel(const long long* __restrict__ labels, int M, int* __restrict__ counts) {
+  const int c = blockIdx.x;
+  int n = 0;
+  for (int i = threadIdx.x; i < M; i += 256) n += (labels[i] == c);
+  __shared__ int red[8];
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    counts[c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+class_compact_kernel(const long long* __restrict__ labels, int M, int C,
+                     const int* __restrict__ counts, int* __restrict__ offsets,
+                     int* __restrict__ rows) {
+  const int c = blockIdx.x;
+  __shared__ int warp_sums[8];
+  __shared__ int base;
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int k = 0; k < c; ++k) off += counts[k];
+    base = off;
+    offsets[c] = off;
+    if (c == C - 1) offsets[C] = off + counts[c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int start = 0; start < M; start += 256) {
+    int i = start + threadIdx.x;
+    bool hit = (i < M) && (labels[i] == c);
+    unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    int in_warp = __popc(ballot & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      int s = warp_sums[w];
+      if (w < warp) before += s;
+      total += s;
+    }
+    if (hit) rows[base + before + in_warp] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) base += total;
+    __syncthreads();
+  }
+}
+
+int launch_class_index(const long long* labels, int M, int C, int* counts, int* offsets,
+                       int* rows, cudaStream_t stream) {
+  class_count_kernel<<<C, 256, 0, stream>>>(labels, M, counts);
+  NSGP_LAUNCHED();
+  class_compact_kernel<<<C, 256, 0, stream>>>(labels, M, C, counts, offsets, rows);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Segmented mean over gathered rows: out[s][:] = mean(F[rows[off[s]:off[s+1]]]).
+// Used for the coarse class means (:412-414) and the masked fine-grained
+// prototype means (:443).  mode 1: mean of squared deviations from mu[s]
+// (extension: per-class diagonal covariance).
+// grid = (column chunks of 64 threads x float4, segments, row splits).
+// ---------------------------------------------------------------------------
+constexpr int kSegThreads = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(kSegThreads)
+segment_mean_kernel(const float* __restrict__ F, int D, const int* __restrict__ seg_off,
+                    const int* __restrict__ rows, const float* __restrict__ mu,
+                    float* __restrict__ out) {
+  const int s = blockIdx.y;
+  const int col = (blockIdx.x * kSegThreads + threadIdx.x) * 4;
+  if (col >= D) return;
+  const int beg = seg_off[s], end = seg_off[s + 1];
+  const int n = end - beg;
+  // row split: contiguous slices so that S == 1 keeps the plain sequential order
+  const int per = (n + gridDim.z - 1) / gridDim.z;
+  const int r0 = beg + blockIdx.z * per;
+  const int r1 = min(end, r0 + per);
+  float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE == 1) m4 = *reinterpret_cast<const float4*>(mu + (long long)s * D + col);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = __ldg(reinterpret_cast<const float4*>(F + (long long)rows[r + u] * D + col));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (MODE == 1) {
+        float a = v[u].x - m4.x, b = v[u].y - m4.y, c = v[u].z - m4.z, d = v[u].w - m4.w;
+        acc.x += a * a; acc.y += b * b; acc.z += c * c; acc.w += d * d;
+      } else {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(F + (long long)rows[r] * D + col));
+    if (MODE == 1) {
+      float a = v.x - m4.x, b = v.y - m4.y, c = v.z - m4.z, d = v.w - m4.w;
+      acc.x += a * a; acc.y += b * b; acc.z += c * c; acc.w += d * d;
+    } else {
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  const float fn = (float)n;   // n == 0 -> NaN like torch.mean of an empty slice
+  float* o = out + (long long)s * D + col;
+  if (gridDim.z == 1) {
+    *reinterpret_cast<float4*>(o) = make_float4(acc.x / fn, acc.y / fn, acc.z / fn, acc.w / fn);
+  } else if (r1 > r0 || (n == 0 && blockIdx.z == 0)) {
+    atomicAdd(o + 0, acc.x / fn);
+    atomicAdd(o + 1, acc.y / fn);
+    atomicAdd(o + 2, acc.z / fn);
+    atomicAdd(o + 3, acc.w / fn);
+  }
+}
+
+int launch_segment_mean(const float* F, int D, const int* seg_off, const int* rows, int nseg,
+                        int max_seg_rows, const float* mu, int mode, float* out,
+                        cudaStream_t stream) {
+  NSGP_REQUIRE(D % 4 == 0, "segment_mean: D must be a multiple of 4");
+  if (nseg == 0) return 0;
+  int chunks = ceil_div(D, kSegThreads * 4);
+  int splits = 1;
+  // fill the 148 SMs a few times over when there are few / long segments
+  while (splits < 32 && (long long)chunks * nseg * splits < 148 * 8 &&
+         max_seg_rows / (splits * 2) >= 16)
+    splits *= 2;
+  if (splits > 1)
+    NSGP_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)nseg * D * sizeof(float), stream));
+  dim3 grid(chunks, nseg, splits);
+  if (mode == 1)
+    segment_mean_kernel<1><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out);
+  else
+    segment_mean_kernel<0><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// L2-normalise gathered rows and split into tf32 hi/lo (:417): one CTA per row,
+// the row (<= 50 KB) is re-read from L1/L2 for the second pass.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+normalize_split_kernel(const float* __restrict__ F, int D, const int* __restrict__ rows,
+                       float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(F + (long long)rows[i] * D);
+  const int n4 = D >> 2;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < n4; j += 256) {
+    float4 v = __ldg(src + j);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float red[8];
+  __shared__ float norm_s;
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    norm_s = sqrtf(t);
+  }
+  __syncthreads();
+  const float nrm = norm_s;
+  float4* dh = reinterpret_cast<float4*>(hi + (long long)i * D);
+  float4* dl = reinterpret_cast<float4*>(lo + (long long)i * D);
+  for (int j = threadIdx.x; j < n4; j += 256) {
+    float4 v = __ldg(src + j), h, l;
+    tf32_split(v.x / nrm, h.x, l.x);
+    tf32_split(v.y / nrm, h.y, l.y);
+    tf32_split(v.z / nrm, h.z, l.z);
+    tf32_split(v.w / nrm, h.w, l.w);
+    dh[j] = h;
+    dl[j] = l;
+  }
+}
+
+int launch_normalize_split(const float* F, int D, const int* rows, int n, float* hi, float* lo,
+                           cudaStream_t stream) {
+  NSGP_REQUIRE(D % 4 == 0, "normalize: D must be a multiple of 4");
+  if (n == 0) return 0;
+  normalize_split_kernel<<<n, 256, 0, stream>>>(F, D, rows, hi, lo);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Threshold + neighbour count (:420-421) on the upper block-triangular Gram
+// produced by the contraction engine: one warp per row.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+threshold_count_kernel(const float* __restrict__ S, int n, int ld, float thresh,
+                       unsigned char* __restrict__ mask, int* __restrict__ counts,
+                       float* __restrict__ sim_out) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  int cnt = 0;
+  for (int j = lane; j < n; j += 32) {
+    float v = (i <= j) ? S[(long long)i * ld + j] : S[(long long)j * ld + i];
+    bool m = v >= thresh;
+    mask[(long long)i * n + j] = m ? 1 : 0;
+    if (sim_out) sim_out[(long long)i * n + j] = v;
+    cnt += m;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[i] = cnt;
+}
+
+int launch_threshold_count(const float* S, int n, int ld, float thresh, unsigned char* mask,
+                           int* counts, float* sim_out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  threshold_count_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(S, n, ld, thresh, mask, counts,
+                                                             sim_out);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Replay gather (:458-463 stages ALL prototypes every step; :58-59 a sampled
+// subset): out[p][:] = protos[idx[p]][:]  (+ sigma[idx[p]][:] * eps, extension).
+// eps is counter-based: Philox4x32-10 keyed by seed, counter (col/4, p, 0, 0),
+// Box-Muller on (u0,u1),(u2,u3) - identical to oracle.restated.gaussian_noise.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t x) {
+  return (float)(((double)x + 0.5) * (1.0 / 4294967296.0));
+}
+
+__global__ void __launch_bounds__(128)
+replay_gather_kernel(const float* __restrict__ protos, const float* __restrict__ sigma,
+                     const long long* __restrict__ idx, int D, unsigned long long seed,
+                     float* __restrict__ out) {
+  const int p = blockIdx.y;
+  const int q = blockIdx.x * 128 + threadIdx.x;   // float4 column group
+  if (q * 4 >= D) return;
+  const long long src = idx ? idx[p] : p;
+  float4 v = __ldg(reinterpret_cast<const float4*>(protos + src * D) + q);
+  if (sigma) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(sigma + src * D) + q);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)q, (uint32_t)p, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    float u0 = u01(r[0]), u1 = u01(r[1]), u2 = u01(r[2]), u3 = u01(r[3]);
+    const float two_pi = 6.283185307179586f;
+    float rad0 = sqrtf(-2.0f * logf(u0)), rad1 = sqrtf(-2.0f * logf(u2));
+    v.x += s.x * (rad0 * cosf(two_pi * u1));
+    v.y += s.y * (rad0 * sinf(two_pi * u1));
+    v.z += s.z * (rad1 * cosf(two_pi * u3));
+    v.w += s.w * (rad1 * sinf(two_pi * u3));
+  }
+  reinterpret_cast<float4*>(out + (long long)p * D)[q] = v;
+}
+
+int launch_replay_gather(const float* protos, const float* sigma, const long long* idx, int P,
+                         int D, unsigned long long seed, float* out, cudaStream_t stream) {
+  NSGP_REQUIRE(D % 4 == 0, "replay_gather: D must be a multiple of 4");
+  if (P == 0) return 0;
+  dim3 grid(ceil_div(D / 4, 128), P);
+  replay_gather_kernel<<<grid, 128, 0, stream>>>(protos, sigma, idx, D, seed, out);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// k-means assignment epilogue (extension, parity unpinned): given the dot
+// products X C^T from the contraction engine and the centre norms, label =
+// argmin_k (|c_k|^2 - 2 x.c_k), ties -> lowest k.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_sqnorm_kernel(const float* __restrict__ X, int D, int ld, float* __restrict__ out) {
+  const int i = blockIdx.x;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < D; j += 256) {
+    float v = X[(long long)i * ld + j];
+    ss += v * v;
+  }
+  __shared__ float red[8];
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_argmin_kernel(const float* __restrict__ dots, int n, int k, int ld,
+                     const float* __restrict__ cnorm, long long* __restrict__ labels) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float best = INFINITY;
+  int arg = 0;
+  for (int j = 0; j < k; ++j) {
+    float s = cnorm[j] - 2.0f * dots[(long long)i * ld + j];
+    if (s < best) { best = s; arg = j; }
+  }
+  labels[i] = arg;
+}
+
+int launch_row_sqnorm(const float* X, int n, int D, int ld, float* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  row_sqnorm_kernel<<<n, 256, 0, stream>>>(X, D, ld, out);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int launch_kmeans_argmin(const float* dots, int n, int k, int ld, const float* cnorm,
+                         long long* labels, cudaStream_t stream) {
+  if (n == 0) return 0;
+  kmeans_argmin_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(dots, n, k, ld, cnorm, labels);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+}  // namespace nsgp

@@ -1,0 +1,243 @@
+// Staging kernels: batch-mean + tf32 hi/lo split + layout for the contraction
+// engines.  All are HBM-bound element-wise/reduction kernels.
+#include "common.cuh"
+#include "geometry.h"
+
+namespace nsgp {
+
+// ---------------------------------------------------------------------------
+// Conv2d input -> staged planes (implicit-im2col or flat layout).
+// One thread per staged element (plane, c, r, xs); it averages the B input
+// values that land there (nsrunner_roi_replay.py:908 takes the batch mean BEFORE
+// unfolding), splits into tf32 hi/lo and writes both copies.  Halo / padding
+// elements are written as zeros, so the workspace needs no memset.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
+                  int B, long long hl_stride) {
+  const long long plane_elems = (long long)g.Cs * g.Hs * g.Ws;
+  const long long total = plane_elems * g.nphase;
+  const long long img = (long long)g.C * g.H * g.W;
+  const float inv_is_div = (float)B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int xs = (int)(idx % g.Ws);
+    long long rest = idx / g.Ws;
+    int r = (int)(rest % g.Hs);
+    rest /= g.Hs;
+    int c = (int)(rest % g.Cs);
+    int phase = (int)(rest / g.Cs);
+    int y, xx;
+    bool valid;
+    if (g.mode == kModeFlat) {
+      int k = xs;
+      valid = k < g.Hout * g.Wout;
+      int oy = k / g.Wout, ox = k - oy * g.Wout;
+      y = oy * g.sh;
+      xx = ox * g.sw;
+    } else {
+      int py = phase / g.sw, px = phase - py * g.sw;
+      y = g.sh * (r - g.Ht) + py;
+      xx = g.sw * (xs - g.Wl) + px;
+      valid = (y >= 0) && (y < g.H) && (xx >= 0) && (xx < g.W);
+    }
+    float v = 0.f;
+    if (valid) {
+      const float* p = x + ((long long)c * g.H + y) * g.W + xx;
+      float s = 0.f;
+#pragma unroll 4
+      for (int b = 0; b < B; ++b) s += __ldg(p + (long long)b * img);
+      v = s / inv_is_div;
+    }
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    stage[idx] = hi;
+    stage[idx + hl_stride] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Explicit im2col fallback (any kernel size / dilation-free conv whose channel
+// count does not fit the implicit path, e.g. the 7x7 stem with Cin = 3).
+// Rows are written directly in the reference's (Cin, kh, kw) order.
+// stage[hl][row][k],  row < d, k < Hout*Wout, pitch Ws.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stage,
+                           ConvGeom g, int B, long long hl_stride) {
+  const long long total = (long long)g.Cs * g.Ws;
+  const long long img = (long long)g.C * g.H * g.W;
+  const int taps = g.kh * g.kw;
+  const int d = g.C * taps;
+  const int K = g.Hout * g.Wout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(idx % g.Ws);
+    int row = (int)(idx / g.Ws);
+    float v = 0.f;
+    if (row < d && k < K) {
+      int c = row / taps, t = row - c * taps;
+      int i = t / g.kw, j = t - i * g.kw;
+      int oy = k / g.Wout, ox = k - oy * g.Wout;
+      int y = oy * g.sh - g.ph + i, xx = ox * g.sw - g.pw + j;
+      if (y >= 0 && y < g.H && xx >= 0 && xx < g.W) {
+        const float* p = x + ((long long)c * g.H + y) * g.W + xx;
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += __ldg(p + (long long)b * img);
+        v = s / (float)B;
+      }
+    }
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    stage[idx] = hi;
+    stage[idx + hl_stride] = lo;
+  }
+}
+
+int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
+                      cudaStream_t stream) {
+  long long total = (g.mode == kModeExplicit) ? (long long)g.Cs * g.Ws
+                                              : (long long)g.Cs * g.Hs * g.Ws * g.nphase;
+  long long hl = stage_hl_stride(g);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  if (g.mode == kModeExplicit)
+    stage_conv_explicit_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+  else
+    stage_conv_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Linear input (R, d) -> batch-mean row m (d)  [nsrunner_roi_replay.py:901],
+// then the rank-1 update acc += m m^T on the upper block-triangle.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_mean_kernel(const float* __restrict__ x, float* __restrict__ m, int R, int d) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += __ldg(x + (long long)r * d + j);
+  m[j] = s / (float)R;
+}
+
+__global__ void __launch_bounds__(256)
+rank1_update_kernel(const float* __restrict__ m, float* __restrict__ acc, int d, int ld) {
+  // 2D grid: blockIdx.y = row, threads over columns in float4 groups (ld % 4 == 0).
+  int i = blockIdx.y;
+  int j4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j4 >= d) return;
+  // only the upper block-triangle (128-row blocks) is maintained
+  if (j4 + 3 < (i / 128) * 128) return;
+  float mi = __ldg(m + i);
+  float4* p = reinterpret_cast<float4*>(acc + (long long)i * ld + j4);
+  float4 a = *p;
+  a.x += mi * __ldg(m + j4);
+  if (j4 + 1 < d) a.y += mi * __ldg(m + j4 + 1);
+  if (j4 + 2 < d) a.z += mi * __ldg(m + j4 + 2);
+  if (j4 + 3 < d) a.w += mi * __ldg(m + j4 + 3);
+  *p = a;
+}
+
+int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,
+                      cudaStream_t stream) {
+  row_mean_kernel<<<ceil_div(d, 256), 256, 0, stream>>>(x, mean_ws, R, d);
+  NSGP_LAUNCHED();
+  dim3 grid(ceil_div(ceil_div(d, 4), 256), d);
+  rank1_update_kernel<<<grid, 256, 0, stream>>>(mean_ws, acc, d, ld);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Finalize: tap-major upper block-triangle accumulator -> reference-order dense
+// symmetric covariance.  out[c*T+t][c'*T+t'] (+)= acc[min][max] with
+// row' = t*C + c.  32x32 smem-tiled so both sides stay coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cov_finalize_kernel(const float* __restrict__ acc, int ld, float* __restrict__ out, int C,
+                    int T, int d, int accumulate) {
+  // one thread per output element, output-coalesced; the accumulator read is a
+  // gather (stride T) that stays inside L2 - this runs once per task.
+  long long total = (long long)d * d;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int col = (int)(idx % d), row = (int)(idx / d);
+    int ri = (row % T) * C + row / T;   // reference (c,t) -> internal (t,c)
+    int ci = (col % T) * C + col / T;
+    int lo_i = ri < ci ? ri : ci, hi_i = ri < ci ? ci : ri;
+    float v = acc[(long long)lo_i * ld + hi_i];
+    if (accumulate) v += out[idx];
+    out[idx] = v;
+  }
+}
+
+int launch_cov_finalize(const float* acc, int ld, float* out, int C, int T, int accumulate,
+                        cudaStream_t stream) {
+  int d = C * T;
+  long long total = (long long)d * d;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cov_finalize_kernel<<<blocks, 256, 0, stream>>>(acc, ld, out, C, T, d, accumulate);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// tf32 split helpers for persistent operands (projector P, updates).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+             long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float h, l;
+    tf32_split(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// dst(hi/lo)[n][k] = src[k][n]  (d x d), so that B = P^T is K-major for D = U * P.
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                       float* __restrict__ lo, int d, int ld_dst) {
+  __shared__ float tile[32][33];
+  int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int row = by + r, col = bx + tx;
+    tile[r][tx] = (row < d && col < d) ? src[(long long)row * d + col] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int row = bx + r, col = by + tx;   // transposed
+    if (row < d && col < d) {
+      float h, l;
+      tf32_split(tile[tx][r], h, l);
+      hi[(long long)row * ld_dst + col] = h;
+      lo[(long long)row * ld_dst + col] = l;
+    }
+  }
+}
+
+int launch_split(const float* src, float* hi, float* lo, long long n, cudaStream_t stream) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_kernel<<<blocks, 256, 0, stream>>>(src, hi, lo, n);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int launch_transpose_split(const float* src, float* hi, float* lo, int d, int ld_dst,
+                           cudaStream_t stream) {
+  dim3 grid(ceil_div(d, 32), ceil_div(d, 32));
+  transpose_split_kernel<<<grid, 256, 0, stream>>>(src, hi, lo, d, ld_dst);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+}  // namespace nsgp

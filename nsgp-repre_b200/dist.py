@@ -1,0 +1,52 @@
+"""torch.distributed plumbing (one process per GPU, NCCL over NVLink; gloo on CPU
+for the tests).  The only collective on this path is the SUM all-reduce of the
+covariance accumulators (nsrunner_roi_replay.py:746-749) - see
+``CovarianceHooks.all_reduce``; RePRE class sums are additive the same way."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise from RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return int(os.environ.get("RANK", "0")), world
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard_batches(n_batches: int, rank: int, world: int):
+    """Batch indices of this rank: r, r+W, ... (DefaultSampler-style round robin,
+    SURVEY.md 8e)."""
+    return list(range(rank, n_batches, world))
+
+
+def all_reduce_sum_(tensors, group=None):
+    """In-place SUM all-reduce of a list of tensors through ONE flat buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return tensors
+
+
+def max_over_ranks(value: float, device) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,208 @@
+"""``SGDNSCL`` - SGD with null-space gradient projection, drop-in for
+mmdet/engine/optimizers/SGD_NSCL.py:15-415.
+
+Same constructor, param-group keys (``names``, ``svd``), public state
+(``eigens``, ``transforms``, ``state[p]['previous_grad'|'step']``) and methods
+(``get_eigens``, ``get_transforms``, ``adaptive_threshold``, ``step``).
+
+What changed underneath
+* ``step``: ONE C-ABI call.  A fused multi-tensor kernel does the weight decay
+  (in place on ``p.grad``, :399-400), the momentum buffer (:402-411) and
+  ``-lr * buf`` for every parameter; protected layers then get
+  ``W += update.view(Cout,-1) @ P`` (:82-95) from the 3xTF32 tensor-core
+  contraction with the add fused in its epilogue.
+* ``get_eigens``: symmetric eigendecomposition on the GPU (cuSOLVER syevd through
+  ``torch.linalg.eigh``, fp64 by default) instead of a full fp32 SVD (:377);
+  for a PSD matrix the singular values / right singular vectors are the
+  eigenpairs sorted by descending magnitude.  Runs once per task boundary.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import defaultdict
+
+import numpy as np
+import scipy.ndimage
+import torch
+from torch.optim.optimizer import Optimizer
+
+from . import _lib
+from ._lib import lib, check, ptr, SgdTensor, ProjLayer
+
+
+class SGDNSCL(Optimizer):
+    def __init__(self, params, lr=1e-3, momentum=0, dampening=0, nesterov=False, svd=False,
+                 thres=1.001, weight_decay=0, eig_dtype=torch.float64):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, nesterov=nesterov,
+                        weight_decay=weight_decay, svd=svd, thres=thres)
+        super().__init__(params, defaults)
+        self.eigens = defaultdict(dict)
+        self.transforms = defaultdict(dict)
+        self.count = 0
+        self.eig_dtype = eig_dtype
+        self._prepared = {}     # name -> (key, pt_hi, pt_lo)
+        self._stage = {}        # name -> (u_hi, u_lo)
+        self._workspace = None
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault("svd", False)
+            group.setdefault("names", [])
+
+    # ------------------------------------------------------------ projector build
+    def adaptive_threshold(self, svals: torch.Tensor, offset: float = 0):
+        """Boolean mask over the spectrum, True from the elbow index on
+        (SGD_NSCL.py:98-177; host numpy/scipy exactly as there)."""
+        pts = svals.detach().cpu().numpy()
+        assert pts.ndim == 1
+        n = len(pts)
+        if n >= 128:
+            sm = scipy.ndimage.gaussian_filter1d(pts, sigma=10)
+            first = sm[:-1] - sm[1:]
+            second = first[:-1] - first[1:]
+            drop = int(n * 0.03 / 2)
+            assert n - drop >= 10
+            inner = second[drop:-drop]
+            elbow_val = pts[np.argmax(inner) + int((n - len(inner)) / 2)]
+        else:
+            first = pts[:-1] - pts[1:]
+            second = first[:-1] - first[1:]
+            elbow_val = pts[np.argmax(second) + int((n - len(second)) / 2)]
+        i_thres = np.arange(n)[pts >= elbow_val].max()
+        if -1 <= offset <= 1:
+            i_thres = max(0, min(i_thres + int(offset * i_thres), n - 1))
+        else:
+            i_thres = max(min(i_thres + int(offset), n - 1), 0)
+        keep = np.zeros(n, dtype=bool)
+        keep[i_thres:] = True
+        return torch.from_numpy(keep).to(svals.device)
+
+    @torch.no_grad()
+    def get_eigens(self, fea_in, distinguisher=None):
+        """Spectrum + basis of every protected layer's covariance (:360-380)."""
+        for group in self.param_groups:
+            if group["svd"] is False:
+                continue
+            for n, p in zip(group["names"], group["params"]):
+                if n not in fea_in.keys():
+                    continue
+                cov = fea_in[n]
+                _lib.require_cuda(cov, "covariance of %s" % n)
+                work = cov.to(self.eig_dtype)
+                work = (work + work.t()) * 0.5
+                evals, evecs = torch.linalg.eigh(work)          # cuSOLVER syevd
+                order = torch.argsort(evals.abs(), descending=True)
+                eigen = self.eigens[n]
+                eigen["eigen_value"] = evals.abs()[order].to(torch.float32)
+                eigen["eigen_vector"] = evecs[:, order].to(torch.float32)
+
+    @torch.no_grad()
+    def get_transforms(self, offset=0.0):
+        """P = V0 V0^T over the null-side columns; 'backbone' names divided by
+        ||P||_F (:235-290)."""
+        for group in self.param_groups:
+            if group["svd"] is False:
+                continue
+            for n, p in zip(group["names"], group["params"]):
+                if n not in self.eigens.keys():
+                    continue
+                ind = self.adaptive_threshold(self.eigens[n]["eigen_value"], offset=offset)
+                basis = self.eigens[n]["eigen_vector"][:, ind]
+                transform = torch.mm(basis, basis.transpose(1, 0))
+                if "backbone" in n:
+                    transform = transform / torch.norm(transform)
+                self.transforms[n] = transform.detach()
+
+    # ---------------------------------------------------------------------- step
+    def _prepare(self, name: str, P: torch.Tensor):
+        key = (P.data_ptr(), P._version, tuple(P.shape))
+        hit = self._prepared.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        _lib.require_cuda(P, "transform of %s" % name)
+        if P.dim() != 2 or P.shape[0] != P.shape[1]:
+            raise _lib.NsgpError("transform of %s must be square" % name)
+        src = P.detach().float().contiguous()
+        d = src.shape[0]
+        hi = torch.empty(d, d, dtype=torch.float32, device=P.device)
+        lo = torch.empty_like(hi)
+        check(lib.nsgp_projector_prepare(ptr(src), d, ptr(hi), ptr(lo),
+                                         _lib.current_stream(P.device)),
+              "nsgp_projector_prepare")
+        self._prepared[name] = (key, hi, lo)
+        return hi, lo
+
+    def _staging(self, name: str, p: torch.Tensor):
+        st = self._stage.get(name)
+        if st is None or st[0].numel() != p.numel() or st[0].device != p.device:
+            st = (torch.empty(p.numel(), dtype=torch.float32, device=p.device),
+                  torch.empty(p.numel(), dtype=torch.float32, device=p.device))
+            self._stage[name] = st
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        """One optimisation step (:59-96)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            svd = group["svd"]
+            names, params = group["names"], group["params"]
+            if len(params) == 0:
+                continue
+            n_t = len(params)
+            tensors = (SgdTensor * n_t)()
+            layers = []
+            device = params[0].device
+            for i, (n, p) in enumerate(zip(names, params)):
+                grad = p.grad.data          # AttributeError when grad is None, like :75
+                if grad.is_sparse:
+                    raise RuntimeError("Adam does not support sparse gradients, please "
+                                       "consider SparseAdam instead")
+                _lib.require_cuda(p, "parameter %s" % n)
+                if p.dtype != torch.float32 or grad.dtype != torch.float32 or \
+                        not p.is_contiguous() or not grad.is_contiguous():
+                    raise _lib.NsgpError("parameter %s: fp32 contiguous tensors required" % n)
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["previous_grad"] = torch.zeros_like(p.data)
+                state["step"] += 1
+                t = tensors[i]
+                t.w, t.g, t.buf = p.data_ptr(), grad.data_ptr(), state["previous_grad"].data_ptr()
+                t.numel = p.numel()
+                t.first_step = 1 if state["step"] == 1 else 0
+                t.layer = -1
+                if svd and len(self.transforms) > 0 and n in self.transforms.keys():
+                    P = self.transforms[n]
+                    if p.dim() not in (2, 4):
+                        raise _lib.NsgpError("parameter %s: projection needs a 2-D or 4-D "
+                                             "tensor" % n)
+                    cout = p.shape[0]
+                    dd = p.numel() // cout
+                    if P.shape[0] != dd:
+                        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied "
+                                           "(%dx%d and %dx%d)" % (cout, dd, P.shape[0], P.shape[1]))
+                    hi, lo = self._prepare(n, P)
+                    u_hi, u_lo = self._staging(n, p)
+                    L = ProjLayer(cout, dd, hi.data_ptr(), lo.data_ptr(),
+                                  u_hi.data_ptr(), u_lo.data_ptr())
+                    t.layer = len(layers)
+                    layers.append(L)
+            n_l = len(layers)
+            layer_arr = (ProjLayer * max(n_l, 1))(*layers)
+            need = lib.nsgp_sgd_step_workspace_bytes(n_t, n_l)
+            if self._workspace is None or self._workspace.numel() < need or \
+                    self._workspace.device != device:
+                self._workspace = torch.empty(int(need), dtype=torch.uint8, device=device)
+            check(lib.nsgp_sgd_nscl_step(
+                tensors, n_t, layer_arr, n_l, float(group["lr"]), float(group["momentum"]),
+                float(group["dampening"]), float(group["weight_decay"]),
+                1 if group["nesterov"] else 0, ptr(self._workspace), self._workspace.numel(),
+                _lib.current_stream(device)), "nsgp_sgd_nscl_step")
+        return loss

@@ -1,0 +1,238 @@
+"""RePRE prototype build + replay staging, drop-in for
+``StandardMultiPrototypeReplayHead`` (mmdet/models/roi_heads/
+standard_roi_replay_head.py:375-501).
+
+GPU kernels do the bandwidth/compute work - per-class segmented means (:412-414),
+L2-normalise + cosine Gram + ``>= 0.6`` + neighbour counts (:417-421), masked
+means (:443), the device-resident replay gather (:458-463).  The tiny
+sequential part - density ordering and the greedy cover (:421-448, at most nine
+picks per class) - stays on the host and calls ``torch.sort`` on the CPU counts
+exactly like the reference does, so equal-count ties resolve identically.
+"""
+from __future__ import annotations
+
+import os
+import os.path as osp
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+
+def get_work_dir(previous_path: str) -> str:
+    """Path rule of :363-370: '..._N' -> '..._N+1' ('coco' paths -> './')."""
+    if "coco" in previous_path:
+        return "./"
+    parts = previous_path.split("_")
+    parts[-1] = str(int(parts[-1]) + 1)
+    return "_".join(parts)
+
+
+class MultiPrototypeReplay:
+    """Builds and serves the coarse + fine-grained prototypes of the old classes.
+
+    ``build`` mirrors the loop at :404-449; results: ``bbox_featss`` (P,D) fp32 on
+    the device, ``tmp_label`` (P,) int64, ``save_idx`` = the ``mask.pth`` payload
+    (list[class] of list[<=max_proto-1] bool masks over that class's rows).
+    """
+
+    def __init__(self, max_prototype: int = 10, thresh: float = 0.6):
+        self.max_proto = max_prototype
+        self.thresh = thresh
+        self.bbox_featss = None
+        self.tmp_label = None
+        self.save_idx = None
+        self.sigma = None
+        self._out = None
+
+    # ------------------------------------------------------------------ build
+    @torch.no_grad()
+    def build(self, feats: torch.Tensor, cls_targets: torch.Tensor, previous_cls,
+              saved_masks=None):
+        _lib.require_cuda(feats, "bbox_featss")
+        dev = feats.device
+        feats = feats.detach()
+        feats = feats.reshape(feats.shape[0], -1)
+        if feats.dtype != torch.float32 or not feats.is_contiguous():
+            feats = feats.float().contiguous()
+        M, D = feats.shape
+        labels = cls_targets.detach().to(device=dev, dtype=torch.int64).contiguous()
+        previous_cls = list(previous_cls)
+        stream = _lib.current_stream(dev)
+        save_idx = list(saved_masks) if saved_masks is not None else []
+        if not previous_cls:
+            self.bbox_featss = feats.new_zeros(0, D)
+            self.tmp_label = torch.zeros(0, dtype=torch.long, device=dev)
+            self.save_idx = save_idx
+            return self
+
+        # stable class index over [0, C)
+        C = max(previous_cls) + 1
+        counts = torch.empty(C, dtype=torch.int32, device=dev)
+        offsets = torch.empty(C + 1, dtype=torch.int32, device=dev)
+        rows = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        check(lib.repre_class_index(ptr(labels), M, C, ptr(counts), ptr(offsets), ptr(rows),
+                                    stream), "repre_class_index")
+        h_off = offsets.cpu().tolist()
+
+        # neighbour masks / counts of every class, launched back to back
+        per_class = {}
+        ws = None
+        for c in previous_cls:
+            n = h_off[c + 1] - h_off[c]
+            if n == 0:
+                # the reference dies in sim_sum[-0//3] (:422); keep that contract
+                raise IndexError("class %d has no stored RoI feature "
+                                 "(index 0 is out of bounds for dimension 0 with size 0)" % c)
+            need = lib.repre_cosine_count_workspace_bytes(n, D)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+            mask = torch.empty(n, n, dtype=torch.uint8, device=dev)
+            cnt = torch.empty(n, dtype=torch.int32, device=dev)
+            check(lib.repre_cosine_count(
+                ptr(feats), D, rows.data_ptr() + 4 * h_off[c], n, float(self.thresh),
+                ptr(mask), ptr(cnt), None, ptr(ws), ws.numel(), stream), "repre_cosine_count")
+            per_class[c] = (mask, cnt)
+
+        # host: density order + greedy cover (sequential, <= max_proto-1 picks)
+        seg_rows, seg_off, seg_label = [], [0], []
+        h_rows = rows.cpu()
+        for c in previous_cls:
+            mask_d, cnt_d = per_class[c]
+            sim_mask = mask_d.cpu().bool()
+            cnt = cnt_d.cpu().long()
+            cls_rows = h_rows[h_off[c]:h_off[c + 1]]
+            # coarse prototype: all rows of the class (:412-414)
+            seg_rows.append(cls_rows)
+            seg_off.append(seg_off[-1] + cls_rows.numel())
+            seg_label.append(c)
+            sim_sum, idx = cnt.sort(dim=-1, descending=True)             # :421
+            thr = sim_sum[-sim_sum.shape[0] // 3]                        # :422
+            covered = cnt <= thr                                         # :423
+            tmp_mask = save_idx[c] if c < len(save_idx) else []          # :425-428
+            for proto_count in range(self.max_proto - 1):                # :430
+                for id_ in idx.tolist():
+                    if proto_count < len(tmp_mask):
+                        m = tmp_mask[proto_count].cpu().bool()
+                    else:
+                        if covered[id_]:
+                            continue
+                        m = sim_mask[id_]
+                        tmp_mask.append(m)
+                    covered = torch.logical_or(covered, m)
+                    sel = cls_rows[m]
+                    seg_rows.append(sel)
+                    seg_off.append(seg_off[-1] + sel.numel())
+                    seg_label.append(c)
+                    break
+            if c >= len(save_idx):
+                save_idx.append(tmp_mask)
+
+        # one launch: coarse + fine means of every class
+        all_rows = torch.cat(seg_rows).to(torch.int32).to(dev)
+        off_t = torch.tensor(seg_off, dtype=torch.int32, device=dev)
+        nseg = len(seg_label)
+        out = torch.empty(nseg, D, dtype=torch.float32, device=dev)
+        max_rows = max(b - a for a, b in zip(seg_off[:-1], seg_off[1:]))
+        check(lib.repre_segment_mean(ptr(feats), D, ptr(off_t), ptr(all_rows), nseg,
+                                     int(max_rows), ptr(out), stream), "repre_segment_mean")
+        self.bbox_featss = out
+        self.tmp_label = torch.tensor(seg_label, dtype=torch.long, device=dev)
+        self.save_idx = save_idx
+        self._segments = (off_t, all_rows, max_rows)
+        self._feats = feats
+        return self
+
+    @torch.no_grad()
+    def build_sigma(self):
+        """Extension (BASELINE north_star item 4; no reference counterpart): per-
+        prototype diagonal standard deviation for Gaussian replay."""
+        off_t, all_rows, max_rows = self._segments
+        nseg, D = self.bbox_featss.shape
+        var = torch.empty_like(self.bbox_featss)
+        check(lib.repre_segment_var(ptr(self._feats), D, ptr(off_t), ptr(all_rows), nseg,
+                                    int(max_rows), ptr(self.bbox_featss), ptr(var),
+                                    _lib.current_stream(var.device)), "repre_segment_var")
+        self.sigma = var.sqrt_()
+        return self.sigma
+
+    # ----------------------------------------------------------------- replay
+    @torch.no_grad()
+    def staged(self, idx=None, out=None, sigma=None, seed=0):
+        """Classifier input of the replay branch (:458-463): the prototypes are
+        device-resident; this gathers them (all of them when ``idx`` is None, as
+        the reference stages every prototype every step) into ``out``."""
+        protos = self.bbox_featss
+        P = protos.shape[0] if idx is None else idx.shape[0]
+        D = protos.shape[1]
+        if out is None:
+            if self._out is None or self._out.shape != (P, D):
+                self._out = torch.empty(P, D, dtype=torch.float32, device=protos.device)
+            out = self._out
+        if idx is not None:
+            idx = idx.to(device=protos.device, dtype=torch.int64).contiguous()
+        check(lib.repre_replay_gather(ptr(protos), ptr(sigma), ptr(idx), P, D, int(seed),
+                                      ptr(out), _lib.current_stream(protos.device)),
+              "repre_replay_gather")
+        return out
+
+
+class StandardMultiPrototypeReplayHead(nn.Module):
+    """Constructor keywords and attributes of the reference head (:377-390):
+    ``previous_path, task_id, task_split, max_prototype, work_dir``; attributes
+    ``replay``, ``bbox_featss``, ``tmp_label``; ``loss`` adds ``replay_loss_cls``.
+
+    Stand-alone form: ``bbox_head`` is any module mapping (P,12544)-features to
+    ``(cls_score, bbox_pred)``.  When mmdet is importable ``registry.py`` builds
+    the real subclass of ``StandardRoIHead`` from the same mixin logic.
+    """
+
+    def __init__(self, bbox_head: nn.Module = None, previous_path=None, task_id=1,
+                 task_split=(0, 10, 20), max_prototype=10, work_dir=None, device=None,
+                 **kwargs):
+        super().__init__()
+        self.bbox_head = bbox_head
+        self.replay = False
+        self.task_split = list(task_split)
+        self.task_id = task_id
+        self.max_proto = max_prototype
+        self.with_shared_head = False
+        self._proto = MultiPrototypeReplay(max_prototype)
+        if previous_path is not None and osp.exists(previous_path):
+            assert task_id != 1
+            self.replay = True
+            dev = torch.device(device) if device is not None else torch.device("cuda")
+            (bbox_featss, self.cls_targets, self.cls_weights, self.bbox_targets,
+             self.bbox_weights, self.roiss) = torch.load(
+                osp.join(previous_path, "rois_etc.pth"), map_location=dev)
+            previous_cls = range(self.task_split[0], self.task_split[task_id - 1])
+            saved = None
+            if osp.exists(osp.join(previous_path, "mask.pth")):
+                saved = torch.load(osp.join(previous_path, "mask.pth"), map_location="cpu")
+            self._proto.build(bbox_featss, self.cls_targets, previous_cls, saved)
+            self.bbox_featss = self._proto.bbox_featss
+            self.tmp_label = self._proto.tmp_label
+            out_dir = work_dir if work_dir is not None else get_work_dir(previous_path)
+            torch.save(self._proto.save_idx, osp.join(out_dir, "mask.pth"))
+
+    def replay_loss(self, bbox_feats, sampling_results=None, rois=None) -> dict:
+        """:468-501 - logits of classes < task_split[task_id] plus background;
+        cross-entropy on the softmax output (double softmax kept on purpose)."""
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+        pre_idx = self.task_split[self.task_id]
+        kept = torch.cat([cls_score[:, :pre_idx], cls_score[:, -1:]], dim=-1)
+        losses = {"replay_loss_cls": F.cross_entropy(kept.softmax(dim=-1),
+                                                     self.tmp_label.to(kept.device))}
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats,
+                    replay_loss=losses)
+
+    def loss(self, x=None, rpn_results_list=None, batch_data_samples=None, base_losses=None):
+        """:454-466.  ``base_losses`` stands for ``super().loss(...)``."""
+        losses = dict(base_losses or {})
+        if self.replay:
+            staged = self._proto.staged()
+            losses.update(self.replay_loss(staged)["replay_loss"])
+        return losses

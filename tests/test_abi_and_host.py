@@ -1,0 +1,98 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header
+declares; host-side logic (threshold rule, path rule, registry, sharding)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "nsgp_repre_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:nsgp|repre)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    import nsgp_repre_b200 as pkg
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(pkg._lib.lib, s), "missing export %s" % s
+        assert s in pkg._lib.SIGNATURES, "ctypes signature missing for %s" % s
+    assert pkg._lib.lib.nsgp_abi_version() == 1
+
+
+def test_layout_queries_are_host_only():
+    from nsgp_repre_b200._lib import lib, CovLayout
+    L = CovLayout()
+    # 3x3 s1 p1, Cin=256 at 50x84: implicit taps
+    assert lib.nsgp_cov_conv2d_layout(256, 50, 84, 3, 3, 1, 1, 1, 1, L) == 0
+    assert (L.d, L.d_int, L.taps) == (2304, 2304, 9)
+    # 7x7 s2 p3 stem, Cin=3 -> explicit im2col fallback, rows padded to 8
+    assert lib.nsgp_cov_conv2d_layout(3, 64, 96, 7, 7, 2, 2, 3, 3, L) == 0
+    assert (L.d, L.d_int, L.taps) == (147, 152, 1)
+    # 1x1 s2 downsample -> flat
+    assert lib.nsgp_cov_conv2d_layout(256, 50, 84, 1, 1, 2, 2, 0, 0, L) == 0
+    assert (L.d, L.d_int, L.taps) == (256, 256, 1)
+    assert lib.nsgp_cov_conv2d_layout(0, 50, 84, 1, 1, 1, 1, 0, 0, L) != 0
+    assert b"invalid conv geometry" in lib.nsgp_last_error()
+
+
+def test_missing_gpu_fails_loudly():
+    """No CPU fallback: host tensors are rejected by the product layer."""
+    from nsgp_repre_b200 import CovarianceHooks, _lib
+    net = torch.nn.Conv2d(8, 8, 3, padding=1)
+    hooks = CovarianceHooks(torch.nn.Sequential(net))
+    with pytest.raises(_lib.NsgpError):
+        hooks.compute_cov(net, (torch.randn(1, 8, 5, 5),), None)
+
+
+@pytest.mark.parametrize("offset", [0.0, 0.5, -0.5, 3.0])
+def test_adaptive_threshold_matches_reference_fixture(golden_dir, offset):
+    from nsgp_repre_b200 import SGDNSCL
+    g = torch.load(os.path.join(golden_dir, "projector.pt"), weights_only=False)
+    opt = SGDNSCL([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
+    for name, ent in g["proj"][offset].items():
+        mask = opt.adaptive_threshold(ent["svals"], offset=offset)
+        assert mask.dtype == torch.bool
+        assert int(mask.long().argmax()) == ent["i_thres"], name
+        assert bool(mask[ent["i_thres"]:].all()) and not bool(mask[:ent["i_thres"]].any())
+
+
+def test_work_dir_rule():
+    from nsgp_repre_b200.prototypes import get_work_dir
+    assert get_work_dir("work_dirs/x_19_1_1") == "work_dirs/x_19_1_2"
+    assert get_work_dir("work_dirs/coco_40_40_1") == "./"
+
+
+def test_registry_names_match_reference_configs():
+    from nsgp_repre_b200 import registry
+    assert {"SGDNSCL", "StandardMultiPrototypeReplayHead"} <= set(registry.REGISTRY)
+    opt = registry.build(dict(type="SGDNSCL", lr=0.02, momentum=0.9, weight_decay=1e-4,
+                              svd=True), params=[torch.nn.Parameter(torch.zeros(2))])
+    assert opt.defaults["svd"] is True and opt.defaults["momentum"] == 0.9
+
+
+def test_standin_module_names_match_mmdet():
+    from nsgp_repre_b200.standin import FasterRCNNStandIn
+    m = FasterRCNNStandIn(with_roi=True)
+    names = dict(m.named_modules())
+    for n in ["backbone.conv1", "backbone.layer2.0.conv1", "backbone.layer2.0.downsample.0",
+              "backbone.layer4.2.conv3", "neck.lateral_convs.3.conv", "neck.fpn_convs.0.conv",
+              "rpn_head.rpn_conv", "roi_head.bbox_head.shared_fcs.0"]:
+        assert n in names, n
+    convs = [n for n, mod in names.items()
+             if isinstance(mod, torch.nn.Conv2d) and re.match("backbone|neck", n)]
+    assert len(convs) == 61          # backbone + neck hooked convs
+    trainable = [n for n in convs if names[n].weight.requires_grad]
+    assert len(trainable) == 50      # frozen_stages=1
+
+
+def test_shard_batches():
+    from nsgp_repre_b200.dist import shard_batches
+    got = sorted(sum((shard_batches(11, r, 4) for r in range(4)), []))
+    assert got == list(range(11))

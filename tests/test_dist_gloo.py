@@ -1,0 +1,54 @@
+"""world_size-2 gloo test of the multi-GPU host logic (data-sharded covariance
+sums + one flat SUM all-reduce, nsrunner_roi_replay.py:746-749) on CPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from nsgp_repre_b200 import dist as D
+    from nsgp_repre_b200.covariance import CovarianceHooks, _LayerAcc
+    from oracle import restated as O
+    r, w = D.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # every rank accumulates its shard of 6 seeded batches into CPU stand-ins of the
+    # accumulators; the reduce must equal the single-process sum
+    g = torch.Generator().manual_seed(0)
+    batches = [torch.randn(2, 4, 6, 7, generator=g) for _ in range(6)]
+    mine = D.shard_batches(len(batches), rank, world)
+    acc = torch.zeros(36, 36)
+    for i in mine:
+        acc += O.cov_conv2d(batches[i], (3, 3), (1, 1), (1, 1))
+    hooks = CovarianceHooks(torch.nn.Identity())
+    hooks._layers["conv.weight"] = _LayerAcc(None, acc.view(-1).clone())
+    hooks._layers["other.weight"] = _LayerAcc(None, torch.full((5,), float(rank + 1)))
+    hooks.all_reduce()
+    total = sum(O.cov_conv2d(b, (3, 3), (1, 1), (1, 1)) for b in batches)
+    ok = torch.allclose(hooks._layers["conv.weight"].acc.view(36, 36), total, rtol=1e-5, atol=1e-4)
+    ok &= bool((hooks._layers["other.weight"].acc == 3.0).all())
+    t = [torch.ones(3) * (rank + 1), torch.ones(2, 2) * 10 * (rank + 1)]
+    D.all_reduce_sum_(t)
+    ok &= bool((t[0] == 3).all() and (t[1] == 30).all())
+    ok &= D.max_over_ranks(float(rank), "cpu") == 1.0
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_covariance_allreduce_world2():
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
