@@ -85,8 +85,9 @@ int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* layout /* host 
  *   (mmdet/engine/optimizers/SGD_NSCL.py:387-415, 59-96)
  * ------------------------------------------------------------------------- */
 
-/* dst_hi/dst_lo (d x d) = tf32 hi/lo split of P^T, the K-major operand of
- * update @ P (SGD_NSCL.py:85-90).  Done once per task after get_transforms. */
+/* pt_hi/pt_lo (d rows, pitch round_up(d,4)) = tf32 hi/lo split of P^T, the K-major
+ * operand of update @ P (SGD_NSCL.py:85-90).  Done once per task after
+ * get_transforms. */
 int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, void* stream);
 
 typedef struct {
@@ -102,7 +103,7 @@ typedef struct {
   int cout, d;             /* update.view(cout, d) @ P(d,d) */
   const float* pt_hi;      /* from nsgp_projector_prepare */
   const float* pt_lo;
-  float* u_hi;             /* scratch (cout x d) each: staged update */
+  float* u_hi;             /* scratch, cout rows of pitch round_up(d,4) each: staged update */
   float* u_lo;
 } nsgp_proj_layer_t;
 

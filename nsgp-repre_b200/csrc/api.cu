@@ -135,7 +135,7 @@ int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* L, float* cov_o
 // ---------------------------------------------------------------- projection
 int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, void* stream_) {
   NSGP_REQUIRE(P && pt_hi && pt_lo && d > 0, "projector_prepare: bad arguments");
-  return launch_transpose_split(P, pt_hi, pt_lo, d, d, (cudaStream_t)stream_);
+  return launch_transpose_split(P, pt_hi, pt_lo, d, (int)round_up(d, 4), (cudaStream_t)stream_);
 }
 
 size_t nsgp_sgd_step_workspace_bytes(int n_tensors, int n_layers) {
@@ -168,6 +168,7 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
       NSGP_REQUIRE((long long)L.cout * L.d == t.numel,
                    "sgd_step: tensor %d: cout*d != numel", i);
       d.u_hi = L.u_hi; d.u_lo = L.u_lo;
+      d.d = L.d; d.ldu = (int)round_up(L.d, 4);
     }
     host[i] = d;
     chunk_start[i] = total;
@@ -188,8 +189,9 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
     if (tensors[i].layer < 0) continue;
     const nsgp_proj_layer_t& L = layers[tensors[i].layer];
     ContractionArgs a{};
-    a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, L.d);
-    a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, L.d);
+    const int ldk = (int)round_up(L.d, 4);
+    a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, ldk);
+    a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
     a.out = tensors[i].w;
     a.ld = L.d;
     a.n_cols = L.d;

@@ -6,20 +6,30 @@
 namespace nsgp {
 
 enum StageMode : int {
-  kModeImplicit = 0,  // phase planes with zero halo; taps are shifted TMA windows
+  kModeImplicit = 0,  // kw column-shifted copies per row phase; row taps are TMA y offsets
   kModeFlat = 1,      // 1x1, pad 0: K = Hout*Wout flattened, no halo, no waste
   kModeExplicit = 2,  // explicit im2col rows in reference order (fallback)
 };
 
+// Implicit layout.  TMA needs the innermost (column) coordinate 16-byte aligned, so
+// a +-1 column tap shift cannot be a coordinate.  Instead every kernel column j gets
+// its own copy of the (batch-averaged) map, already shifted and stride-sampled:
+//     copy(p, j)[c][r][x] = mean_b in[c][sh*(r - Ht) + py_p][sw*x - pw + j]   (0 outside)
+// for x < Wout; p enumerates the distinct row phases py = (i - ph) mod sh.  Tap (i, j)
+// at output position (oy, ox) then reads copy(p(i), j)[c][oy + yoff_i][ox]: the row
+// tap is a plain TMA y offset (zero halo rows are staged), the K tail ox >= Wout is
+// out of bounds of the tensor map and reads as zero.
 struct ConvGeom {
   int C, H, W, kh, kw, sh, sw, ph, pw;
   int Hout, Wout;
   int mode;
   int T;        // taps that index Gram rows (implicit: kh*kw, else 1)
   int Cs;       // staged rows per tap (implicit/flat: C; explicit: round_up(d, 8))
-  int nphase;   // implicit: sh*sw, else 1
+  int ncopy;    // implicit: (#row phases) * kw, else 1
+  int nrowphase;
+  int rowphase_py[kMaxTaps];   // py of row-phase slot p
   int Hs, Ws;   // staged plane height / pitch
-  int Ht, Wl;   // top / left halo in plane units
+  int Ht;       // top halo in plane rows
   int d;        // true covariance dimension C*kh*kw
   int d_int;    // internal accumulator dimension (T*Cs)
 };
@@ -41,25 +51,32 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
   g.Wout = (W + 2 * pw - kw) / sw + 1;
   if (g.Hout <= 0 || g.Wout <= 0) return -1;
   g.d = C * kh * kw;
+  g.ncopy = 1; g.nrowphase = 1;
   const bool one_by_one = (kh == 1 && kw == 1 && ph == 0 && pw == 0);
   if (one_by_one && C % 8 == 0) {
     g.mode = kModeFlat;
-    g.T = 1; g.Cs = C; g.nphase = 1;
+    g.T = 1; g.Cs = C;
     g.Hs = 1; g.Ws = (int)round_up((long long)g.Hout * g.Wout, 4);
-    g.Ht = g.Wl = 0;
+    g.Ht = 0;
   } else if (kh * kw <= kMaxTaps && C % 8 == 0) {
     g.mode = kModeImplicit;
-    g.T = kh * kw; g.Cs = C; g.nphase = sh * sw;
+    g.T = kh * kw; g.Cs = C;
+    g.nrowphase = 0;
+    for (int i = 0; i < kh; ++i) {
+      int py = pos_mod(i - ph, sh), p = 0;
+      while (p < g.nrowphase && g.rowphase_py[p] != py) ++p;
+      if (p == g.nrowphase) g.rowphase_py[g.nrowphase++] = py;
+    }
+    g.ncopy = g.nrowphase * kw;
     g.Ht = ceil_div(ph, sh);
-    g.Wl = ceil_div(pw, sw);
-    int qy_max = floor_div(kh - 1 - ph, sh), qx_max = floor_div(kw - 1 - pw, sw);
+    int qy_max = floor_div(kh - 1 - ph, sh);
     g.Hs = g.Hout + qy_max + g.Ht;
-    g.Ws = (int)round_up(g.Wout + qx_max + g.Wl, 4);
+    g.Ws = (int)round_up(g.Wout, 4);
   } else {
     g.mode = kModeExplicit;
-    g.T = 1; g.Cs = (int)round_up(g.d, 8); g.nphase = 1;
+    g.T = 1; g.Cs = (int)round_up(g.d, 8);
     g.Hs = 1; g.Ws = (int)round_up((long long)g.Hout * g.Wout, 4);
-    g.Ht = g.Wl = 0;
+    g.Ht = 0;
   }
   g.d_int = g.T * g.Cs;
   *out = g;
@@ -67,7 +84,7 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
 }
 
 static inline long long stage_hl_stride(const ConvGeom& g) {
-  return (long long)g.Cs * g.Hs * g.Ws * g.nphase;
+  return (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
 }
 static inline size_t stage_bytes(const ConvGeom& g) {
   return (size_t)stage_hl_stride(g) * 2 * sizeof(float);
@@ -83,17 +100,18 @@ static inline Operand conv_operand(const ConvGeom& g, const float* stage) {
   if (g.mode == kModeImplicit) {
     o.Kh = g.Hout; o.Kw = g.Wout;
     o.rows = g.T * g.Cs;
-    for (int i = 0; i < g.kh; ++i)
+    for (int i = 0; i < g.kh; ++i) {
+      int ay = i - g.ph;
+      int qy = floor_div(ay, g.sh), py = pos_mod(ay, g.sh), p = 0;
+      while (g.rowphase_py[p] != py) ++p;
       for (int j = 0; j < g.kw; ++j) {
         int t = i * g.kw + j;
-        int ay = i - g.ph, ax = j - g.pw;
-        int qy = floor_div(ay, g.sh), py = pos_mod(ay, g.sh);
-        int qx = floor_div(ax, g.sw), px = pos_mod(ax, g.sw);
-        o.tap_plane[t] = py * g.sw + px;
+        o.tap_plane[t] = p * g.kw + j;
         o.tap_yoff[t] = qy + g.Ht;
-        o.tap_xoff[t] = qx + g.Wl;
-        o.tap_ext[t] = g.Wout + qx + g.Wl;   // columns past the last valid output read 0
+        o.tap_xoff[t] = 0;
+        o.tap_ext[t] = g.Wout;   // columns past the last valid output read 0
       }
+    }
   } else {
     o.Kh = 1; o.Kw = g.Hout * g.Wout;
     o.rows = (g.mode == kModeExplicit) ? g.d : g.Cs;

@@ -48,8 +48,10 @@ sgd_prologue_kernel(const SgdTensorDev* __restrict__ tensors,
     if (t.u_hi) {
       float h, l;
       tf32_split(upd, h, l);
-      t.u_hi[i] = h;
-      t.u_lo[i] = l;
+      long long o = i;
+      if (t.ldu != t.d) { long long r = i / t.d; o = r * t.ldu + (i - r * t.d); }
+      t.u_hi[o] = h;
+      t.u_lo[o] = l;
     } else {
       t.w[i] = w + upd;
     }

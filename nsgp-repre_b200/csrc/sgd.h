@@ -10,6 +10,8 @@ struct SgdTensorDev {
   float* u_lo;
   long long numel;
   int first;     // state just created: buf = grad (SGD_NSCL.py:405-406)
+  int d;         // protected: row length of update.view(cout, d); staged pitch is ldu
+  int ldu;
   int pad;
 };
 int launch_sgd_prologue(const SgdTensorDev* tensors_dev, const int* chunk_start_dev,

@@ -16,9 +16,9 @@ __global__ void __launch_bounds__(256)
 stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
                   int B, long long hl_stride) {
   const long long plane_elems = (long long)g.Cs * g.Hs * g.Ws;
-  const long long total = plane_elems * g.nphase;
+  const long long total = plane_elems * g.ncopy;
   const long long img = (long long)g.C * g.H * g.W;
-  const float inv_is_div = (float)B;
+  const float fb = (float)B;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int xs = (int)(idx % g.Ws);
@@ -26,7 +26,7 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
     int r = (int)(rest % g.Hs);
     rest /= g.Hs;
     int c = (int)(rest % g.Cs);
-    int phase = (int)(rest / g.Cs);
+    int copy = (int)(rest / g.Cs);
     int y, xx;
     bool valid;
     if (g.mode == kModeFlat) {
@@ -36,10 +36,10 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
       y = oy * g.sh;
       xx = ox * g.sw;
     } else {
-      int py = phase / g.sw, px = phase - py * g.sw;
-      y = g.sh * (r - g.Ht) + py;
-      xx = g.sw * (xs - g.Wl) + px;
-      valid = (y >= 0) && (y < g.H) && (xx >= 0) && (xx < g.W);
+      int p = copy / g.kw, j = copy - p * g.kw;
+      y = g.sh * (r - g.Ht) + g.rowphase_py[p];
+      xx = g.sw * xs - g.pw + j;
+      valid = (xs < g.Wout) && (y >= 0) && (y < g.H) && (xx >= 0) && (xx < g.W);
     }
     float v = 0.f;
     if (valid) {
@@ -47,7 +47,7 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
       float s = 0.f;
 #pragma unroll 4
       for (int b = 0; b < B; ++b) s += __ldg(p + (long long)b * img);
-      v = s / inv_is_div;
+      v = s / fb;
     }
     float hi, lo;
     tf32_split(v, hi, lo);
@@ -97,7 +97,7 @@ stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stag
 int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
                       cudaStream_t stream) {
   long long total = (g.mode == kModeExplicit) ? (long long)g.Cs * g.Ws
-                                              : (long long)g.Cs * g.Hs * g.Ws * g.nphase;
+                                              : (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
   long long hl = stage_hl_stride(g);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;

@@ -127,7 +127,8 @@ class SGDNSCL(Optimizer):
             raise _lib.NsgpError("transform of %s must be square" % name)
         src = P.detach().float().contiguous()
         d = src.shape[0]
-        hi = torch.empty(d, d, dtype=torch.float32, device=P.device)
+        ld = (d + 3) // 4 * 4
+        hi = torch.empty(d, ld, dtype=torch.float32, device=P.device)
         lo = torch.empty_like(hi)
         check(lib.nsgp_projector_prepare(ptr(src), d, ptr(hi), ptr(lo),
                                          _lib.current_stream(P.device)),
@@ -137,9 +138,11 @@ class SGDNSCL(Optimizer):
 
     def _staging(self, name: str, p: torch.Tensor):
         st = self._stage.get(name)
-        if st is None or st[0].numel() != p.numel() or st[0].device != p.device:
-            st = (torch.empty(p.numel(), dtype=torch.float32, device=p.device),
-                  torch.empty(p.numel(), dtype=torch.float32, device=p.device))
+        cout = p.shape[0]
+        need = cout * ((p.numel() // cout + 3) // 4 * 4)
+        if st is None or st[0].numel() != need or st[0].device != p.device:
+            st = (torch.empty(need, dtype=torch.float32, device=p.device),
+                  torch.empty(need, dtype=torch.float32, device=p.device))
             self._stage[name] = st
         return st
 

@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle
+restatement and the golden fixtures produced by the reference's own functions.
+
+Tolerances (BASELINE.json north_star): covariances, projectors, projected updates
+and prototypes within 1e-4 relative Frobenius error; neighbour masks identical
+except for documented near-ties (|S - 0.6| < 1e-5); integer / index results
+bit-exact.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_fro
+from oracle import restated as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+# 3xTF32 on tcgen05: operands carry ~21 mantissa bits and the tensor core accumulates
+# with truncation (~2^-25.6 relative per accumulate step, measured on B200); the K
+# chain per TMEM accumulator is bounded to 32 K-blocks (384 steps) -> <= ~1e-5.
+ENGINE_TOL = 2e-5
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import nsgp_repre_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(params=[0, 1], ids=["tcgen05", "simt"])
+def engine(request, pkg):
+    prev = pkg._lib.lib.nsgp_set_engine(request.param)
+    yield request.param
+    pkg._lib.lib.nsgp_set_engine(prev)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------- engine
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (200, 136, 100),
+                                   (64, 8, 36), (384, 640, 1056), (8, 8, 4), (130, 300, 3076)])
+def test_contraction_gemm_3xtf32(pkg, engine, M, N, K):
+    """C += A B^T on the selected engine vs fp64; 3xTF32 must be fp32-faithful."""
+    lib, ptr = pkg._lib.lib, pkg._lib.ptr
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g)
+    C0 = torch.randn(M, N + (-N) % 4, device="cuda", generator=g)
+    ah, al, bh, bl = (torch.empty_like(A), torch.empty_like(A), torch.empty_like(B),
+                      torch.empty_like(B))
+    pkg._lib.check(lib.nsgp_split_tf32(ptr(A), ptr(ah), ptr(al), A.numel(), _stream()), "split")
+    pkg._lib.check(lib.nsgp_split_tf32(ptr(B), ptr(bh), ptr(bl), B.numel(), _stream()), "split")
+    assert torch.equal((ah.view(torch.int32) & 0x1FFF), torch.zeros_like(ah, dtype=torch.int32))
+    C = C0.clone()
+    pkg._lib.check(lib.nsgp_debug_gemm_nt(ptr(ah), ptr(al), ptr(bh), ptr(bl), M, N, K, ptr(C),
+                                          C.shape[1], _stream()), "gemm")
+    want = C0.double()
+    want[:, :N] += A.double() @ B.double().t()
+    assert rel_fro(C[:, :N], want[:, :N]) < ENGINE_TOL
+    assert torch.equal(C[:, N:], C0[:, N:])          # padding columns untouched
+
+
+# ----------------------------------------------------------------------- covariance
+def test_covariance_toy_model_matches_reference_fixture(pkg, engine, golden_dir):
+    """Every conv geometry of R50-FPN at toy size, 3 batches, through the forward
+    hooks, against the fixture produced by the reference's compute_cov/update_cov."""
+    g = _load(golden_dir, "cov_toy.pt")
+    net = synth.ToyDetector()
+    net.load_state_dict(g["state_dict"])
+    batches = synth.toy_batches(seed=g["seed"])
+    net = net.cuda()
+    hooks = pkg.CovarianceHooks(net, add_default_ignores=False)
+    fea = hooks.cal_fea_in([b.cuda() for b in batches])
+    assert set(fea) == set(g["fea_in"])
+    for k, ref in g["fea_in"].items():
+        assert fea[k].shape == ref.shape
+        assert rel_fro(fea[k], ref) < TOL, k
+        assert rel_fro(fea[k], fea[k].t()) == 0.0          # exactly symmetric
+
+
+GEOMS = [
+    # (Cin, H, W, k, s, p, B)                      what it stands for
+    (64, 40, 56, 3, 1, 1, 2),     # layer1 conv2: 9 taps x 64 rows, tiles span taps
+    (128, 31, 45, 3, 2, 1, 3),    # layerN.0 conv2: stride-2 phases, odd extent
+    (256, 25, 42, 3, 1, 1, 1),    # fpn conv at P5-like extent (Wout not /32)
+    (256, 50, 84, 1, 1, 0, 2),    # 1x1 flat
+    (512, 25, 42, 1, 2, 0, 2),    # downsample 1x1 s2
+    (3, 64, 96, 7, 2, 3, 2),      # stem, explicit im2col, d = 147
+    (64, 17, 23, 1, 1, 0, 4),     # d = 64 < one tile
+    (8, 9, 11, 3, 1, 1, 2),       # tiny
+    (16, 12, 40, 5, 1, 2, 2),     # 25 taps -> explicit fallback
+]
+
+
+@pytest.mark.parametrize("Cin,H,W,k,s,p,B", GEOMS)
+def test_covariance_layer_geometries(pkg, engine, Cin, H, W, k, s, p, B):
+    g = torch.Generator().manual_seed(Cin * 131 + H)
+    conv = torch.nn.Conv2d(Cin, 4, k, stride=s, padding=p, bias=False).cuda()
+    model = torch.nn.Sequential(conv)
+    hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+    want = None
+    for _ in range(2):
+        x = torch.relu(torch.randn(B, Cin, H, W, generator=g))
+        with torch.no_grad():
+            model(x.cuda())
+        c = O.cov_conv2d(x.double(), (k, k), (s, s), (p, p))
+        want = c if want is None else want + c
+    hooks.remove()
+    got = hooks.fea_in["0.weight"]
+    assert got.shape == (Cin * k * k, Cin * k * k)
+    assert rel_fro(got, want) < 2e-5
+
+
+def test_covariance_long_k_chain(pkg, engine):
+    """N = 67 200 positions (the P2-level extent at 800x1344): exercises K splits
+    and the fp32 accumulation chain."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(torch.randn(1, 64, 200, 336, generator=g)) + 0.5
+    conv = torch.nn.Conv2d(64, 4, 3, padding=1, bias=False).cuda()
+    model = torch.nn.Sequential(conv)
+    hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+    with torch.no_grad():
+        model(x.cuda())
+    hooks.remove()
+    want = O.cov_conv2d(x.double(), (3, 3), (1, 1), (1, 1))
+    assert rel_fro(hooks.fea_in["0.weight"], want) < 2e-5
+
+
+def test_covariance_linear_and_update_cov(pkg, engine):
+    g = torch.Generator().manual_seed(11)
+    lin = torch.nn.Linear(200, 6).cuda()
+    model = torch.nn.Sequential(lin)
+    hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+    xs = [torch.randn(5, 200, generator=g) for _ in range(3)]
+    with torch.no_grad():
+        for x in xs:
+            model(x.cuda())
+    hooks.remove()
+    want = sum(O.cov_linear(x.double()) for x in xs)
+    assert rel_fro(hooks.fea_in["0.weight"], want) < ENGINE_TOL
+    # update_cov(rows, key): the reference's (N, d) entry point
+    rows = torch.randn(333, 72, generator=g)
+    hooks.update_cov(rows.cuda(), "extra.weight")
+    hooks.update_cov(rows.cuda(), "extra.weight")
+    assert rel_fro(hooks.fea_in["extra.weight"], 2 * O.gram(rows.double())) < ENGINE_TOL
+
+
+def test_covariance_merge_previous_and_save(pkg, tmp_path):
+    conv = torch.nn.Conv2d(8, 4, 3, padding=1).cuda()
+    model = torch.nn.Sequential(conv)
+    hooks = pkg.CovarianceHooks(model, add_default_ignores=False)
+    x = torch.randn(2, 8, 10, 12)
+    old = {"0.weight": torch.eye(72)}
+    out = hooks.cal_fea_in([x.cuda()], previous=old, save_path=str(tmp_path / "covariance.pth"))
+    want = O.cov_conv2d(x, (3, 3), (1, 1), (1, 1)) + old["0.weight"]
+    assert rel_fro(out["0.weight"], want) < TOL
+    again = torch.load(str(tmp_path / "covariance.pth"), map_location="cpu")
+    assert set(again) == {"0.weight"} and rel_fro(again["0.weight"], want) < TOL
+
+
+# ------------------------------------------------------------------------ projector
+@pytest.mark.parametrize("offset", [0.0, 0.5, -0.5, 3.0])
+def test_projector_matches_reference_fixture(pkg, golden_dir, offset):
+    """get_eigens (GPU syevd) + get_transforms vs the reference's fp32 SVD build.
+    P = V0 V0^T is compared, never the basis (sign / rotation ambiguity)."""
+    g = _load(golden_dir, "projector.pt")
+    ents = g["proj"][offset]
+    covs = {n: synth.decaying_cov(*g["seeds"][n][:2], rank=g["seeds"][n][2]).cuda()
+            for n in ents}
+    params = [torch.nn.Parameter(torch.zeros(4, covs[n].shape[0], device="cuda")) for n in ents]
+    opt = pkg.SGDNSCL(params, lr=0.02, svd=True)
+    opt.param_groups[0]["names"] = list(ents)
+    opt.get_eigens(covs)
+    opt.get_transforms(offset=offset)
+    for n, ent in ents.items():
+        assert rel_fro(opt.eigens[n]["eigen_value"], ent["svals"]) < 1e-5
+        mask = opt.adaptive_threshold(opt.eigens[n]["eigen_value"], offset=offset)
+        assert int(mask.long().argmax()) == ent["i_thres"], n
+        assert rel_fro(opt.transforms[n], ent["transform"]) < TOL, n
+
+
+# ------------------------------------------------------------------------- SGD step
+@pytest.mark.parametrize("tag", ["mom_wd", "plain", "nesterov_damp"])
+def test_sgd_nscl_steps_match_reference_fixture(pkg, engine, golden_dir, tag):
+    g = _load(golden_dir, "sgd_steps.pt")
+    proj = _load(golden_dir, "projector.pt")["proj"][0.0]
+    run = g["steps"][tag]
+    names = list(g["init"])
+    params = [torch.nn.Parameter(g["init"][n].clone().cuda()) for n in names]
+    opt = pkg.SGDNSCL(params, svd=True, **run["kw"])
+    opt.param_groups[0]["names"] = names
+    for n, e in proj.items():
+        opt.transforms[n] = e["transform"].cuda()
+    for step, want in zip(g["grads"], run["traj"]):
+        for n, p in zip(names, params):
+            p.grad = step[n].clone().cuda()
+        opt.step()
+        for n, p in zip(names, params):
+            assert rel_fro(p, want["w"][n]) < 1e-5, (tag, n)
+            assert rel_fro(p.grad, want["grad_after"][n]) < 1e-6, (tag, n)
+            if float(want["buf"][n].abs().max()) > 0:
+                assert rel_fro(opt.state[p]["previous_grad"], want["buf"][n]) < 1e-6, (tag, n)
+
+
+def test_projected_update_r50_shapes(pkg, engine):
+    """update @ P at layer shapes of the R50-FPN protected set,
+    'backbone' scaling included, against the oracle step in fp64."""
+    shapes = {"backbone.layer2.0.conv2.weight": (128, 128, 3, 3),
+              "backbone.layer3.0.conv1.weight": (256, 512, 1, 1),
+              "neck.fpn_convs.0.conv.weight": (256, 256, 3, 3),
+              "neck.lateral_convs.0.conv.weight": (256, 256, 1, 1),
+              "backbone.layer2.0.bn2.weight": (128,)}
+    g = torch.Generator().manual_seed(1)
+    transforms = {}
+    for n, s in shapes.items():
+        if len(s) == 4:
+            d = s[1] * s[2] * s[3]
+            transforms[n] = synth.decaying_cov(d, d, rank=17)
+            ev, evec = torch.linalg.eigh(transforms[n].double())
+            basis = evec[:, :d - 17]
+            P = basis @ basis.t()
+            if "backbone" in n:
+                P = P / torch.linalg.norm(P)
+            transforms[n] = P.float()
+    init = {n: torch.randn(*s, generator=g) for n, s in shapes.items()}
+    kw = dict(lr=0.02, momentum=0.9, weight_decay=1e-4)
+    names = list(shapes)
+    params = [torch.nn.Parameter(init[n].clone().cuda()) for n in names]
+    opt = pkg.SGDNSCL(params, svd=True, **kw)
+    opt.param_groups[0]["names"] = names
+    for n, P in transforms.items():
+        opt.transforms[n] = P.cuda()
+    ref_p = {n: init[n].double().clone() for n in names}
+    ref_t = {n: P.double() for n, P in transforms.items()}
+    states = {}
+    for step in range(2):
+        grads = {n: torch.randn(*shapes[n], generator=g) for n in names}
+        for n, p in zip(names, params):
+            p.grad = grads[n].clone().cuda()
+        opt.step()
+        before = {n: ref_p[n].clone() for n in names}
+        O.sgd_nscl_step(ref_p, {n: v.double() for n, v in grads.items()}, states, ref_t,
+                        svd=True, **kw)
+        for n, p in zip(names, params):
+            # compare the applied update (W_new - W_old), not W itself
+            got = p.detach().double().cpu() - before[n]
+            want = ref_p[n] - before[n]
+            assert rel_fro(p, ref_p[n]) < 1e-6, n
+            assert rel_fro(got, want) < TOL, (step, n)
+
+
+# ----------------------------------------------------------------------- prototypes
+def test_prototypes_match_reference_fixture(pkg, engine, golden_dir):
+    g = _load(golden_dir, "prototypes.pt")
+    feats, lab = synth.proto_features()
+    mp = pkg.MultiPrototypeReplay(max_prototype=10).build(feats.cuda(), lab.cuda(), range(0, 3))
+    assert torch.equal(mp.tmp_label.cpu(), g["tmp_label"])
+    assert [len(m) for m in mp.save_idx] == [len(m) for m in g["masks"]]
+    for mine, ref in zip(mp.save_idx, g["masks"]):
+        for a, b in zip(mine, ref):
+            assert torch.equal(a.cpu().bool(), b)
+    assert rel_fro(mp.bbox_featss, g["protos"]) < 1e-5
+    # next task replays the saved masks (mask.pth) and adds one class
+    feats2, lab2 = synth.proto_features(seed=1, classes=4, per_class=60, bg=20)
+    feats2 = torch.cat([feats, feats2[lab2 == 3]])
+    lab2 = torch.cat([lab, lab2[lab2 == 3]])
+    mp2 = pkg.MultiPrototypeReplay(max_prototype=10).build(
+        feats2.cuda(), lab2.cuda(), range(0, 4), saved_masks=[list(m) for m in g["masks"]])
+    assert torch.equal(mp2.tmp_label.cpu(), g["tmp_label2"])
+    assert rel_fro(mp2.bbox_featss, g["protos2"]) < 1e-5
+
+
+def test_cosine_count_mask_vs_oracle(pkg, engine):
+    """Neighbour mask / counts (:417-421): identical to the oracle except where the
+    similarity is within 1e-5 of the threshold (documented near-tie rule)."""
+    feats, lab = synth.proto_features(seed=4, classes=2, per_class=150, D=12544, sub=3, bg=10)
+    lib, ptr = pkg._lib.lib, pkg._lib.ptr
+    F = feats.cuda()
+    rows = torch.nonzero(lab == 1).flatten().to(torch.int32).cuda()
+    n = rows.numel()
+    ws = torch.empty(lib.repre_cosine_count_workspace_bytes(n, 12544), dtype=torch.uint8,
+                     device="cuda")
+    mask = torch.empty(n, n, dtype=torch.uint8, device="cuda")
+    cnt = torch.empty(n, dtype=torch.int32, device="cuda")
+    sim = torch.empty(n, n, device="cuda")
+    pkg._lib.check(lib.repre_cosine_count(ptr(F), 12544, ptr(rows), n, 0.6, ptr(mask), ptr(cnt),
+                                          ptr(sim), ptr(ws), ws.numel(), _stream()), "cosine")
+    s_ref, m_ref, c_ref = O.cosine_neighbour_mask(feats[lab == 1].double())
+    assert rel_fro(sim, s_ref) < 1e-5
+    differ = mask.cpu().bool() != m_ref
+    assert bool(((s_ref - 0.6).abs()[differ] < 1e-5).all())
+    assert torch.equal(cnt.cpu().long(), mask.cpu().long().sum(-1))
+    if not differ.any():
+        assert torch.equal(cnt.cpu().long(), c_ref)
+
+
+def test_class_index_and_segment_mean_edge_cases(pkg):
+    lib, ptr = pkg._lib.lib, pkg._lib.ptr
+    g = torch.Generator().manual_seed(2)
+    M, D, C = 1000, 256, 7
+    lab = torch.randint(0, C + 2, (M,), generator=g)
+    lab[lab == 3] = 0                                    # class 3 empty
+    F = torch.randn(M, D, generator=g)
+    counts = torch.empty(C, dtype=torch.int32, device="cuda")
+    offsets = torch.empty(C + 1, dtype=torch.int32, device="cuda")
+    rows = torch.empty(M, dtype=torch.int32, device="cuda")
+    pkg._lib.check(lib.repre_class_index(ptr(lab.cuda()), M, C, ptr(counts), ptr(offsets),
+                                         ptr(rows), _stream()), "class_index")
+    off = offsets.cpu().tolist()
+    for c in range(C):
+        want = torch.nonzero(lab == c).flatten()
+        assert counts[c].item() == want.numel()
+        assert torch.equal(rows[off[c]:off[c + 1]].cpu().long(), want)      # bit-exact, stable
+    out = torch.empty(C, D, device="cuda")
+    mx = int(counts.max().item())
+    pkg._lib.check(lib.repre_segment_mean(ptr(F.cuda()), D, ptr(offsets), ptr(rows), C, mx,
+                                          ptr(out), _stream()), "segment_mean")
+    for c in range(C):
+        if c == 3:
+            assert bool(out[c].isnan().all())            # torch.mean of an empty slice
+        else:
+            assert rel_fro(out[c], F[lab == c].double().mean(0)) < 1e-6
+
+
+def test_replay_gather_identity_index_and_gaussian(pkg):
+    g = torch.Generator().manual_seed(9)
+    protos = torch.randn(37, 12544, generator=g)
+    mp = pkg.MultiPrototypeReplay()
+    mp.bbox_featss = protos.cuda()
+    out = mp.staged()
+    assert torch.equal(out.cpu(), protos)                                    # bit-exact copy
+    idx = torch.randperm(37, generator=g)[:16]
+    assert torch.equal(mp.staged(idx=idx.cuda()).cpu(), O.replay_gather(protos, idx))
+    # extension (parity unpinned by the reference): Gaussian jitter, counter-based RNG
+    sigma = torch.rand(37, 12544, generator=g)
+    got = mp.staged(idx=idx.cuda(), sigma=sigma.cuda(), seed=1234)
+    want = O.replay_gather_gaussian(protos, sigma, idx, 1234)
+    assert float((got.cpu() - want).abs().max()) < 1e-4
+
+
+def test_kmeans_assign_extension(pkg, engine):
+    """Extension named by BASELINE.json (no reference counterpart, parity unpinned)."""
+    lib, ptr = pkg._lib.lib, pkg._lib.ptr
+    g = torch.Generator().manual_seed(6)
+    n, k, D = 500, 12, 12544
+    cent = torch.randn(k, D, generator=g)
+    x = cent[torch.randint(0, k, (n,), generator=g)] + 0.5 * torch.randn(n, D, generator=g)
+    ws = torch.empty(lib.repre_kmeans_assign_workspace_bytes(n, k, D), dtype=torch.uint8,
+                     device="cuda")
+    lab = torch.empty(n, dtype=torch.int64, device="cuda")
+    pkg._lib.check(lib.repre_kmeans_assign(ptr(x.cuda()), n, D, ptr(cent.cuda()), k, ptr(lab),
+                                           ptr(ws), ws.numel(), _stream()), "kmeans")
+    want, _ = O.kmeans_assign(x.double(), cent.double())
+    assert torch.equal(lab.cpu(), want)
+
+
+def test_head_loss_adds_replay_loss(pkg, tmp_path):
+    """StandardMultiPrototypeReplayHead drop-in: artifacts in, mask.pth out,
+    replay_loss_cls equal to the oracle's double-softmax CE (:497-499)."""
+    feats, lab = synth.proto_features(classes=3, per_class=40, D=12544, bg=10)
+    prev, cur = tmp_path / "x_1", tmp_path / "x_2"
+    prev.mkdir(), cur.mkdir()
+    M = feats.shape[0]
+    torch.save([feats, lab, torch.ones(M), torch.zeros(M, 4), torch.zeros(M, 4),
+                torch.zeros(M, 5)], str(prev / "rois_etc.pth"))
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(12544, 6)
+
+        def forward(self, x):
+            return self.fc(x), None
+
+    torch.manual_seed(0)
+    head = pkg.StandardMultiPrototypeReplayHead(
+        bbox_head=Head().cuda(), previous_path=str(prev), task_id=2, task_split=[0, 3, 5],
+        max_prototype=10)
+    assert head.replay and os.path.exists(str(cur / "mask.pth"))
+    losses = head.loss()
+    protos, tmp_label, _ = O.build_prototypes(feats, lab, range(0, 3), max_proto=10)
+    score = head.bbox_head.fc(protos.cuda())
+    want = O.replay_loss(score.cpu(), tmp_label, 5)
+    assert abs(float(losses["replay_loss_cls"]) - float(want)) < 1e-5
