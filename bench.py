@@ -1,0 +1,536 @@
+#!/usr/bin/env python
+"""Benchmark of the NSGP-RePRE hot path (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic batch
+(VOC 19+1 incremental step, Faster R-CNN R50-FPN, 800x1333 padded to 800x1344, batch 8):
+
+  1. covariance accumulation of every hooked backbone+neck conv (61 layers,
+     1 856 algorithmic GFLOP)        - BRNullSpaceRunner.compute_cov/update_cov
+  2. one SGDNSCL.step with the null-space projection of the 50 protected layers
+     (118 algorithmic GFLOP)         - SGDNSCL.step
+  3. RePRE prototype build over M = B*512 RoI features (19 old classes) and the
+     replay gather                   - StandardMultiPrototypeReplayHead
+
+`value`   : algorithmic TFLOP/s of (1)+(2) over the whole job, layer inputs /
+            gradients / RoI features already resident in HBM, called through the
+            host mirror of the reference plug-in surface -> C ABI.
+`e2e`     : same metric with HOST inputs: pinned image batch -> H2D -> stand-in
+            detector forward with the covariance hooks registered -> SGDNSCL.step ->
+            pinned RoI features -> H2D -> prototype build -> replay gather -> D2H of
+            the step's results.  (Includes the stand-in detector's torch/cuDNN
+            forward, which is not part of the hot path - see e2e_breakdown_ms.)
+`--impl reference`: the oracle port of the reference's torch CPU path (the reference
+            itself is pure Python and /root/reference does not exist on the GPU
+            box) timed on the host cores over a bounded sample of the same layers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "nsgp_cov_projection_throughput"
+UNIT = "TFLOP/s"
+OLD_CLASSES = 19          # VOC 19+1
+ROIS_PER_IMG = 512
+FEAT_DIM = 256 * 7 * 7
+IGNORE_KEYS = ["rpn", "roi_head"]        # cl_faster_rcnn_nsgp_repre_19_1_2.py:18
+
+
+# --------------------------------------------------------------------------- layers
+def trace_layers(height, width, standin_mod):
+    """(name, Cin, H, W, k, s, p, Cout, trainable) of every hooked backbone/neck conv,
+    from a shape-only forward of the stand-in detector on the meta device."""
+    model = standin_mod.FasterRCNNStandIn(with_rpn=False, with_roi=False).to("meta")
+    recs = []
+    names = {m: n for n, m in model.named_modules()}
+
+    def hook(m, inp, out):
+        x = inp[0]
+        recs.append(dict(name=names[m], Cin=x.shape[1], H=x.shape[2], W=x.shape[3],
+                         k=m.kernel_size[0], s=m.stride[0], p=m.padding[0],
+                         Cout=m.out_channels, trainable=bool(m.weight.requires_grad)))
+
+    hs = [m.register_forward_hook(hook) for m in model.modules()
+          if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        model.eval()
+        model(torch.empty(1, 3, height, width, device="meta"))
+    for h in hs:
+        h.remove()
+    for r in recs:
+        r["Hout"] = (r["H"] + 2 * r["p"] - r["k"]) // r["s"] + 1
+        r["Wout"] = (r["W"] + 2 * r["p"] - r["k"]) // r["s"] + 1
+        r["N"] = r["Hout"] * r["Wout"]
+        r["d"] = r["Cin"] * r["k"] ** 2
+        r["cov_flops"] = 2.0 * r["N"] * r["d"] ** 2
+        r["proj_flops"] = 2.0 * r["Cout"] * r["d"] ** 2 if r["trainable"] else 0.0
+    return recs
+
+
+def synthetic_images(batch, height, width, seed):
+    """uint8 U[0,255] images normalised like the reference configs
+    (cl_faster_rcnn_nsgp_repre_19_1_2.py:30-31), pinned host fp32."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (batch, 3, height, width), generator=g, dtype=torch.uint8).float()
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
+    return ((img - mean) / std).contiguous()
+
+
+def synthetic_rois(batch, seed, device="cpu"):
+    """M = B*512 RoI features, 75 % background, every old class a
+    mixture of 3 sub-centres + 0.35 noise."""
+    g = torch.Generator().manual_seed(seed)
+    M = batch * ROIS_PER_IMG
+    lab = torch.full((M,), OLD_CLASSES, dtype=torch.int64)
+    fg = torch.randperm(M, generator=g)[: M // 4]
+    lab[fg] = torch.randint(0, OLD_CLASSES, (fg.numel(),), generator=g)
+    cent = torch.randn(OLD_CLASSES + 1, 3, FEAT_DIM, generator=g)
+    cent[OLD_CLASSES] = 0
+    which = torch.randint(0, 3, (M,), generator=g)
+    feats = cent[lab, which] + 0.35 * torch.randn(M, FEAT_DIM, generator=g)
+    return feats.contiguous(), lab
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [v.strip() for v in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                    "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm),
+                       reasons=sorted(reasons))
+        return out
+
+
+# --------------------------------------------------------------------------- CPU port
+def cpu_reference_rate(layers, budget_s, feats=None, labels=None, threads=None):
+    """Times the oracle port of the reference's torch CPU path (compute_cov +
+    update_cov, SGDNSCL.step projection, prototype build) on a bounded sample of
+    the workload's layers; returns (TFLOP/s, cores, description, seconds)."""
+    from oracle import restated as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    # spread sample: sort by cost, take every k-th layer until the budget is used
+    order = sorted(layers, key=lambda r: r["cov_flops"])
+    assumed_rate = 0.35e12 * max(1, threads) / 8          # FLOP/s guess, only for sizing
+    picked, est = [], 0.0
+    step = max(1, len(order) // 12)
+    for r in order[::step]:
+        cost = (r["cov_flops"] + r["proj_flops"]) / assumed_rate
+        if est + cost > budget_s and picked:
+            continue
+        picked.append(r)
+        est += cost
+    g = torch.Generator().manual_seed(0)
+    flops, secs = 0.0, 0.0
+    for r in picked:
+        x = torch.relu(torch.randn(1, r["Cin"], r["H"], r["W"], generator=g))
+        t0 = time.perf_counter()
+        cov = O.cov_conv2d(x, (r["k"],) * 2, (r["s"],) * 2, (r["p"],) * 2)
+        fea = {}
+        O.accumulate(fea, "k", cov)
+        O.accumulate(fea, "k", cov)
+        secs += time.perf_counter() - t0
+        flops += r["cov_flops"]
+        if r["trainable"]:
+            upd = torch.randn(r["Cout"], r["d"], generator=g)
+            P = cov / cov.norm()
+            w = torch.zeros(r["Cout"], r["d"])
+            t0 = time.perf_counter()
+            w.add_(upd @ P)
+            secs += time.perf_counter() - t0
+            flops += r["proj_flops"]
+    proto_s = None
+    if feats is not None:
+        t0 = time.perf_counter()
+        O.build_prototypes(feats, labels, range(OLD_CLASSES), 10)
+        proto_s = time.perf_counter() - t0
+    desc = ("oracle port (torch CPU fp32) of compute_cov/update_cov + projection on %d of %d "
+            "layers [%s], B=1 (covariance FLOPs do not depend on B)" %
+            (len(picked), len(layers), ", ".join(r["name"] for r in picked)))
+    return flops / secs / 1e12, threads, desc, secs, proto_s
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=800)
+    ap.add_argument("--width", type=int, default=1344)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": "VOC 19+1 incremental step, Faster R-CNN R50-FPN, synthetic "
+                          "%dx1333 (padded %dx%d) batch %d: NSGP covariance (61 backbone+neck "
+                          "layers) + SGDNSCL projection (50 layers) + RePRE prototypes "
+                          "(M=%d, %d classes)" % (args.height, args.height, args.width,
+                                                  args.batch, args.batch * ROIS_PER_IMG,
+                                                  OLD_CLASSES),
+              "batch_per_gpu": args.batch, "l2": "inputs_exceed_l2 (9 GB of layer inputs per step)",
+              "parallelism": "data-sharded x%d, one all-reduce of the covariance sums at the end"
+                             % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from nsgp_repre_b200 import standin
+        layers = trace_layers(args.height, args.width, standin)
+        per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+        rates, total_s = [], 0.0
+        desc, cores = "", 1
+        for i in range(args.warmup + args.steps):
+            r, cores, desc, secs, _ = cpu_reference_rate(layers, per_step)
+            if i >= args.warmup:
+                rates.append(r); total_s += secs
+        value = sum(rates) / len(rates)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": desc},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+    import nsgp_repre_b200 as pkg
+    from nsgp_repre_b200 import standin, _lib
+    assert pkg._lib.lib.nsgp_get_engine() == 0
+
+    torch.manual_seed(1234)
+    model = standin.FasterRCNNStandIn(with_rpn=False, with_roi=False).to(dev).eval()
+    layers = trace_layers(args.height, args.width, standin)
+    modules = dict(model.named_modules())
+    cov_flops = sum(r["cov_flops"] for r in layers)
+    proj_flops = sum(r["proj_flops"] for r in layers)
+    step_flops = cov_flops + proj_flops
+
+    # host inputs (pinned) and their device-resident copies
+    images_h = synthetic_images(args.batch, args.height, args.width, 1000 * rank).pin_memory()
+    feats_h, labels_h = synthetic_rois(args.batch, 7 + rank)
+    feats_h = feats_h.pin_memory()
+    labels_h = labels_h.pin_memory()
+
+    # layer inputs of one forward of the random-init detector, kept resident in HBM
+    layer_inputs = {}
+    names = {m: n for n, m in model.named_modules()}
+    cap = [m.register_forward_hook(
+        lambda m, i, o: layer_inputs.__setitem__(names[m], i[0].detach().contiguous()))
+        for m in model.modules() if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        model(images_h.to(dev, non_blocking=True))
+    for h in cap:
+        h.remove()
+    torch.cuda.synchronize()
+    input_bytes = sum(t.numel() * 4 for t in layer_inputs.values())
+
+    hooks = pkg.CovarianceHooks(model, ignore_keys=IGNORE_KEYS)
+    hooked = [(r["name"], modules[r["name"]]) for r in layers]
+
+    def cov_pass():
+        for n, m in hooked:
+            hooks.compute_cov(m, (layer_inputs[n],), None)
+
+    # projector build (task boundary, outside the hot path): one covariance pass,
+    # GPU syevd, adaptive threshold, P = V0 V0^T
+    t0 = time.perf_counter()
+    cov_pass()
+    fea = hooks.fea_in
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    opt = pkg.SGDNSCL([p for _, p in named], lr=0.02, momentum=0.9, weight_decay=1e-4, svd=True)
+    opt.param_groups[0]["names"] = [n for n, _ in named]
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    opt.get_eigens(fea)
+    opt.get_transforms(offset=0.0)
+    torch.cuda.synchronize()
+    projector_build_s = time.perf_counter() - t1
+    n_protected = len(opt.transforms)
+    del fea
+    hooks.reset()
+    g = torch.Generator(device=dev).manual_seed(1)
+    grads = {n: torch.randn(p.shape, device=dev, generator=g) for n, p in named}
+
+    feats_d = feats_h.to(dev)
+    labels_d = labels_h.to(dev)
+    proto = pkg.MultiPrototypeReplay(max_prototype=10)
+
+    for n, p in named:
+        p.grad = grads[n]            # as left by backward(); step() adds wd*w in place
+
+    def sgd_step():
+        opt.step()
+
+    def repre_step(f, l):
+        proto.build(f, l, range(OLD_CLASSES))
+        return proto.staged()
+
+    def hot_step():
+        cov_pass()
+        sgd_step()
+        repre_step(feats_d, labels_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count() - n0
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    total_ms, launches = timed(hot_step, args.steps, args.warmup)
+    clk = clocks.stop()
+    ms_per_step = total_ms / args.steps
+
+    # the one collective of this path: SUM all-reduce of the covariance sums (once per
+    # task, nsrunner_roi_replay.py:746-749) - timed separately, not per step
+    allreduce_ms = None
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hooks.all_reduce()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(t.item())
+
+    # per-phase device times + the roofline of the dominant kernel (event pairs
+    # around every launch of that kind, on the launch stream)
+    def phase_ms(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    cov_ms = phase_ms(cov_pass)
+    sgd_ms = phase_ms(sgd_step)
+    repre_ms = phase_ms(lambda: repre_step(feats_d, labels_d))
+    torch.cuda.synchronize()
+    _lib.profile_read()
+    _lib.profile_enable(True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        hot_step()
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    gram_ms, gram_n = prof["gram"]
+    gram_ms_step = gram_ms / prof_steps
+    tf32_peak = None
+    hbm_peak = None
+    peaks_src = "fallback"
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        hbm_peak = pk["hbm_gbs"]
+        peaks_src = "measured (MEASURED_PEAKS.json: bf16_tflops_sustained/2 - tf32 runs at half the bf16 rate)"
+    except Exception:
+        tf32_peak, hbm_peak = 1400.0 / 2.0, 6650.0
+    # issued tensor work: upper block-triangle of 128x128 tiles, 3 tf32 products each,
+    # K padded to 32-wide blocks per staged row
+    issued = 0.0
+    for r in layers:
+        tiles = -(-r["d"] // 128)
+        pairs = tiles * (tiles + 1) // 2
+        kpad = (r["Hout"] * (-(-r["Wout"] // 32)) * 32) if r["k"] > 1 and r["Cin"] % 8 == 0 \
+            else (-(-r["N"] // 32) * 32)
+        issued += pairs * 3 * 2.0 * 128 * 128 * kpad
+    achieved = cov_flops / (gram_ms_step * 1e-3) / 1e12
+    roofline = {"kernel": "contraction_tc_kernel<128,Gram> (tcgen05 kind::tf32, 3xTF32)",
+                "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": None,
+                "peak_source": peaks_src,
+                "launches_per_step": gram_n / prof_steps, "ms_per_step": gram_ms_step,
+                "issued_tflops": issued / (gram_ms_step * 1e-3) / 1e12,
+                "issued_frac": issued / (gram_ms_step * 1e-3) / 1e12 / tf32_peak,
+                "note": "achieved = algorithmic 2*N*d^2 FLOPs of the 61 layers / summed Gram "
+                        "kernel time; issued = tf32 MMA FLOPs actually issued (3 products, "
+                        "upper block-triangle, padded K)"}
+    kernel_ms = {k: v[0] / prof_steps for k, v in prof.items()}
+
+    # RePRE statistics as bandwidth: algorithmic bytes = one read of F + prototypes out
+    repre_bytes = feats_d.numel() * 4 + labels_d.numel() * 8
+    repre_gbs = repre_bytes / (repre_ms * 1e-3) / 1e9
+
+    # ------------------------------------------------------------------ e2e
+    e2e = None
+    breakdown = None
+    if not args.no_e2e:
+        hooks.remove()
+        hooks.register()
+        img_d = torch.empty_like(images_h, device=dev)
+        f_d = torch.empty_like(feats_h, device=dev)
+        l_d = torch.empty_like(labels_h, device=dev)
+        res_h = torch.empty(4, dtype=torch.float32).pin_memory()
+        lab_out_h = torch.empty(10 * OLD_CLASSES, dtype=torch.int64).pin_memory()
+        key0 = "backbone.layer2.0.conv1.weight"
+
+        def e2e_step():
+            img_d.copy_(images_h, non_blocking=True)
+            with torch.no_grad():
+                model(img_d)                          # hooks fire: 61 covariance updates
+            sgd_step()
+            f_d.copy_(feats_h, non_blocking=True)
+            l_d.copy_(labels_h, non_blocking=True)
+            staged = repre_step(f_d, l_d)
+            res = torch.stack([staged.sum(), staged[0, 0],
+                               hooks._layers[key0].acc[:16].sum(), named[-1][1].sum()])
+            res_h.copy_(res, non_blocking=True)
+            n = proto.tmp_label.numel()
+            lab_out_h[:n].copy_(proto.tmp_label, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_ms, _ = timed(e2e_step, args.steps, max(1, args.warmup))
+        hooks.remove()
+        e2e_ms_step = e2e_ms / args.steps
+        # forward without hooks, for the breakdown
+        fwd_ms = phase_ms(lambda: model(img_d))
+        h2d = images_h.numel() * 4 + feats_h.numel() * 4 + labels_h.numel() * 8
+        d2h = res_h.numel() * 4 + proto.tmp_label.numel() * 8
+        e2e = {"value": world * step_flops / (e2e_ms_step * 1e-3) / 1e12, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms_step}
+        breakdown = {"standin_detector_forward_no_hooks": fwd_ms, "covariance_hooks": cov_ms,
+                     "sgdnscl_step": sgd_ms, "repre_build_gather": repre_ms,
+                     "note": "stand-in detector forward is torch/cuDNN, outside the hot path"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r, cores, desc, secs, proto_s = cpu_reference_rate(layers, args.cpu_budget_s,
+                                                           feats_h, labels_h)
+        cpu_baseline = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": desc + "; %.1f s of CPU work" % secs,
+                        "repre_prototype_build_s": proto_s}
+
+    value = world * step_flops / (ms_per_step * 1e-3) / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": config, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "phase_ms": {"covariance_61_layers": cov_ms, "sgdnscl_step_projection": sgd_ms,
+                         "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms},
+            "kernel_ms_per_step": kernel_ms,
+            "tflops": {"covariance_algorithmic": cov_flops / (cov_ms * 1e-3) / 1e12,
+                       "projection_algorithmic": proj_flops / (sgd_ms * 1e-3) / 1e12},
+            "repre_stats": {"GB/s": repre_gbs, "bytes": repre_bytes, "peak_GB/s": hbm_peak,
+                            "frac": repre_gbs / hbm_peak},
+            "e2e_breakdown_ms": breakdown,
+            "algorithmic_gflop_per_step": {"covariance": cov_flops / 1e9,
+                                           "projection": proj_flops / 1e9},
+            "projector_build_s": projector_build_s, "protected_layers": n_protected,
+            "layer_input_bytes": input_bytes}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,15 @@ unsigned long long nsgp_launch_count(void);
 int nsgp_set_engine(int engine);
 int nsgp_get_engine(void);
 
+/* Optional device timing per kernel kind (bench.py's roofline leg): when enabled,
+ * every launch of that kind is bracketed by a cudaEvent pair on its stream.
+ * kinds: 0 Gram contraction (tcgen05), 1 GEMM contraction (tcgen05), 2 staging,
+ * 3 SGD prologue, 4 RePRE statistics.  nsgp_profile_read synchronises, returns the
+ * summed milliseconds and launch count since the last read, and clears them. */
+int nsgp_profile_enable(int on);
+int nsgp_profile_read(int kind, double* ms_total /* host */,
+                      unsigned long long* launches /* host */);
+
 /* ------------------------------------------------------------------------- *
  * a1/a2  per-layer input covariance
  *   replaces BRNullSpaceRunner.compute_cov + update_cov

@@ -40,6 +40,8 @@ SIGNATURES = {
     "nsgp_launch_count": (C.c_ulonglong, []),
     "nsgp_set_engine": (c_int, [c_int]),
     "nsgp_get_engine": (c_int, []),
+    "nsgp_profile_enable": (c_int, [c_int]),
+    "nsgp_profile_read": (c_int, [c_int, C.POINTER(c_double), C.POINTER(C.c_ulonglong)]),
     "nsgp_cov_conv2d_layout": (c_int, [c_int] * 9 + [C.POINTER(CovLayout)]),
     "nsgp_cov_linear_layout": (c_int, [c_int, C.POINTER(CovLayout)]),
     "nsgp_cov_conv2d_accumulate": (c_int, [c_void_p] + [c_int] * 10 +
@@ -102,6 +104,23 @@ def current_stream(device=None) -> int:
 def require_cuda(t, name="tensor"):
     if not t.is_cuda:
         raise NsgpError("%s must live on a CUDA device (there is no CPU fallback)" % name)
+
+
+PROFILE_KINDS = {"gram": 0, "gemm": 1, "stage": 2, "sgd": 3, "repre": 4}
+
+
+def profile_enable(on: bool) -> None:
+    lib.nsgp_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{kind: (milliseconds, launches)} accumulated since the last read."""
+    out = {}
+    for name, k in PROFILE_KINDS.items():
+        ms, n = c_double(0.0), C.c_ulonglong(0)
+        check(lib.nsgp_profile_read(k, C.byref(ms), C.byref(n)), "nsgp_profile_read")
+        out[name] = (ms.value, int(n.value))
+    return out
 
 
 def launch_count() -> int:

@@ -15,6 +15,25 @@ static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 int g_engine = 0;
 
+int g_profile = 0;
+namespace {
+struct ProfRec { cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof[kProfKinds];
+cudaEvent_t g_prof_open[kProfKinds];
+}
+void profile_begin(int kind, cudaStream_t s) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_prof_open[kind] = e;
+}
+void profile_end(int kind, cudaStream_t s) {
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_prof[kind].push_back({g_prof_open[kind], e});
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -54,6 +73,29 @@ int nsgp_set_engine(int engine) {
   return prev;
 }
 int nsgp_get_engine(void) { return g_engine; }
+
+int nsgp_profile_enable(int on) {
+  int prev = g_profile;
+  g_profile = on ? 1 : 0;
+  return prev;
+}
+
+int nsgp_profile_read(int kind, double* ms_total, unsigned long long* launches) {
+  NSGP_REQUIRE(kind >= 0 && kind < kProfKinds && ms_total && launches, "profile_read: bad arguments");
+  double total = 0.0;
+  for (auto& r : g_prof[kind]) {
+    NSGP_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    NSGP_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    total += ms;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  *ms_total = total;
+  *launches = g_prof[kind].size();
+  g_prof[kind].clear();
+  return 0;
+}
 
 // ---------------------------------------------------------------- covariance
 int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,

@@ -36,6 +36,20 @@ extern unsigned long long g_launches;   // kernels launched by this library
     NSGP_CHECK_CUDA(cudaGetLastError());                                          \
   } while (0)
 
+// ---- optional per-kernel-kind device timing (bench.py's roofline leg) --------
+// When enabled every launch of a profiled kind is bracketed by a cudaEvent pair on
+// the launch stream; nsgp_profile_read synchronises and sums them.
+enum ProfKind : int { kProfGram = 0, kProfGemm = 1, kProfStage = 2, kProfSgd = 3,
+                      kProfRepre = 4, kProfKinds = 5 };
+extern int g_profile;
+void profile_begin(int kind, cudaStream_t s);
+void profile_end(int kind, cudaStream_t s);
+struct ProfScope {
+  int kind; cudaStream_t s;
+  ProfScope(int k, cudaStream_t st) : kind(k), s(st) { if (g_profile) profile_begin(kind, s); }
+  ~ProfScope() { if (g_profile) profile_end(kind, s); }
+};
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 

@@ -459,6 +459,7 @@ int launch_tc(const TcMaps& maps, const TcParams& p, cudaStream_t stream) {
   }
   int items = p.n_tiles * p.splits;
   int grid = items < sm_count() ? items : sm_count();
+  ProfScope prof(EPI == kEpiGramAtomic ? kProfGram : kProfGemm, stream);
   kern<<<grid, kThreads, smem, stream>>>(maps, p);
   NSGP_LAUNCHED();
   return 0;

@@ -148,6 +148,7 @@ int launch_segment_mean(const float* F, int D, const int* seg_off, const int* ro
   if (splits > 1)
     NSGP_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)nseg * D * sizeof(float), stream));
   dim3 grid(chunks, nseg, splits);
+  ProfScope prof(kProfRepre, stream);
   if (mode == 1)
     segment_mean_kernel<1><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out);
   else

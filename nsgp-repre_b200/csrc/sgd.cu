@@ -62,6 +62,7 @@ int launch_sgd_prologue(const SgdTensorDev* tensors_dev, const int* chunk_start_
                         int n_tensors, int total_chunks, float lr, float momentum,
                         float one_minus_damp, float wd, int nesterov, cudaStream_t stream) {
   if (total_chunks == 0) return 0;
+  ProfScope prof(kProfSgd, stream);
   sgd_prologue_kernel<<<total_chunks, 256, 0, stream>>>(
       tensors_dev, chunk_start_dev, n_tensors, lr, momentum, one_minus_damp, wd, nesterov);
   NSGP_LAUNCHED();

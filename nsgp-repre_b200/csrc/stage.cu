@@ -102,6 +102,7 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
+  ProfScope prof(kProfStage, stream);
   if (g.mode == kModeExplicit)
     stage_conv_explicit_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
   else
