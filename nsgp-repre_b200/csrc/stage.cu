@@ -57,6 +57,127 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
 }
 
 // ---------------------------------------------------------------------------
+// Fast paths (same staged layout as stage_conv_kernel, 128-bit loads and stores).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void split_store4(float* hi, float* lo, float a, float b, float c,
+                                             float d) {
+  float4 h, l;
+  tf32_split(a, h.x, l.x);
+  tf32_split(b, h.y, l.y);
+  tf32_split(c, h.z, l.z);
+  tf32_split(d, h.w, l.w);
+  *reinterpret_cast<float4*>(hi) = h;
+  *reinterpret_cast<float4*>(lo) = l;
+}
+
+// 1x1 stride-1 conv input with H*W % 4 == 0: the staged plane is the batch mean of
+// x itself.  One thread per float4.
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, long long n4,
+                      int B, long long img, long long hl_stride) {
+  const float inv_div = (float)B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* p = x + i * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int b = 0;
+    for (; b + B_UNROLL <= B; b += B_UNROLL) {
+      float4 v[B_UNROLL];
+#pragma unroll
+      for (int u = 0; u < B_UNROLL; ++u) v[u] = ldg_stream4(p + (long long)(b + u) * img);
+#pragma unroll
+      for (int u = 0; u < B_UNROLL; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; b < B; ++b) {
+      float4 v = ldg_stream4(p + (long long)b * img);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    split_store4(stage + i * 4, stage + i * 4 + hl_stride, s.x / inv_div, s.y / inv_div,
+                 s.z / inv_div, s.w / inv_div);
+  }
+}
+
+// 3x3 stride-1 pad-1 conv input with W % 4 == 0: each thread averages one aligned
+// float4 of the input row and writes it to the three column-shifted copies; the
+// +-1 neighbours come from the adjacent lanes (or one extra scalar load at the
+// warp / row edges).  Halo rows (r = 0, Hs-1) are written as zeros.
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                       int W, int B, long long hl_stride) {
+  const int W4 = W >> 2, Hs = H + 2;
+  const long long total = (long long)C * Hs * W4;
+  const long long img = (long long)C * H * W;
+  const long long copy_stride = (long long)C * Hs * W;
+  const float fb = (float)B;
+  const int lane = threadIdx.x & 31;
+  // every lane of a warp runs the same number of iterations (shuffles below)
+  const long long total_r = (total + 31) / 32 * 32;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_r;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const bool live = idx < total;
+    int x4 = 0, r = 0, c = 0;
+    if (live) {
+      x4 = (int)(idx % W4);
+      long long rest = idx / W4;
+      r = (int)(rest % Hs);
+      c = (int)(rest / Hs);
+    }
+    const int y = r - 1;
+    const bool row_ok = live && y >= 0 && y < H;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = x + ((long long)c * H + y) * W + x4 * 4;
+    if (row_ok) {
+      int b = 0;
+      for (; b + B_UNROLL <= B; b += B_UNROLL) {
+        float4 v[B_UNROLL];
+#pragma unroll
+        for (int u = 0; u < B_UNROLL; ++u) v[u] = ldg_stream4(p + (long long)(b + u) * img);
+#pragma unroll
+        for (int u = 0; u < B_UNROLL; ++u) { m.x += v[u].x; m.y += v[u].y; m.z += v[u].z; m.w += v[u].w; }
+      }
+      for (; b < B; ++b) {
+        float4 v = ldg_stream4(p + (long long)b * img);
+        m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+      }
+      m.x /= fb; m.y /= fb; m.z /= fb; m.w /= fb;
+    }
+    // neighbours: left = mean at x-1, right = mean at x+4 (same row)
+    float left = __shfl_up_sync(0xffffffffu, m.w, 1);
+    float right = __shfl_down_sync(0xffffffffu, m.x, 1);
+    if (row_ok) {
+      if (x4 == 0) left = 0.f;
+      else if (lane == 0) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += __ldg(p - 1 + (long long)b * img);
+        left = s / fb;
+      }
+      if (x4 == W4 - 1) right = 0.f;
+      else if (lane == 31) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += __ldg(p + 4 + (long long)b * img);
+        right = s / fb;
+      }
+    } else {
+      left = right = 0.f;
+    }
+    if (live) {
+      float* o = stage + ((long long)c * Hs + r) * W + x4 * 4;
+      split_store4(o, o + hl_stride, left, m.x, m.y, m.z);                                  // j = 0
+      split_store4(o + copy_stride, o + copy_stride + hl_stride, m.x, m.y, m.z, m.w);      // j = 1
+      split_store4(o + 2 * copy_stride, o + 2 * copy_stride + hl_stride, m.y, m.z, m.w, right);  // j = 2
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Explicit im2col fallback (any kernel size / dilation-free conv whose channel
 // count does not fit the implicit path, e.g. the 7x7 stem with Cin = 3).
 // Rows are written directly in the reference's (Cin, kh, kw) order.
@@ -99,14 +220,29 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
   long long total = (g.mode == kModeExplicit) ? (long long)g.Cs * g.Ws
                                               : (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
   long long hl = stage_hl_stride(g);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  if (blocks < 1) blocks = 1;
+  const long long img = (long long)g.C * g.H * g.W;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && img % 4 == 0;
   ProfScope prof(kProfStage, stream);
-  if (g.mode == kModeExplicit)
-    stage_conv_explicit_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
-  else
-    stage_conv_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+  if (g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && aligned && (g.H * g.W) % 4 == 0) {
+    long long n4 = (long long)g.C * g.H * g.W / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    stage_flat_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, n4, B, img, hl);
+  } else if (g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 &&
+             g.ph == 1 && g.pw == 1 && aligned && g.W % 4 == 0) {
+    long long n = (long long)g.C * g.Hs * (g.W / 4);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    stage_3x3s1_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl);
+  } else {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    if (g.mode == kModeExplicit)
+      stage_conv_explicit_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+    else
+      stage_conv_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+  }
   NSGP_LAUNCHED();
   return 0;
 }

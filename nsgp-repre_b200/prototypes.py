@@ -14,6 +14,7 @@ from __future__ import annotations
 import os
 import os.path as osp
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -47,6 +48,7 @@ class MultiPrototypeReplay:
         self.save_idx = None
         self.sigma = None
         self._out = None
+        self._ws = None
 
     # ------------------------------------------------------------------ build
     @torch.no_grad()
@@ -78,69 +80,89 @@ class MultiPrototypeReplay:
                                     stream), "repre_class_index")
         h_off = offsets.cpu().tolist()
 
-        # neighbour masks / counts of every class, launched back to back
-        per_class = {}
-        ws = None
+        # neighbour masks / counts of every class, launched back to back into ONE
+        # device buffer [masks | counts | rows] that comes back in a single D2H copy
+        sizes = []
         for c in previous_cls:
             n = h_off[c + 1] - h_off[c]
             if n == 0:
                 # the reference dies in sim_sum[-0//3] (:422); keep that contract
                 raise IndexError("class %d has no stored RoI feature "
                                  "(index 0 is out of bounds for dimension 0 with size 0)" % c)
-            need = lib.repre_cosine_count_workspace_bytes(n, D)
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
-            mask = torch.empty(n, n, dtype=torch.uint8, device=dev)
-            cnt = torch.empty(n, dtype=torch.int32, device=dev)
+            sizes.append(n)
+        mask_bytes = sum(n * n for n in sizes)
+        mask_pad = (mask_bytes + 15) // 16 * 16
+        cnt_elems = sum(sizes)
+        pack = torch.empty(mask_pad + 4 * cnt_elems + 4 * max(M, 1), dtype=torch.uint8,
+                           device=dev)
+        cnt_all = pack[mask_pad:mask_pad + 4 * cnt_elems].view(torch.int32)
+        pack[mask_pad + 4 * cnt_elems:].view(torch.int32).copy_(rows)
+        need = max(lib.repre_cosine_count_workspace_bytes(n, D) for n in sizes)
+        ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
+            self._ws.device == dev else torch.empty(int(need), dtype=torch.uint8, device=dev)
+        self._ws = ws
+        m_off = c_off = 0
+        for c, n in zip(previous_cls, sizes):
             check(lib.repre_cosine_count(
                 ptr(feats), D, rows.data_ptr() + 4 * h_off[c], n, float(self.thresh),
-                ptr(mask), ptr(cnt), None, ptr(ws), ws.numel(), stream), "repre_cosine_count")
-            per_class[c] = (mask, cnt)
+                pack.data_ptr() + m_off, cnt_all.data_ptr() + 4 * c_off, None, ptr(ws),
+                ws.numel(), stream), "repre_cosine_count")
+            m_off += n * n
+            c_off += n
+        host = pack.cpu().numpy()                                   # the one sync
+        h_cnt = host[mask_pad:mask_pad + 4 * cnt_elems].view(np.int32)
+        h_rows_np = host[mask_pad + 4 * cnt_elems:].view(np.int32)
 
         # host: density order + greedy cover (sequential, <= max_proto-1 picks)
         seg_rows, seg_off, seg_label = [], [0], []
-        h_rows = rows.cpu()
-        for c in previous_cls:
-            mask_d, cnt_d = per_class[c]
-            sim_mask = mask_d.cpu().bool()
-            cnt = cnt_d.cpu().long()
-            cls_rows = h_rows[h_off[c]:h_off[c + 1]]
+        m_off = c_off = 0
+        for c, n in zip(previous_cls, sizes):
+            sim_mask = host[m_off:m_off + n * n].reshape(n, n).astype(bool)
+            cnt_np = h_cnt[c_off:c_off + n]
+            m_off += n * n
+            c_off += n
+            cls_rows = h_rows_np[h_off[c]:h_off[c + 1]]
             # coarse prototype: all rows of the class (:412-414)
             seg_rows.append(cls_rows)
-            seg_off.append(seg_off[-1] + cls_rows.numel())
+            seg_off.append(seg_off[-1] + n)
             seg_label.append(c)
-            sim_sum, idx = cnt.sort(dim=-1, descending=True)             # :421
-            thr = sim_sum[-sim_sum.shape[0] // 3]                        # :422
-            covered = cnt <= thr                                         # :423
+            # torch's CPU sort, the call the reference makes, so ties order identically
+            sim_sum, idx = torch.from_numpy(cnt_np.astype(np.int64)).sort(dim=-1, descending=True)  # :421
+            thr = int(sim_sum[-n // 3])                                  # :422
+            covered = cnt_np <= thr                                      # :423
+            idx_np = idx.numpy()
             tmp_mask = save_idx[c] if c < len(save_idx) else []          # :425-428
             for proto_count in range(self.max_proto - 1):                # :430
-                for id_ in idx.tolist():
-                    if proto_count < len(tmp_mask):
-                        m = tmp_mask[proto_count].cpu().bool()
-                    else:
-                        if covered[id_]:
-                            continue
-                        m = sim_mask[id_]
-                        tmp_mask.append(m)
-                    covered = torch.logical_or(covered, m)
-                    sel = cls_rows[m]
-                    seg_rows.append(sel)
-                    seg_off.append(seg_off[-1] + sel.numel())
-                    seg_label.append(c)
-                    break
+                if proto_count < len(tmp_mask):                          # replayed mask.pth entry
+                    m = tmp_mask[proto_count].cpu().numpy().astype(bool)
+                else:
+                    cand = idx_np[~covered[idx_np]]
+                    if cand.size == 0:
+                        continue
+                    m = sim_mask[cand[0]]
+                    tmp_mask.append(torch.from_numpy(m.copy()))
+                covered = covered | m
+                sel = cls_rows[m]
+                seg_rows.append(sel)
+                seg_off.append(seg_off[-1] + sel.size)
+                seg_label.append(c)
             if c >= len(save_idx):
                 save_idx.append(tmp_mask)
 
         # one launch: coarse + fine means of every class
-        all_rows = torch.cat(seg_rows).to(torch.int32).to(dev)
-        off_t = torch.tensor(seg_off, dtype=torch.int32, device=dev)
         nseg = len(seg_label)
+        idx_host = np.concatenate([np.asarray(seg_off, dtype=np.int32),
+                                   np.asarray(seg_label, dtype=np.int32)] +
+                                  [r.astype(np.int32, copy=False) for r in seg_rows])
+        idx_dev = torch.from_numpy(idx_host).to(dev)                 # one H2D copy
+        off_t = idx_dev[:nseg + 1]
+        all_rows = idx_dev[2 * nseg + 1:]
         out = torch.empty(nseg, D, dtype=torch.float32, device=dev)
         max_rows = max(b - a for a, b in zip(seg_off[:-1], seg_off[1:]))
         check(lib.repre_segment_mean(ptr(feats), D, ptr(off_t), ptr(all_rows), nseg,
                                      int(max_rows), ptr(out), stream), "repre_segment_mean")
         self.bbox_featss = out
-        self.tmp_label = torch.tensor(seg_label, dtype=torch.long, device=dev)
+        self.tmp_label = idx_dev[nseg + 1:2 * nseg + 1].to(torch.int64)
         self.save_idx = save_idx
         self._segments = (off_t, all_rows, max_rows)
         self._feats = feats
