@@ -69,26 +69,21 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
 
 // ---- K-major virtual operand ---------------------------------------------------
 // Both engines (SIMT bring-up and tcgen05) consume operands described this way.
-// A virtual matrix of `rows` = T * Cs rows and K = Kh * Kw columns is backed by
-// staged planes  stage[hl][plane][Cs][Hs][Ws]  (hl: 0 = tf32 hi part, 1 = lo part).
-// Row r = t * Cs + c (tap-major).  Column k = (krow, kx):
-//     element = stage[hl][tap_plane[t]][c][krow + tap_yoff[t]][kx + tap_xoff[t]]
-//               if kx + tap_xoff[t] < tap_ext[t] else 0
-// Plain row-major matrices are the T = 1, Kh = 1 special case.
+// A virtual matrix of `rows` = T * Cs rows and K columns: row r = t * Cs + c
+// (tap-major) is the K contiguous fp32 words at
+//     base + hl * hl_stride + tap_off[t] + c * row_pitch          (hl: 0 = tf32 hi, 1 = lo)
+// and reads as zero for k >= K.  Plain row-major matrices are the T = 1 case; the
+// staged conv layouts (geometry.h) put every tap at its own offset.
 constexpr int kMaxTaps = 9;
 
 struct Operand {
-  const float* base;       // stage base (hi part of plane 0)
+  const float* base;       // hi part
   long long hl_stride;     // elements between the hi and the lo copy
-  long long plane_stride;  // elements between planes (= Cs*Hs*Ws)
+  long long row_pitch;     // elements between consecutive rows c of one tap (% 4 == 0)
   int T, Cs;               // taps, rows per tap
-  int Hs, Ws;              // plane height / row pitch (elements, Ws % 4 == 0)
-  int Kh, Kw;              // K space: Kh rows of Kw valid columns
+  int K;                   // valid columns
   int rows;                // valid virtual rows (<= T*Cs)
-  int tap_plane[kMaxTaps];
-  int tap_yoff[kMaxTaps];
-  int tap_xoff[kMaxTaps];
-  int tap_ext[kMaxTaps];
+  long long tap_off[kMaxTaps];   // element offset of tap t (% 4 == 0)
 };
 
 // Epilogue of the contraction engines.
@@ -114,6 +109,6 @@ int contraction(const ContractionArgs& a, cudaStream_t stream);         // dispa
 extern int g_engine;   // 0 = tcgen05 (product), 1 = SIMT (bring-up / cross-check)
 
 // number of 32-wide K blocks of an operand
-static inline int k_blocks(const Operand& o) { return o.Kh * ceil_div(o.Kw, 32); }
+static inline int k_blocks(const Operand& o) { return ceil_div(o.K, 32); }
 
 }  // namespace nsgp

@@ -6,14 +6,10 @@
 
 namespace nsgp {
 
-__device__ __forceinline__ float fetch(const Operand& o, int row, int kb, int kk, int nxc) {
-  if (row >= o.rows) return 0.f;
+__device__ __forceinline__ float fetch(const Operand& o, int row, int k) {
+  if (row >= o.rows || k >= o.K) return 0.f;
   int t = row / o.Cs, c = row - t * o.Cs;
-  int krow = kb / nxc, kx = (kb - krow * nxc) * 32 + kk;
-  int xs = kx + o.tap_xoff[t];
-  if (xs >= o.tap_ext[t]) return 0.f;
-  const float* p = o.base + (long long)o.tap_plane[t] * o.plane_stride +
-                   ((long long)c * o.Hs + krow + o.tap_yoff[t]) * o.Ws + xs;
+  const float* p = o.base + o.tap_off[t] + (long long)c * o.row_pitch + k;
   return __ldg(p) + __ldg(p + o.hl_stride);
 }
 
@@ -35,8 +31,7 @@ contraction_simt_kernel(const __grid_constant__ ContractionArgs a, int tiles_n) 
     cb = blockIdx.x - rb * tiles_n;
   }
   const int r0 = rb * 64, c0 = cb * 64;
-  const int nxc = (a.A.Kw + 31) / 32;
-  const int nkb = a.A.Kh * nxc;
+  const int nkb = (a.A.K + 31) / 32;
   const int kb0 = (int)((long long)nkb * blockIdx.y / gridDim.y);
   const int kb1 = (int)((long long)nkb * (blockIdx.y + 1) / gridDim.y);
   const int ty = tid >> 4, tx = tid & 15;
@@ -46,8 +41,8 @@ contraction_simt_kernel(const __grid_constant__ ContractionArgs a, int tiles_n) 
     for (int e = 0; e < 8; ++e) {
       int lin = tid + e * 256;
       int row = lin >> 5, kk = lin & 31;
-      As[kk][row] = fetch(a.A, r0 + row, kb, kk, nxc);
-      Bs[kk][row] = fetch(a.B, c0 + row, kb, kk, nxc);
+      As[kk][row] = fetch(a.A, r0 + row, kb * 32 + kk);
+      Bs[kk][row] = fetch(a.B, c0 + row, kb * 32 + kk);
     }
     __syncthreads();
 #pragma unroll 8

@@ -90,32 +90,31 @@ static inline size_t stage_bytes(const ConvGeom& g) {
   return (size_t)stage_hl_stride(g) * 2 * sizeof(float);
 }
 
-// Virtual K-major operand over the staged planes.
+// Virtual K-major operand over the staged planes.  Implicit mode: K is the FLAT
+// index oy * Ws + x over the staged rows (the < 4 padding columns per row are staged
+// as zeros), so tap (i, j) is simply the copy's plane shifted by yoff_i rows.
 static inline Operand conv_operand(const ConvGeom& g, const float* stage) {
   Operand o{};
   o.base = stage;
   o.hl_stride = stage_hl_stride(g);
-  o.plane_stride = (long long)g.Cs * g.Hs * g.Ws;
-  o.T = g.T; o.Cs = g.Cs; o.Hs = g.Hs; o.Ws = g.Ws;
+  o.T = g.T; o.Cs = g.Cs;
   if (g.mode == kModeImplicit) {
-    o.Kh = g.Hout; o.Kw = g.Wout;
+    const long long plane = (long long)g.Cs * g.Hs * g.Ws;
+    o.row_pitch = (long long)g.Hs * g.Ws;
+    o.K = g.Hout * g.Ws;
     o.rows = g.T * g.Cs;
     for (int i = 0; i < g.kh; ++i) {
       int ay = i - g.ph;
       int qy = floor_div(ay, g.sh), py = pos_mod(ay, g.sh), p = 0;
       while (g.rowphase_py[p] != py) ++p;
-      for (int j = 0; j < g.kw; ++j) {
-        int t = i * g.kw + j;
-        o.tap_plane[t] = p * g.kw + j;
-        o.tap_yoff[t] = qy + g.Ht;
-        o.tap_xoff[t] = 0;
-        o.tap_ext[t] = g.Wout;   // columns past the last valid output read 0
-      }
+      for (int j = 0; j < g.kw; ++j)
+        o.tap_off[i * g.kw + j] = (long long)(p * g.kw + j) * plane + (long long)(qy + g.Ht) * g.Ws;
     }
   } else {
-    o.Kh = 1; o.Kw = g.Hout * g.Wout;
+    o.row_pitch = g.Ws;
+    o.K = g.Hout * g.Wout;
     o.rows = (g.mode == kModeExplicit) ? g.d : g.Cs;
-    o.tap_plane[0] = 0; o.tap_yoff[0] = 0; o.tap_xoff[0] = 0; o.tap_ext[0] = o.Kw;
+    o.tap_off[0] = 0;
   }
   return o;
 }
@@ -125,9 +124,9 @@ static inline Operand matrix_operand(const float* hi, const float* lo, int rows,
   Operand o{};
   o.base = hi;
   o.hl_stride = (long long)(lo - hi);
-  o.plane_stride = 0;
-  o.T = 1; o.Cs = rows; o.Hs = 1; o.Ws = ld; o.Kh = 1; o.Kw = K; o.rows = rows;
-  o.tap_plane[0] = 0; o.tap_yoff[0] = 0; o.tap_xoff[0] = 0; o.tap_ext[0] = K;
+  o.row_pitch = ld;
+  o.T = 1; o.Cs = rows; o.K = K; o.rows = rows;
+  o.tap_off[0] = 0;
   return o;
 }
 

@@ -1,0 +1,34 @@
+"""Micro-benchmark of the covariance call (stage + Gram) on one layer geometry.
+usage: bench_gram.py Cin H W k s p [B]   -> per-kernel ms and TFLOP/s (algorithmic, issued)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import nsgp_repre_b200 as pkg
+from nsgp_repre_b200 import _lib
+
+Cin, H, W, k, s, p = [int(v) for v in sys.argv[1:7]]
+B = int(sys.argv[7]) if len(sys.argv) > 7 else 8
+x = torch.relu(torch.randn(B, Cin, H, W, device="cuda"))
+hooks = pkg.CovarianceHooks(torch.nn.Identity())
+for _ in range(3):
+    hooks._accumulate_conv(x, "k", (k, k), (s, s), (p, p))
+torch.cuda.synchronize()
+_lib.profile_read()
+_lib.profile_enable(True)
+reps = 10
+for _ in range(reps):
+    hooks._accumulate_conv(x, "k", (k, k), (s, s), (p, p))
+torch.cuda.synchronize()
+_lib.profile_enable(False)
+prof = _lib.profile_read()
+Hout = (H + 2 * p - k) // s + 1
+Wout = (W + 2 * p - k) // s + 1
+N, d = Hout * Wout, Cin * k * k
+flops = 2.0 * N * d * d
+g = prof["gram"][0] / reps
+st = prof["stage"][0] / reps
+tiles = -(-d // 128)
+kpad = Hout * (-(-Wout // 32)) * 32 if k > 1 else -(-N // 32) * 32
+issued = tiles * (tiles + 1) / 2 * 3 * 2.0 * 128 * 128 * kpad
+print("Cin=%d %dx%d k%d s%d B=%d  N=%d d=%d | gram %.3f ms  %.0f TF alg  %.0f TF issued(128-tiles) | stage %.3f ms (%.0f GB/s in)" %
+      (Cin, H, W, k, s, B, N, d, g, flops / g / 1e9, issued / g / 1e9, st, x.numel() * 4 / st / 1e6))
