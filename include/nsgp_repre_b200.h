@@ -78,6 +78,18 @@ int nsgp_cov_conv2d_accumulate(const float* x, int B, int Cin, int H, int W, int
                                int sh, int sw, int ph, int pw, float* acc, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* The two halves of nsgp_cov_conv2d_accumulate as separate stream-ordered calls, so
+ * a caller can run the HBM-bound staging of layer i+1 (on the stream that produced
+ * x) concurrently with the tensor-bound contraction of layer i (on a side stream):
+ *   stage:    workspace <- tf32 hi/lo planes of the batch-averaged, im2col-free operand
+ *   contract: acc += X^T X from a staged workspace (same geometry arguments). */
+int nsgp_cov_conv2d_stage(const float* x, int B, int Cin, int H, int W, int kh, int kw, int sh,
+                          int sw, int ph, int pw, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int nsgp_cov_conv2d_contract(int Cin, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                             int pw, float* acc, const void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* Linear: acc += m^T m with m = mean over the R rows of x (R,d)
  * (nsrunner_roi_replay.py:900-901, 930-934). */
 int nsgp_cov_linear_accumulate(const float* x, int R, int d, float* acc, void* workspace,
@@ -125,6 +137,51 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                        const nsgp_proj_layer_t* layers, int n_layers, double lr,
                        double momentum, double dampening, double weight_decay, int nesterov,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Prepared plan of the same step: the grouped projection GEMM (all protected layers
+ * in ONE persistent tcgen05 launch, work items sorted by cost) is encoded once into a
+ * caller-provided device buffer; every step then uploads the small tensor table and
+ * makes two launches.  Rebuild when a weight / projector / staging pointer or a shape
+ * changes (gradient and momentum pointers may change freely between steps). */
+typedef struct {
+  int n_problems, n_items, kind;
+  size_t off_items, bytes;
+} nsgp_group_t;
+
+typedef struct {
+  int n_tensors, total_chunks, all_have_buf;
+  size_t off_chunks, off_group;
+  nsgp_group_t group;
+  size_t bytes;
+} nsgp_sgd_plan_t;
+
+size_t nsgp_sgd_plan_bytes(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                           const nsgp_proj_layer_t* layers, int n_layers);
+int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                        const nsgp_proj_layer_t* layers, int n_layers,
+                        void* plan_dev /* 256-byte aligned */, size_t plan_bytes,
+                        nsgp_sgd_plan_t* plan /* host, out */, void* stream);
+int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                       const nsgp_proj_layer_t* layers, int n_layers, void* plan_dev,
+                       const nsgp_sgd_plan_t* plan /* host */, double lr, double momentum,
+                       double dampening, double weight_decay, int nesterov, void* stream);
+
+/* Grouped covariance contraction: the Gram updates of many staged layers (one job
+ * per nsgp_cov_conv2d_stage call, each with its own workspace) as ONE persistent
+ * launch - no per-layer launch gaps or tails.  The table is built once per set of
+ * (geometry, workspace, accumulator) jobs and re-launched every forward. */
+typedef struct {
+  int Cin, H, W, kh, kw, sh, sw, ph, pw;
+  float* acc;
+  const void* workspace;
+  size_t workspace_bytes;
+} nsgp_cov_job_t;
+
+size_t nsgp_cov_group_bytes(const nsgp_cov_job_t* jobs /* host */, int n_jobs);
+int nsgp_cov_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs,
+                         void* table_dev /* 64-byte aligned */, size_t table_bytes,
+                         nsgp_group_t* group /* host, out */, void* stream);
+int nsgp_group_launch(const void* table_dev, const nsgp_group_t* group /* host */, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * a9/a10/a11  RePRE prototypes

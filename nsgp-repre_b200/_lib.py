@@ -33,6 +33,23 @@ class ProjLayer(C.Structure):
                 ("u_hi", c_void_p), ("u_lo", c_void_p)]
 
 
+class Group(C.Structure):
+    _fields_ = [("n_problems", c_int), ("n_items", c_int), ("kind", c_int),
+                ("off_items", c_size_t), ("bytes", c_size_t)]
+
+
+class SgdPlan(C.Structure):
+    _fields_ = [("n_tensors", c_int), ("total_chunks", c_int), ("all_have_buf", c_int),
+                ("off_chunks", c_size_t), ("off_group", c_size_t), ("group", Group),
+                ("bytes", c_size_t)]
+
+
+class CovJob(C.Structure):
+    _fields_ = [("Cin", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
+                ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int),
+                ("acc", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
 # name -> (restype, argtypes); every symbol of include/nsgp_repre_b200.h
 SIGNATURES = {
     "nsgp_abi_version": (c_int, []),
@@ -46,6 +63,8 @@ SIGNATURES = {
     "nsgp_cov_linear_layout": (c_int, [c_int, C.POINTER(CovLayout)]),
     "nsgp_cov_conv2d_accumulate": (c_int, [c_void_p] + [c_int] * 10 +
                                    [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nsgp_cov_conv2d_stage": (c_int, [c_void_p] + [c_int] * 10 + [c_void_p, c_size_t, c_void_p]),
+    "nsgp_cov_conv2d_contract": (c_int, [c_int] * 9 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "nsgp_cov_linear_accumulate": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
                                            c_size_t, c_void_p]),
     "nsgp_cov_finalize": (c_int, [c_void_p, C.POINTER(CovLayout), c_void_p, c_int, c_void_p]),
@@ -54,6 +73,16 @@ SIGNATURES = {
     "nsgp_sgd_nscl_step": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
                                    c_double, c_double, c_double, c_double, c_int,
                                    c_void_p, c_size_t, c_void_p]),
+    "nsgp_sgd_plan_bytes": (c_size_t, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int]),
+    "nsgp_sgd_plan_build": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
+                                    c_void_p, c_size_t, C.POINTER(SgdPlan), c_void_p]),
+    "nsgp_sgd_plan_step": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
+                                   c_void_p, C.POINTER(SgdPlan), c_double, c_double, c_double,
+                                   c_double, c_int, c_void_p]),
+    "nsgp_cov_group_bytes": (c_size_t, [C.POINTER(CovJob), c_int]),
+    "nsgp_cov_group_build": (c_int, [C.POINTER(CovJob), c_int, c_void_p, c_size_t,
+                                     C.POINTER(Group), c_void_p]),
+    "nsgp_group_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p]),
     "repre_class_index": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
     "repre_segment_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, check, ptr, CovLayout
+from ._lib import lib, check, ptr, CovLayout, CovJob, Group
 
 
 class _LayerAcc:
@@ -34,6 +34,18 @@ class _LayerAcc:
         self.layout = layout
         self.acc = acc
         self.calls = 0
+
+
+class _JobSet:
+    """One forward's worth of staged layers for the grouped launch."""
+
+    def __init__(self):
+        self.jobs = []          # [key, geometry tuple, workspace tensor, layer accumulator]
+        self.pos = 0
+        self.sig = None
+        self.table = None
+        self.group = None
+        self.done = None        # event: the grouped launch has finished reading the set
 
 
 class CovarianceHooks:
@@ -47,8 +59,29 @@ class CovarianceHooks:
 
     DEFAULT_IGNORE = ["roi_head.bbox_head.fc_cls", "roi_head.bbox_head.fc_reg", "teacher"]
 
-    def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True):
+    def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
+                 mode="grouped", ring=3):
+        """``mode``
+        * ``"grouped"`` (default): every hook call only STAGES its layer (HBM-bound) into
+          that layer's own workspace on the caller's stream; at the end of the forward
+          (``flush``) the Gram updates of all staged layers run as ONE persistent
+          tcgen05 launch on a side stream, overlapping the next forward.  Two workspace
+          sets alternate so the next forward never waits for the launch in flight.
+        * ``"overlap"``: per-layer launches, contraction of layer i on a side stream while
+          the caller's stream stages layer i+1; ``ring`` staged workspaces rotate.
+        * ``"immediate"``: stage + contract back to back on the caller's stream.
+        Every result access joins the side stream first."""
         self.model = model
+        if mode not in ("grouped", "overlap", "immediate"):
+            raise ValueError("mode must be 'grouped', 'overlap' or 'immediate'")
+        self.mode = mode
+        self._sets = [_JobSet(), _JobSet()]
+        self._cur = 0
+        self._ring_n = max(2, int(ring))
+        self._ring = []             # [workspace tensor, done event]
+        self._ring_pos = 0
+        self._side = None
+        self._pending = False
         self.ignore_keys = list(ignore_keys) + (self.DEFAULT_IGNORE if add_default_ignores else [])
         self._names = {}
         self._layers: "OrderedDict[str, _LayerAcc]" = OrderedDict()
@@ -70,12 +103,101 @@ class CovarianceHooks:
         self._names = {m: n for n, m in self.model.named_modules()}
         for _, m in self.hooked_modules():
             self._handles.append(m.register_forward_hook(self.compute_cov))
+        # end of a forward of the whole model: launch the grouped contraction
+        self._handles.append(self.model.register_forward_hook(lambda *a: self.flush()))
         return self
 
     def remove(self):
         for h in self._handles:
             h.remove()
         self._handles = []
+
+    # ------------------------------------------------------------- side stream
+    def _side_stream(self, device):
+        if self._side is None or self._side.device != device:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
+    def _ring_slot(self, nbytes: int, device):
+        """Next staged workspace of the ring, grown on demand; the caller's stream
+        first waits until the contraction that last read it has finished."""
+        if len(self._ring) < self._ring_n:
+            self._ring.append([None, None])
+        slot = self._ring[self._ring_pos % len(self._ring)]
+        self._ring_pos += 1
+        if slot[1] is not None:
+            torch.cuda.current_stream(device).wait_event(slot[1])
+        if slot[0] is None or slot[0].numel() < nbytes or slot[0].device != device:
+            slot[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return slot
+
+    # ------------------------------------------------------------ grouped mode
+    def _stage_job(self, x, key, geom, B, layout, la):
+        js = self._sets[self._cur]
+        dev = x.device
+        main = torch.cuda.current_stream(dev)
+        if js.pos == 0 and js.done is not None:
+            main.wait_event(js.done)          # the set's previous launch must be finished
+        if js.pos < len(js.jobs) and js.jobs[js.pos][0] == key and js.jobs[js.pos][1] == geom \
+                and js.jobs[js.pos][2].device == dev and js.jobs[js.pos][3] is la:
+            ws = js.jobs[js.pos][2]
+        else:
+            del js.jobs[js.pos:]
+            ws = torch.empty(int(layout.workspace_bytes), dtype=torch.uint8, device=dev)
+            js.jobs.append([key, geom, ws, la])
+            js.sig = None
+        check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(), main.cuda_stream),
+              "nsgp_cov_conv2d_stage")
+        js.pos += 1
+        la.calls += 1
+
+    def flush(self):
+        """Launch the grouped contraction of every layer staged since the last flush
+        (called automatically after each forward of the hooked model and by ``join``)."""
+        js = self._sets[self._cur]
+        if js.pos == 0:
+            return
+        del js.jobs[js.pos:]
+        dev = js.jobs[0][2].device
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        staged = torch.cuda.Event()
+        staged.record(main)
+        side.wait_event(staged)
+        if js.sig is None:
+            n = len(js.jobs)
+            arr = (CovJob * n)()
+            for i, (key, geom, ws, la) in enumerate(js.jobs):
+                j = arr[i]
+                (j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw) = geom
+                j.acc, j.workspace, j.workspace_bytes = la.acc.data_ptr(), ws.data_ptr(), ws.numel()
+            need = int(lib.nsgp_cov_group_bytes(arr, n))
+            if need == 0:
+                raise _lib.NsgpError("nsgp_cov_group_bytes failed: %s" %
+                                     lib.nsgp_last_error().decode("utf-8", "replace"))
+            if js.table is None or js.table.numel() < need or js.table.device != dev:
+                js.table = torch.empty(need, dtype=torch.uint8, device=dev)
+            js.group = Group()
+            import ctypes
+            check(lib.nsgp_cov_group_build(arr, n, ptr(js.table), js.table.numel(),
+                                           ctypes.byref(js.group), side.cuda_stream),
+                  "nsgp_cov_group_build")
+            js.sig = True
+        import ctypes
+        check(lib.nsgp_group_launch(ptr(js.table), ctypes.byref(js.group), side.cuda_stream),
+              "nsgp_group_launch")
+        js.done = torch.cuda.Event()
+        js.done.record(side)
+        js.pos = 0
+        self._cur ^= 1
+        self._pending = True
+
+    def join(self):
+        """Make the current stream wait for every contraction issued on the side stream."""
+        self.flush()
+        if self._pending and self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._pending = False
 
     def _ws(self, nbytes: int, device) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() < nbytes or \
@@ -122,10 +244,37 @@ class CovarianceHooks:
         check(lib.nsgp_cov_conv2d_layout(Cin, H, W, kh, kw, sh, sw, ph, pw, layout),
               "nsgp_cov_conv2d_layout")
         la = self._layer(key, layout, x.device)
-        ws = self._ws(layout.workspace_bytes, x.device)
-        check(lib.nsgp_cov_conv2d_accumulate(
-            ptr(x), B, Cin, H, W, kh, kw, sh, sw, ph, pw, ptr(la.acc), ptr(ws), ws.numel(),
-            _lib.current_stream(x.device)), "nsgp_cov_conv2d_accumulate")
+        mode = self.mode
+        if mode == "grouped" and lib.nsgp_get_engine() != 0:
+            mode = "overlap"            # the bring-up engine has no grouped launch
+        if mode == "grouped":
+            self._stage_job(x, key, (Cin, H, W, kh, kw, sh, sw, ph, pw), B, layout, la)
+            return
+        if mode == "immediate":
+            ws = self._ws(layout.workspace_bytes, x.device)
+            check(lib.nsgp_cov_conv2d_accumulate(
+                ptr(x), B, Cin, H, W, kh, kw, sh, sw, ph, pw, ptr(la.acc), ptr(ws), ws.numel(),
+                _lib.current_stream(x.device)), "nsgp_cov_conv2d_accumulate")
+            la.calls += 1
+            return
+        # stage on the caller's stream (it produced x), contract on the side stream
+        slot = self._ring_slot(layout.workspace_bytes, x.device)
+        ws = slot[0]
+        main = torch.cuda.current_stream(x.device)
+        side = self._side_stream(x.device)
+        check(lib.nsgp_cov_conv2d_stage(
+            ptr(x), B, Cin, H, W, kh, kw, sh, sw, ph, pw, ptr(ws), ws.numel(),
+            main.cuda_stream), "nsgp_cov_conv2d_stage")
+        staged = torch.cuda.Event()
+        staged.record(main)
+        side.wait_event(staged)
+        check(lib.nsgp_cov_conv2d_contract(
+            Cin, H, W, kh, kw, sh, sw, ph, pw, ptr(la.acc), ptr(ws), ws.numel(),
+            side.cuda_stream), "nsgp_cov_conv2d_contract")
+        done = torch.cuda.Event()
+        done.record(side)
+        slot[1] = done
+        self._pending = True
         la.calls += 1
 
     def _accumulate_linear(self, x, key):
@@ -141,6 +290,7 @@ class CovarianceHooks:
             x = x.float().contiguous()
         layout = CovLayout()
         check(lib.nsgp_cov_linear_layout(d, layout), "nsgp_cov_linear_layout")
+        self.join()                  # same accumulator may have a contraction in flight
         la = self._layer(key, layout, x.device)
         ws = self._ws(layout.workspace_bytes, x.device)
         check(lib.nsgp_cov_linear_accumulate(ptr(x), x.shape[0], d, ptr(la.acc), ptr(ws),
@@ -159,6 +309,7 @@ class CovarianceHooks:
 
     # ---------------------------------------------------------------- results
     def _finalize(self, key: str) -> torch.Tensor:
+        self.join()
         la = self._layers[key]
         d = la.layout.d
         out = torch.empty(d, d, dtype=torch.float32, device=la.acc.device)
@@ -177,6 +328,7 @@ class CovarianceHooks:
         return list(self._layers.keys())
 
     def reset(self):
+        self.join()
         for la in self._layers.values():
             la.acc.zero_()
             la.calls = 0
@@ -185,18 +337,18 @@ class CovarianceHooks:
     # ------------------------------------------------- cal_fea_in tail (:746-757)
     def all_reduce(self, group=None):
         """SUM over ranks of every accumulator, as ``all_reduce_dict(self.fea_in)``
-        (:746-749) - one flat fp32 buffer, one NCCL all-reduce over NVLink."""
+        (:746-749), in place on the fp32 sums, NCCL over NVLink (gloo in the CPU tests)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or \
                 dist.get_world_size(group) == 1 or not self._layers:
             return
-        accs = [la.acc for la in self._layers.values()]
-        flat = torch.cat([a.view(-1) for a in accs])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        off = 0
-        for a in accs:
-            a.copy_(flat[off:off + a.numel()])
-            off += a.numel()
+        self.join()
+        # in place, one collective per accumulator, all in flight together: no 0.6 GB
+        # flatten-and-copy round trip; NCCL pipelines them back to back over NVLink
+        works = [dist.all_reduce(la.acc, op=dist.ReduceOp.SUM, group=group, async_op=True)
+                 for la in self._layers.values()]
+        for w in works:
+            w.wait()
 
     def merge_previous(self, old_fea_in: dict):
         """``fea_in[k] + old_fea_in[k]`` for task_id != 1 (:750-753); keys of the

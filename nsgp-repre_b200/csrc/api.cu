@@ -125,21 +125,38 @@ int nsgp_cov_linear_layout(int d, nsgp_cov_layout_t* out) {
   return 0;
 }
 
-int nsgp_cov_conv2d_accumulate(const float* x, int B, int C, int H, int W, int kh, int kw,
-                               int sh, int sw, int ph, int pw, float* acc, void* workspace,
-                               size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  NSGP_REQUIRE(x && acc && workspace, "cov_conv2d: null pointer");
-  NSGP_REQUIRE(B > 0, "cov_conv2d: empty batch");
-  ConvGeom g;
-  NSGP_REQUIRE(make_conv_geom(C, H, W, kh, kw, sh, sw, ph, pw, &g) == 0,
+static int cov_conv2d_setup(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                            void* workspace, size_t workspace_bytes, ConvGeom* g, float** stage) {
+  NSGP_REQUIRE(make_conv_geom(C, H, W, kh, kw, sh, sw, ph, pw, g) == 0,
                "cov_conv2d: invalid conv geometry");
   char* ws = align_up((char*)workspace, 1024);
-  NSGP_REQUIRE(ws + stage_bytes(g) <= (char*)workspace + workspace_bytes,
+  NSGP_REQUIRE(ws + stage_bytes(*g) <= (char*)workspace + workspace_bytes,
                "cov_conv2d: workspace too small (%zu < %zu)", workspace_bytes,
-               stage_bytes(g) + 1024);
-  float* stage = reinterpret_cast<float*>(ws);
-  int rc = launch_stage_conv(x, stage, g, B, stream);
+               stage_bytes(*g) + 1024);
+  *stage = reinterpret_cast<float*>(ws);
+  return 0;
+}
+
+int nsgp_cov_conv2d_stage(const float* x, int B, int C, int H, int W, int kh, int kw, int sh,
+                          int sw, int ph, int pw, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  NSGP_REQUIRE(x && workspace, "cov_conv2d_stage: null pointer");
+  NSGP_REQUIRE(B > 0, "cov_conv2d: empty batch");
+  ConvGeom g;
+  float* stage;
+  int rc = cov_conv2d_setup(C, H, W, kh, kw, sh, sw, ph, pw, workspace, workspace_bytes, &g, &stage);
+  if (rc) return rc;
+  return launch_stage_conv(x, stage, g, B, (cudaStream_t)stream_);
+}
+
+int nsgp_cov_conv2d_contract(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                             float* acc, const void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  NSGP_REQUIRE(acc && workspace, "cov_conv2d_contract: null pointer");
+  ConvGeom g;
+  float* stage;
+  int rc = cov_conv2d_setup(C, H, W, kh, kw, sh, sw, ph, pw, const_cast<void*>(workspace),
+                            workspace_bytes, &g, &stage);
   if (rc) return rc;
   ContractionArgs a{};
   a.A = conv_operand(g, stage);
@@ -151,7 +168,18 @@ int nsgp_cov_conv2d_accumulate(const float* x, int B, int C, int H, int W, int k
   a.epi = kEpiGramAtomic;
   int tiles_1d = ceil_div(a.A.rows, 128);
   a.splits = pick_splits(tiles_1d * (tiles_1d + 1) / 2, k_blocks(a.A));
-  return contraction(a, stream);
+  return contraction(a, (cudaStream_t)stream_);
+}
+
+int nsgp_cov_conv2d_accumulate(const float* x, int B, int C, int H, int W, int kh, int kw,
+                               int sh, int sw, int ph, int pw, float* acc, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  NSGP_REQUIRE(x && acc && workspace, "cov_conv2d: null pointer");
+  int rc = nsgp_cov_conv2d_stage(x, B, C, H, W, kh, kw, sh, sw, ph, pw, workspace,
+                                 workspace_bytes, stream_);
+  if (rc) return rc;
+  return nsgp_cov_conv2d_contract(C, H, W, kh, kw, sh, sw, ph, pw, acc, workspace,
+                                  workspace_bytes, stream_);
 }
 
 int nsgp_cov_linear_accumulate(const float* x, int R, int d, float* acc, void* workspace,
@@ -180,6 +208,48 @@ int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, vo
   return launch_transpose_split(P, pt_hi, pt_lo, d, (int)round_up(d, 4), (cudaStream_t)stream_);
 }
 
+static int sgd_tables(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                      const nsgp_proj_layer_t* layers, int n_layers, double momentum_hint,
+                      std::vector<SgdTensorDev>* host, std::vector<int>* chunk_start) {
+  host->resize(n_tensors);
+  chunk_start->resize(n_tensors + 1);
+  int total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    const nsgp_sgd_tensor_t& t = tensors[i];
+    NSGP_REQUIRE(t.w && t.g, "sgd_step: tensor %d has a null weight/grad pointer", i);
+    NSGP_REQUIRE(momentum_hint == 0.0 || t.buf, "sgd_step: tensor %d needs a momentum buffer", i);
+    SgdTensorDev d{};
+    d.w = t.w; d.g = t.g; d.buf = t.buf; d.numel = t.numel; d.first = t.first_step;
+    if (t.layer >= 0) {
+      NSGP_REQUIRE(t.layer < n_layers && layers, "sgd_step: tensor %d: bad layer index", i);
+      const nsgp_proj_layer_t& L = layers[t.layer];
+      NSGP_REQUIRE((long long)L.cout * L.d == t.numel,
+                   "sgd_step: tensor %d: cout*d != numel", i);
+      d.u_hi = L.u_hi; d.u_lo = L.u_lo;
+      d.d = L.d; d.ldu = (int)round_up(L.d, 4);
+    }
+    (*host)[i] = d;
+    (*chunk_start)[i] = total;
+    total += sgd_chunks(t.numel);
+  }
+  (*chunk_start)[n_tensors] = total;
+  return 0;
+}
+
+static ContractionArgs proj_args(const nsgp_proj_layer_t& L, float* w) {
+  ContractionArgs a{};
+  const int ldk = (int)round_up(L.d, 4);
+  a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, ldk);
+  a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
+  a.out = w;
+  a.ld = L.d;
+  a.n_cols = L.d;
+  a.alpha = 1.f;
+  a.epi = kEpiGemmRmw;
+  a.splits = 1;
+  return a;
+}
+
 size_t nsgp_sgd_step_workspace_bytes(int n_tensors, int n_layers) {
   (void)n_layers;
   return (size_t)n_tensors * sizeof(SgdTensorDev) + (size_t)(n_tensors + 1) * sizeof(int) + 512;
@@ -195,28 +265,11 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   NSGP_REQUIRE(tensors && workspace, "sgd_step: null pointer");
   NSGP_REQUIRE(workspace_bytes >= nsgp_sgd_step_workspace_bytes(n_tensors, n_layers),
                "sgd_step: workspace too small");
-  std::vector<SgdTensorDev> host(n_tensors);
-  std::vector<int> chunk_start(n_tensors + 1);
-  int total = 0;
-  for (int i = 0; i < n_tensors; ++i) {
-    const nsgp_sgd_tensor_t& t = tensors[i];
-    NSGP_REQUIRE(t.w && t.g, "sgd_step: tensor %d has a null weight/grad pointer", i);
-    NSGP_REQUIRE(momentum == 0.0 || t.buf, "sgd_step: tensor %d needs a momentum buffer", i);
-    SgdTensorDev d{};
-    d.w = t.w; d.g = t.g; d.buf = t.buf; d.numel = t.numel; d.first = t.first_step;
-    if (t.layer >= 0) {
-      NSGP_REQUIRE(t.layer < n_layers && layers, "sgd_step: tensor %d: bad layer index", i);
-      const nsgp_proj_layer_t& L = layers[t.layer];
-      NSGP_REQUIRE((long long)L.cout * L.d == t.numel,
-                   "sgd_step: tensor %d: cout*d != numel", i);
-      d.u_hi = L.u_hi; d.u_lo = L.u_lo;
-      d.d = L.d; d.ldu = (int)round_up(L.d, 4);
-    }
-    host[i] = d;
-    chunk_start[i] = total;
-    total += sgd_chunks(t.numel);
-  }
-  chunk_start[n_tensors] = total;
+  std::vector<SgdTensorDev> host;
+  std::vector<int> chunk_start;
+  int rc = sgd_tables(tensors, n_tensors, layers, n_layers, momentum, &host, &chunk_start);
+  if (rc) return rc;
+  const int total = chunk_start[n_tensors];
   char* ws = align_up((char*)workspace, 256);
   SgdTensorDev* dev_t = reinterpret_cast<SgdTensorDev*>(ws);
   int* dev_c = reinterpret_cast<int*>(ws + (size_t)n_tensors * sizeof(SgdTensorDev));
@@ -224,26 +277,154 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                                   cudaMemcpyHostToDevice, stream));
   NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_c, chunk_start.data(), chunk_start.size() * sizeof(int),
                                   cudaMemcpyHostToDevice, stream));
-  int rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, total, (float)lr, (float)momentum,
-                               (float)(1.0 - dampening), (float)weight_decay, nesterov, stream);
+  rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, total, (float)lr, (float)momentum,
+                           (float)(1.0 - dampening), (float)weight_decay, nesterov, stream);
   if (rc) return rc;
   for (int i = 0; i < n_tensors; ++i) {
     if (tensors[i].layer < 0) continue;
-    const nsgp_proj_layer_t& L = layers[tensors[i].layer];
-    ContractionArgs a{};
-    const int ldk = (int)round_up(L.d, 4);
-    a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, ldk);
-    a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
-    a.out = tensors[i].w;
-    a.ld = L.d;
-    a.n_cols = L.d;
-    a.alpha = 1.f;
-    a.epi = kEpiGemmRmw;
-    a.splits = 1;
-    rc = contraction(a, stream);
+    rc = contraction(proj_args(layers[tensors[i].layer], tensors[i].w), stream);
     if (rc) return rc;
   }
   return 0;
+}
+
+// ---- prepared plan: tables uploaded once, two launches per step ---------------
+static void proj_problems(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                          const nsgp_proj_layer_t* layers, std::vector<ContractionArgs>* out) {
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].layer >= 0) out->push_back(proj_args(layers[tensors[i].layer], tensors[i].w));
+}
+
+size_t nsgp_sgd_plan_bytes(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                           const nsgp_proj_layer_t* layers, int n_layers) {
+  if (!tensors || n_tensors <= 0) return 1024;
+  std::vector<ContractionArgs> probs;
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].layer >= 0 && tensors[i].layer < n_layers && layers)
+      probs.push_back(proj_args(layers[tensors[i].layer], tensors[i].w));
+  return nsgp_sgd_step_workspace_bytes(n_tensors, n_layers) + 1024 +
+         group_table_bytes(probs.data(), (int)probs.size());
+}
+
+int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                        const nsgp_proj_layer_t* layers, int n_layers, void* plan_dev,
+                        size_t plan_bytes, nsgp_sgd_plan_t* plan, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(tensors && plan_dev && plan && n_tensors > 0, "sgd_plan_build: bad arguments");
+  NSGP_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255) == 0,
+               "sgd_plan_build: plan buffer must be 256-byte aligned");
+  NSGP_REQUIRE(g_engine == 0, "sgd_plan_build: plans need the tcgen05 engine");
+  for (int i = 0; i < n_tensors; ++i)
+    NSGP_REQUIRE(tensors[i].layer < n_layers && (tensors[i].layer < 0 || layers),
+                 "sgd_plan_build: tensor %d: bad layer index", i);
+  const size_t off_chunks = round_up((long long)((size_t)n_tensors * sizeof(SgdTensorDev)), 256);
+  const size_t off_group =
+      round_up((long long)(off_chunks + (size_t)(n_tensors + 1) * sizeof(int)), 256);
+  NSGP_REQUIRE(off_group <= plan_bytes, "sgd_plan_build: plan buffer too small");
+  std::vector<ContractionArgs> probs;
+  proj_problems(tensors, n_tensors, layers, &probs);
+  GroupInfo gi{};
+  int rc = group_table_build(probs.data(), (int)probs.size(), kProfGemm,
+                             (char*)plan_dev + off_group, plan_bytes - off_group, &gi, stream);
+  if (rc) return rc;
+  plan->n_tensors = n_tensors;
+  plan->total_chunks = 0;
+  plan->all_have_buf = 0;
+  plan->off_chunks = off_chunks;
+  plan->off_group = off_group;
+  plan->group.n_problems = gi.n_problems;
+  plan->group.n_items = gi.n_items;
+  plan->group.kind = gi.kind;
+  plan->group.off_items = gi.off_items;
+  plan->group.bytes = gi.bytes;
+  plan->bytes = off_group + gi.bytes;
+  return 0;
+}
+
+int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
+                       const nsgp_proj_layer_t* layers, int n_layers, void* plan_dev,
+                       const nsgp_sgd_plan_t* plan, double lr, double momentum, double dampening,
+                       double weight_decay, int nesterov, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(tensors && plan_dev && plan, "sgd_plan_step: null pointer");
+  NSGP_REQUIRE(n_tensors == plan->n_tensors, "sgd_plan_step: plan was built for %d tensors",
+               plan->n_tensors);
+  // the tensor table (weights, gradients, momentum buffers, first-step flags) is
+  // re-uploaded every step - gradients are usually fresh allocations; the grouped
+  // GEMM table (staged updates, projectors, weights) is the part that is reused
+  std::vector<SgdTensorDev> host;
+  std::vector<int> chunk_start;
+  int rc = sgd_tables(tensors, n_tensors, layers, n_layers, momentum, &host, &chunk_start);
+  if (rc) return rc;
+  SgdTensorDev* dev_t = reinterpret_cast<SgdTensorDev*>(plan_dev);
+  int* dev_c = reinterpret_cast<int*>((char*)plan_dev + plan->off_chunks);
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_t, host.data(), host.size() * sizeof(SgdTensorDev),
+                                  cudaMemcpyHostToDevice, stream));
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_c, chunk_start.data(), chunk_start.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, stream));
+  rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, chunk_start[n_tensors], (float)lr,
+                           (float)momentum, (float)(1.0 - dampening), (float)weight_decay,
+                           nesterov, stream);
+  if (rc) return rc;
+  GroupInfo gi{plan->group.n_problems, plan->group.n_items, plan->group.kind,
+               plan->group.off_items, plan->group.bytes};
+  return group_launch((const char*)plan_dev + plan->off_group, gi, stream);
+}
+
+// ---- grouped covariance contraction (deferred mode of the hooks) ----------------
+static int cov_job_args(const nsgp_cov_job_t& j, ContractionArgs* out) {
+  ConvGeom g;
+  float* stage;
+  int rc = cov_conv2d_setup(j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw,
+                            const_cast<void*>(j.workspace), j.workspace_bytes, &g, &stage);
+  if (rc) return rc;
+  NSGP_REQUIRE(j.acc != nullptr, "cov_group: null accumulator");
+  ContractionArgs a{};
+  a.A = conv_operand(g, stage);
+  a.B = a.A;
+  a.out = j.acc;
+  a.ld = (int)round_up(g.d_int, 4);
+  a.n_cols = a.A.rows;
+  a.alpha = 1.f;
+  a.epi = kEpiGramAtomic;
+  a.splits = 1;
+  *out = a;
+  return 0;
+}
+
+size_t nsgp_cov_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs) {
+  if (!jobs || n_jobs <= 0) return 1024;
+  std::vector<ContractionArgs> probs(n_jobs);
+  for (int i = 0; i < n_jobs; ++i)
+    if (cov_job_args(jobs[i], &probs[i])) return 0;
+  return group_table_bytes(probs.data(), n_jobs) + 256;
+}
+
+int nsgp_cov_group_build(const nsgp_cov_job_t* jobs, int n_jobs, void* table_dev,
+                         size_t table_bytes, nsgp_group_t* group, void* stream_) {
+  NSGP_REQUIRE(jobs && table_dev && group && n_jobs > 0, "cov_group_build: bad arguments");
+  NSGP_REQUIRE(g_engine == 0, "cov_group_build: groups need the tcgen05 engine");
+  std::vector<ContractionArgs> probs(n_jobs);
+  for (int i = 0; i < n_jobs; ++i) {
+    int rc = cov_job_args(jobs[i], &probs[i]);
+    if (rc) return rc;
+  }
+  GroupInfo gi{};
+  int rc = group_table_build(probs.data(), n_jobs, kProfGram, table_dev, table_bytes, &gi,
+                             (cudaStream_t)stream_);
+  if (rc) return rc;
+  group->n_problems = gi.n_problems;
+  group->n_items = gi.n_items;
+  group->kind = gi.kind;
+  group->off_items = gi.off_items;
+  group->bytes = gi.bytes;
+  return 0;
+}
+
+int nsgp_group_launch(const void* table_dev, const nsgp_group_t* group, void* stream_) {
+  NSGP_REQUIRE(table_dev && group, "group_launch: null pointer");
+  GroupInfo gi{group->n_problems, group->n_items, group->kind, group->off_items, group->bytes};
+  return group_launch(table_dev, gi, (cudaStream_t)stream_);
 }
 
 // ---------------------------------------------------------------- RePRE

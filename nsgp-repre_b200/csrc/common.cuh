@@ -102,6 +102,17 @@ struct ContractionArgs {
   int splits;       // split-K factor (Gram only)
 };
 
+// grouped contraction (tcgen05 engine only): a host-side list of problems that is
+// uploaded once as a device table and launched as ONE persistent kernel
+struct GroupInfo {
+  int n_problems, n_items, kind;   // kind: ProfKind of the launch (kProfGram / kProfGemm)
+  size_t off_items, bytes;
+};
+size_t group_table_bytes(const ContractionArgs* probs, int n);
+int group_table_build(const ContractionArgs* probs, int n, int kind, void* table_dev,
+                      size_t table_bytes, GroupInfo* info, cudaStream_t stream);
+int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream);
+
 // engines
 int contraction_simt(const ContractionArgs& a, cudaStream_t stream);
 int contraction_tc(const ContractionArgs& a, cudaStream_t stream);      // tcgen05/TMA

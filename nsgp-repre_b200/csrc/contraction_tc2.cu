@@ -16,6 +16,7 @@
 //   TMEM: 2 accumulator buffers x 256 columns (all 512 columns)
 //
 // Same operand descriptors, staging layout and K-split rule as contraction_tc.cu.
+// (Experimental: selected with NSGP_PAIR_KERNEL=1; see contraction_tc.cu.)
 #include "common.cuh"
 #include "tc_common.cuh"
 

@@ -10,7 +10,6 @@ constexpr int BK = 32;             // fp32 elements per K block = one 128-byte s
 constexpr int UMMA_K = 8;          // tf32: 32 bytes per instruction
 constexpr int kThreads = 192;      // 6 warps
 constexpr int kEpiWarp0 = 2;
-constexpr int kMaxChainBlocks = 32;   // K blocks accumulated in TMEM per work item
 
 struct alignas(64) TcMaps {
   CUtensorMap a[2][kMaxTaps];   // [hi/lo][tap]
@@ -31,6 +30,19 @@ struct TcParams {
   int tiles_m, tiles_n, n_tiles;  // tile grid (Gram: n_tiles counts visited pairs)
   int same_operand;               // Gram: B is A
   int vec_red;                    // use red.global.add.v4.f32 in the epilogue
+  int gram;                       // 1: upper block-triangle of A*A^T, 0: full A*B^T
+};
+
+// Grouped launches: many problems in one persistent launch.  The table lives in
+// device memory: TcProblem[n_problems] followed by TcItem[n_items] (sorted by
+// descending cost so that the static round-robin deal is balanced).
+struct alignas(64) TcProblem {
+  TcMaps maps;
+  TcParams p;
+};
+struct alignas(16) TcItem {
+  int prob, rb, cb, kb0;
+  int kb1, pad0, pad1, pad2;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -201,6 +213,9 @@ __device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc,
 
 // ---- host helpers shared by the launchers --------------------------------------
 int sm_count();
+// chain limits (K blocks accumulated in one TMEM accumulator pair)
+constexpr int kChainGram = 64;
+constexpr int kChainGemm = 160;
 // 2-CTA (cta_group::2) 256x256-tile Gram kernel, contraction_tc2.cu
 int launch_tc2_gram(const TcMaps& maps, const TcParams& p, cudaStream_t stream);
 

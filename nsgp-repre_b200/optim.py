@@ -27,7 +27,7 @@ import torch
 from torch.optim.optimizer import Optimizer
 
 from . import _lib
-from ._lib import lib, check, ptr, SgdTensor, ProjLayer
+from ._lib import lib, check, ptr, SgdTensor, ProjLayer, SgdPlan
 
 
 class SGDNSCL(Optimizer):
@@ -45,6 +45,7 @@ class SGDNSCL(Optimizer):
         self._prepared = {}     # name -> (key, pt_hi, pt_lo)
         self._stage = {}        # name -> (u_hi, u_lo)
         self._workspace = None
+        self._plans = {}        # group index -> (signature, device buffer, SgdPlan)
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -199,13 +200,36 @@ class SGDNSCL(Optimizer):
                     layers.append(L)
             n_l = len(layers)
             layer_arr = (ProjLayer * max(n_l, 1))(*layers)
-            need = lib.nsgp_sgd_step_workspace_bytes(n_t, n_l)
-            if self._workspace is None or self._workspace.numel() < need or \
-                    self._workspace.device != device:
-                self._workspace = torch.empty(int(need), dtype=torch.uint8, device=device)
-            check(lib.nsgp_sgd_nscl_step(
-                tensors, n_t, layer_arr, n_l, float(group["lr"]), float(group["momentum"]),
-                float(group["dampening"]), float(group["weight_decay"]),
-                1 if group["nesterov"] else 0, ptr(self._workspace), self._workspace.numel(),
-                _lib.current_stream(device)), "nsgp_sgd_nscl_step")
+            stream = _lib.current_stream(device)
+            hyper = (float(group["lr"]), float(group["momentum"]), float(group["dampening"]),
+                     float(group["weight_decay"]), 1 if group["nesterov"] else 0)
+            if lib.nsgp_get_engine() != 0:
+                # bring-up engine: one-shot call, per-layer launches
+                need = lib.nsgp_sgd_step_workspace_bytes(n_t, n_l)
+                if self._workspace is None or self._workspace.numel() < need or \
+                        self._workspace.device != device:
+                    self._workspace = torch.empty(int(need), dtype=torch.uint8, device=device)
+                check(lib.nsgp_sgd_nscl_step(tensors, n_t, layer_arr, n_l, *hyper,
+                                             ptr(self._workspace), self._workspace.numel(),
+                                             stream), "nsgp_sgd_nscl_step")
+                continue
+            # prepared plan: rebuilt only when a weight / projector pointer or a shape changes
+            sig = (tuple((t.w, t.numel, t.layer) for t in tensors),
+                   tuple((L.cout, L.d, L.pt_hi, L.pt_lo, L.u_hi, L.u_lo) for L in layers))
+            gi = id(group)
+            hit = self._plans.get(gi)
+            if hit is None or hit[0] != sig:
+                need = int(lib.nsgp_sgd_plan_bytes(tensors, n_t, layer_arr, n_l))
+                buf = hit[1] if hit is not None and hit[1].numel() >= need and \
+                    hit[1].device == device else \
+                    torch.empty(need, dtype=torch.uint8, device=device)
+                plan = SgdPlan()
+                check(lib.nsgp_sgd_plan_build(tensors, n_t, layer_arr, n_l, ptr(buf),
+                                              buf.numel(), ctypes.byref(plan), stream),
+                      "nsgp_sgd_plan_build")
+                hit = (sig, buf, plan)
+                self._plans[gi] = hit
+            check(lib.nsgp_sgd_plan_step(tensors, n_t, layer_arr, n_l, ptr(hit[1]),
+                                         ctypes.byref(hit[2]), *hyper, stream),
+                  "nsgp_sgd_plan_step")
         return loss

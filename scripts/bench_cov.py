@@ -1,0 +1,45 @@
+"""Covariance pass (61 R50-FPN layers @800x1344, B=8) under the three host modes."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import nsgp_repre_b200 as pkg
+from nsgp_repre_b200 import standin, _lib
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+layers = bench.trace_layers(800, 1344, standin)
+g = torch.Generator(device="cuda").manual_seed(0)
+xs = [torch.relu(torch.randn(B, r["Cin"], r["H"], r["W"], device="cuda", generator=g)) for r in layers]
+flops = sum(r["cov_flops"] for r in layers)
+
+def run(mode, join_each):
+    hooks = pkg.CovarianceHooks(torch.nn.Identity(), mode=mode)
+    def one():
+        for r, x in zip(layers, xs):
+            hooks._accumulate_conv(x, r["name"], (r["k"],) * 2, (r["s"],) * 2, (r["p"],) * 2)
+        hooks.flush()
+        if join_each:
+            hooks.join()
+    for _ in range(2):
+        one()
+    hooks.join(); torch.cuda.synchronize()
+    _lib.profile_read(); _lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        one()
+    hooks.join()
+    e1.record(); torch.cuda.synchronize()
+    host = (time.perf_counter() - t0) / reps * 1e3
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    ms = e0.elapsed_time(e1) / reps
+    print("%-10s join_each=%d  %.2f ms/pass (host %.2f)  %.0f TF alg | gram %.2f ms (%d launches)  stage %.2f ms" %
+          (mode, join_each, ms, host, flops / ms / 1e9, prof["gram"][0] / reps, prof["gram"][1] / reps,
+           prof["stage"][0] / reps))
+
+for mode in ("immediate", "overlap", "grouped"):
+    for je in (1, 0):
+        run(mode, je)
