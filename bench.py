@@ -476,13 +476,20 @@ def main():
         lab_out_h = torch.empty(10 * OLD_CLASSES, dtype=torch.int64).pin_memory()
         key0 = "backbone.layer2.0.conv1.weight"
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
         def e2e_step():
+            main = torch.cuda.current_stream(dev)
+            # RoI features travel on a copy stream while the detector runs
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):
+                f_d.copy_(feats_h, non_blocking=True)
+                l_d.copy_(labels_h, non_blocking=True)
             img_d.copy_(images_h, non_blocking=True)
             with torch.no_grad():
                 model(img_d)         # hooks fire: 61 layers staged, one grouped Gram launch
             sgd_step()
-            f_d.copy_(feats_h, non_blocking=True)
-            l_d.copy_(labels_h, non_blocking=True)
+            main.wait_stream(copy_stream)
             staged = repre_step(f_d, l_d)
             hooks.join()             # the step's covariance update is complete before it is read
             res = torch.stack([staged.sum(), staged[0, 0],
@@ -490,7 +497,7 @@ def main():
             res_h.copy_(res, non_blocking=True)
             n = proto.tmp_label.numel()
             lab_out_h[:n].copy_(proto.tmp_label, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            main.synchronize()
 
         e2e_ms, _ = timed(e2e_step, args.steps, max(1, args.warmup))
         hooks.remove()

@@ -144,8 +144,10 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
  * makes two launches.  Rebuild when a weight / projector / staging pointer or a shape
  * changes (gradient and momentum pointers may change freely between steps). */
 typedef struct {
-  int n_problems, n_items, kind;
-  size_t off_items, bytes;
+  int kind;
+  int n_problems[2], n_items[2];   /* [0] single-CTA kernel, [1] CTA-pair (cta_group::2) kernel */
+  size_t off_probs[2], off_items[2];
+  size_t bytes;
 } nsgp_group_t;
 
 typedef struct {
@@ -218,6 +220,17 @@ int repre_cosine_count(const float* F, int D, const int32_t* rows, int n, float 
                        uint8_t* mask, int32_t* counts, float* sim_out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* The same for n_classes classes in four launches (normalise, clear, ONE grouped
+ * tcgen05 Gram over all classes, threshold+count).  rows: device, the classes' row
+ * lists concatenated; sizes: HOST, rows per class.  mask: the (n_c x n_c) uint8
+ * masks packed back to back; counts: concatenated like rows. */
+size_t repre_cosine_count_batched_workspace_bytes(const int32_t* sizes /* host */, int n_classes,
+                                                  int D);
+int repre_cosine_count_batched(const float* F, int D, const int32_t* rows,
+                               const int32_t* sizes /* host */, int n_classes, float thresh,
+                               uint8_t* mask, int32_t* counts, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* out[p][:] = protos[idx[p]][:] (idx NULL: identity, the reference stages every
  * prototype every step, :458-463; idx = randperm()[:64] is :58-59).  Extension:
  * sigma != NULL adds sigma[idx[p]] * N(0,1) noise from Philox4x32-10 keyed by
@@ -232,6 +245,10 @@ size_t repre_kmeans_assign_workspace_bytes(int n, int k, int D);
 int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int k,
                         int64_t* labels, void* workspace, size_t workspace_bytes,
                         void* stream);
+
+/* bring-up: per-CTA wait/issue cycle counters of the last tcgen05 contraction launched
+ * with NSGP_DBG_COUNTERS=1 in the environment (8 counters per CTA, host buffer) */
+int nsgp_debug_read_counters(unsigned long long* out /* host */, int n);
 
 /* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);

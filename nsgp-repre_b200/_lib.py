@@ -34,8 +34,8 @@ class ProjLayer(C.Structure):
 
 
 class Group(C.Structure):
-    _fields_ = [("n_problems", c_int), ("n_items", c_int), ("kind", c_int),
-                ("off_items", c_size_t), ("bytes", c_size_t)]
+    _fields_ = [("kind", c_int), ("n_problems", c_int * 2), ("n_items", c_int * 2),
+                ("off_probs", c_size_t * 2), ("off_items", c_size_t * 2), ("bytes", c_size_t)]
 
 
 class SgdPlan(C.Structure):
@@ -92,11 +92,16 @@ SIGNATURES = {
     "repre_cosine_count_workspace_bytes": (c_size_t, [c_int, c_int]),
     "repre_cosine_count": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "repre_cosine_count_batched_workspace_bytes": (c_size_t, [C.POINTER(C.c_int32), c_int, c_int]),
+    "repre_cosine_count_batched": (c_int, [c_void_p, c_int, c_void_p, C.POINTER(C.c_int32), c_int,
+                                           c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
     "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     C.c_uint64, c_void_p, c_void_p]),
     "repre_kmeans_assign_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "repre_kmeans_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
+    "nsgp_debug_read_counters": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
     "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
 }

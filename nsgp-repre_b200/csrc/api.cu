@@ -236,6 +236,25 @@ static int sgd_tables(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   return 0;
 }
 
+static void group_to_abi(const GroupInfo& gi, nsgp_group_t* g) {
+  g->kind = gi.kind;
+  for (int k = 0; k < 2; ++k) {
+    g->n_problems[k] = gi.sub[k].n_problems;
+    g->n_items[k] = gi.sub[k].n_items;
+    g->off_probs[k] = gi.sub[k].off_probs;
+    g->off_items[k] = gi.sub[k].off_items;
+  }
+  g->bytes = gi.bytes;
+}
+static GroupInfo group_from_abi(const nsgp_group_t& g) {
+  GroupInfo gi{};
+  gi.kind = g.kind;
+  for (int k = 0; k < 2; ++k)
+    gi.sub[k] = SubGroup{g.n_problems[k], g.n_items[k], g.off_probs[k], g.off_items[k]};
+  gi.bytes = g.bytes;
+  return gi;
+}
+
 static ContractionArgs proj_args(const nsgp_proj_layer_t& L, float* w) {
   ContractionArgs a{};
   const int ldk = (int)round_up(L.d, 4);
@@ -332,11 +351,7 @@ int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   plan->all_have_buf = 0;
   plan->off_chunks = off_chunks;
   plan->off_group = off_group;
-  plan->group.n_problems = gi.n_problems;
-  plan->group.n_items = gi.n_items;
-  plan->group.kind = gi.kind;
-  plan->group.off_items = gi.off_items;
-  plan->group.bytes = gi.bytes;
+  group_to_abi(gi, &plan->group);
   plan->bytes = off_group + gi.bytes;
   return 0;
 }
@@ -366,9 +381,7 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                            (float)momentum, (float)(1.0 - dampening), (float)weight_decay,
                            nesterov, stream);
   if (rc) return rc;
-  GroupInfo gi{plan->group.n_problems, plan->group.n_items, plan->group.kind,
-               plan->group.off_items, plan->group.bytes};
-  return group_launch((const char*)plan_dev + plan->off_group, gi, stream);
+  return group_launch((const char*)plan_dev + plan->off_group, group_from_abi(plan->group), stream);
 }
 
 // ---- grouped covariance contraction (deferred mode of the hooks) ----------------
@@ -413,18 +426,13 @@ int nsgp_cov_group_build(const nsgp_cov_job_t* jobs, int n_jobs, void* table_dev
   int rc = group_table_build(probs.data(), n_jobs, kProfGram, table_dev, table_bytes, &gi,
                              (cudaStream_t)stream_);
   if (rc) return rc;
-  group->n_problems = gi.n_problems;
-  group->n_items = gi.n_items;
-  group->kind = gi.kind;
-  group->off_items = gi.off_items;
-  group->bytes = gi.bytes;
+  group_to_abi(gi, group);
   return 0;
 }
 
 int nsgp_group_launch(const void* table_dev, const nsgp_group_t* group, void* stream_) {
   NSGP_REQUIRE(table_dev && group, "group_launch: null pointer");
-  GroupInfo gi{group->n_problems, group->n_items, group->kind, group->off_items, group->bytes};
-  return group_launch(table_dev, gi, (cudaStream_t)stream_);
+  return group_launch(table_dev, group_from_abi(*group), (cudaStream_t)stream_);
 }
 
 // ---------------------------------------------------------------- RePRE
@@ -489,6 +497,97 @@ int repre_cosine_count(const float* F, int D, const int32_t* rows, int n, float 
   return launch_threshold_count(S, n, ld, thresh, mask, counts, sim_out, stream);
 }
 
+// ---- all classes at once: 1 normalise launch, 1 memset, 1 grouped Gram, 1 threshold launch
+static void batched_layout(const int32_t* sizes, int n_classes, int D, size_t* n_total,
+                           size_t* s_elems, size_t* table_bytes) {
+  size_t n = 0, s = 0;
+  for (int c = 0; c < n_classes; ++c) {
+    n += (size_t)sizes[c];
+    s += (size_t)sizes[c] * (size_t)round_up(sizes[c], 4);
+  }
+  *n_total = n;
+  *s_elems = s;
+  std::vector<ContractionArgs> probs;
+  for (int c = 0; c < n_classes; ++c) {
+    if (sizes[c] <= 0) continue;
+    ContractionArgs a{};
+    a.A = matrix_operand(nullptr, nullptr, sizes[c], D, D);
+    a.B = a.A;
+    a.n_cols = sizes[c];
+    a.epi = kEpiGramAtomic;
+    probs.push_back(a);
+  }
+  *table_bytes = group_table_bytes(probs.data(), (int)probs.size()) + 1024;
+}
+
+size_t repre_cosine_count_batched_workspace_bytes(const int32_t* sizes, int n_classes, int D) {
+  if (!sizes || n_classes <= 0) return 1024;
+  size_t n, s, tb;
+  batched_layout(sizes, n_classes, D, &n, &s, &tb);
+  return 2 * (size_t)round_up((long long)n, 8) * D * 4 + s * 4 + tb +
+         (size_t)n_classes * sizeof(ClassExtent) + 4096;
+}
+
+int repre_cosine_count_batched(const float* F, int D, const int32_t* rows, const int32_t* sizes,
+                               int n_classes, float thresh, uint8_t* mask, int32_t* counts,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(F && rows && sizes && mask && counts && workspace, "cosine_count_batched: null pointer");
+  NSGP_REQUIRE(n_classes >= 0 && D > 0 && D % 4 == 0, "cosine_count_batched: bad sizes");
+  if (n_classes == 0) return 0;
+  NSGP_REQUIRE(g_engine == 0, "cosine_count_batched needs the tcgen05 engine");
+  NSGP_REQUIRE(workspace_bytes >= repre_cosine_count_batched_workspace_bytes(sizes, n_classes, D),
+               "cosine_count_batched: workspace too small");
+  size_t n_total, s_elems, table_bytes;
+  batched_layout(sizes, n_classes, D, &n_total, &s_elems, &table_bytes);
+  if (n_total == 0) return 0;
+  char* ws = align_up((char*)workspace, 1024);
+  float* hi = reinterpret_cast<float*>(ws);
+  float* lo = hi + (size_t)round_up((long long)n_total, 8) * D;
+  float* S = lo + (size_t)round_up((long long)n_total, 8) * D;
+  char* table = align_up(reinterpret_cast<char*>(S + s_elems), 256);
+  ClassExtent* ext_dev = reinterpret_cast<ClassExtent*>(align_up(table + table_bytes, 256));
+  NSGP_REQUIRE((char*)(ext_dev + n_classes) <= (char*)workspace + workspace_bytes,
+               "cosine_count_batched: workspace layout overflow");
+  int rc = launch_normalize_split(F, D, rows, (int)n_total, hi, lo, stream);
+  if (rc) return rc;
+  NSGP_CHECK_CUDA(cudaMemsetAsync(S, 0, s_elems * 4, stream));
+  std::vector<ContractionArgs> probs;
+  std::vector<ClassExtent> ext(n_classes);
+  size_t row_off = 0, s_off = 0, mask_off = 0;
+  int max_n = 0;
+  for (int c = 0; c < n_classes; ++c) {
+    const int n = sizes[c], ld = (int)round_up(n, 4);
+    ext[c] = ClassExtent{(long long)s_off, (long long)mask_off, (int)row_off, n, ld, 0};
+    if (n > 0) {
+      ContractionArgs a{};
+      a.A = matrix_operand(hi + row_off * D, lo + row_off * D, n, D, D);
+      a.B = a.A;
+      a.out = S + s_off;
+      a.ld = ld;
+      a.n_cols = n;
+      a.alpha = 1.f;
+      a.epi = kEpiGramAtomic;
+      a.splits = 1;
+      probs.push_back(a);
+    }
+    if (n > max_n) max_n = n;
+    row_off += n;
+    s_off += (size_t)n * ld;
+    mask_off += (size_t)n * n;
+  }
+  GroupInfo gi{};
+  rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table, table_bytes, &gi,
+                         stream);
+  if (rc) return rc;
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(ext_dev, ext.data(), ext.size() * sizeof(ClassExtent),
+                                  cudaMemcpyHostToDevice, stream));
+  rc = group_launch(table, gi, stream);
+  if (rc) return rc;
+  return launch_threshold_count_batched(S, ext_dev, n_classes, max_n, thresh, mask, counts,
+                                        stream);
+}
+
 int repre_replay_gather(const float* protos, const float* sigma, const int64_t* idx, int P,
                         int D, uint64_t seed, float* out, void* stream_) {
   NSGP_REQUIRE(protos && out, "replay_gather: null pointer");
@@ -538,6 +637,11 @@ int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int 
   rc = contraction(a, stream);
   if (rc) return rc;
   return launch_kmeans_argmin(dots, n, k, ld, cn, (long long*)labels, stream);
+}
+
+int nsgp_debug_read_counters(unsigned long long* out, int n) {
+  NSGP_REQUIRE(out && n > 0 && n <= 160 * 8, "debug_read_counters: bad arguments");
+  return debug_read_counters(out, n);
 }
 
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream_) {

@@ -104,14 +104,21 @@ struct ContractionArgs {
 
 // grouped contraction (tcgen05 engine only): a host-side list of problems that is
 // uploaded once as a device table and launched as ONE persistent kernel
+struct SubGroup {
+  int n_problems, n_items;
+  size_t off_probs, off_items;
+};
 struct GroupInfo {
-  int n_problems, n_items, kind;   // kind: ProfKind of the launch (kProfGram / kProfGemm)
-  size_t off_items, bytes;
+  SubGroup sub[2];                 // [0] single-CTA kernel, [1] CTA-pair kernel
+  int kind;                        // ProfKind of the launches (kProfGram / kProfGemm)
+  size_t bytes;
 };
 size_t group_table_bytes(const ContractionArgs* probs, int n);
 int group_table_build(const ContractionArgs* probs, int n, int kind, void* table_dev,
                       size_t table_bytes, GroupInfo* info, cudaStream_t stream);
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream);
+
+int debug_read_counters(unsigned long long* out, int n);
 
 // engines
 int contraction_simt(const ContractionArgs& a, cudaStream_t stream);

@@ -47,6 +47,13 @@ constexpr uint32_t kStageBytes = 4 * kABytes;   // A_hi | A_lo | B_hi | B_lo
 // the scale of the large sum.  The epilogue adds them in fp32 (round-to-nearest).
 constexpr uint32_t kTmemCols = 512;
 
+// number of br-row TMA boxes covering [r0, r0+128) below `rows`
+__device__ __forceinline__ int seg_count(int r0, int rows, int br) {
+  int n = 0;
+  for (int r = r0; r < r0 + BM && r < rows; r += br) ++n;
+  return n;
+}
+
 struct Item {
   const TcMaps* maps;
   const TcParams* p;
@@ -88,11 +95,25 @@ __device__ __forceinline__ Item fetch_item(const TcMaps* pmaps, const TcParams* 
   return it;
 }
 
+// Bring-up instrumentation (NSGP_DBG_COUNTERS=1): per-CTA cycle counters of where the
+// producer and the MMA issuer spend their time.  [0] MMA warp waiting for operands
+// (full barrier), [1] MMA warp issuing (blocks on the tensor pipe), [2] MMA warp waiting
+// for a free accumulator, [3] producer waiting for a free stage, [4] producer issuing
+// (blocks on the TMA unit), [5] total, [6] K blocks.
+__device__ unsigned long long g_dbg_counters[160 * 8];
+
 // ---------------------------------------------------------------- the kernel
+// PAIR = false: one CTA per 128 x 128 tile.
+// PAIR = true : a CTA pair (cluster of 2, cta_group::2) per 256 x 256 tile.  Each CTA
+//   owns 128 of the tile rows (its A tile) and stages half of the B rows; the MMA unit
+//   of each SM reads the other half from the peer.  Per output element that is half
+//   the TMA traffic of the single-CTA kernel - and TMA issue throughput (~58 B/cycle/SM
+//   measured with NSGP_DBG_COUNTERS) is what bounds the single-CTA kernel.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constant__ TcParams pp,
                       const TcProblem* __restrict__ gprobs, const TcItem* __restrict__ gitems,
-                      int n_items) {
+                      int n_items, int prefetch_dist, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -102,144 +123,255 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  constexpr int TILE = PAIR ? 256 : 128;         // tile edge in rows / columns
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const long long t_start = clock64();
+  long long c_wait = 0, c_issue = 0, c_acc = 0, c_kb = 0;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], PAIR ? 2 : 1);     // pair: leader's expect_tx + the peer's arrive
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], PAIR ? 8 : 4);   // epilogue warps (of both CTAs)
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_base_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-        const Item it = fetch_item(&pmaps, &pp, gprobs, gitems, idx);
-        const TcParams& p = *it.p;
-        const int r0 = it.rb * BM, c0 = it.cb * BN;
-        const bool share = p.gram && p.same_operand && it.rb == it.cb;
-        // bytes landed per stage (full boxes always count, OOB parts are zero-filled)
-        int segs_a = 0, segs_b = 0;
-        for (int r = r0; r < r0 + BM && r < p.A.rows; r += p.A.br) ++segs_a;
-        if (!share)
-          for (int r = c0; r < c0 + BN && r < p.B.rows; r += p.B.br) ++segs_b;
-        const uint32_t tx = 2u * (uint32_t)(segs_a * p.A.br + segs_b * p.B.br) * BK * 4u;
-        for (int kb = it.kb0; kb < it.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], tx);
-          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
-          const int kx0 = kb * BK;
-          for (int s = 0; s < segs_a; ++s) {
-            const int r = r0 + s * p.A.br;
-            const int t = r / p.A.Cs, c = r - t * p.A.Cs;
-            const uint32_t off = (uint32_t)(s * p.A.br) * (BK * 4);
-            tma_load_2d(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
-            tma_load_2d(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
-          }
-          for (int s = 0; s < segs_b; ++s) {
-            const int r = c0 + s * p.B.br;
-            const int t = r / p.B.Cs, c = r - t * p.B.Cs;
-            const uint32_t off = (uint32_t)(s * p.B.br) * (BK * 4);
-            tma_load_2d(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
-            tma_load_2d(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // The whole warp runs the loop with warp-uniform values; the single issuing thread
+    // is elected inside each asm block (see tc_common.cuh).  A second cursor runs
+    // prefetch_dist K blocks ahead and pulls the operand rows into L2 - by exactly one
+    // worker per row block (diagonal tile for Gram, first tile of the row / column for
+    // GEMM) - so that the ring's load latency is an L2 hit, not a DRAM fill that every
+    // CTA of the wave waits for together.
+    uint32_t stage = 0, phase = 0;
+    int pf_idx = worker, pf_kb = 0;
+    Item pf_it{};
+    bool pf_live = prefetch_dist > 0 && pf_idx < n_items;
+    if (pf_live) { pf_it = fetch_item(&pmaps, &pp, gprobs, gitems, pf_idx); pf_kb = pf_it.kb0; }
+    auto prefetch_step = [&]() {
+      if (!pf_live) return;
+      const TcParams& q = *pf_it.p;
+      const bool pa = q.gram ? (pf_it.rb == pf_it.cb) : (pf_it.cb == 0);
+      const bool pb = q.gram ? false : (pf_it.rb == 0);
+      const int kx = pf_kb * BK;
+      if (pa) {
+        const int r0 = pf_it.rb * TILE + rank * BM;
+        for (int r = r0; r < r0 + BM && r < q.A.rows; r += q.A.br) {
+          const int t = r / q.A.Cs, c = r - t * q.A.Cs;
+          tma_prefetch_2d_elect(&pf_it.maps->a[0][t], kx, c);
+          tma_prefetch_2d_elect(&pf_it.maps->a[1][t], kx, c);
         }
       }
-    }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    uint32_t stage = 0, phase = 0;
-    uint32_t local_item = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local_item) {
+      if (pb) {
+        const int c0 = pf_it.cb * TILE + rank * BM;
+        for (int r = c0; r < c0 + BM && r < q.B.rows; r += q.B.br) {
+          const int t = r / q.B.Cs, c = r - t * q.B.Cs;
+          tma_prefetch_2d_elect(&pf_it.maps->b[0][t], kx, c);
+          tma_prefetch_2d_elect(&pf_it.maps->b[1][t], kx, c);
+        }
+      }
+      if (++pf_kb >= pf_it.kb1) {
+        pf_idx += n_workers;
+        pf_live = pf_idx < n_items;
+        if (pf_live) { pf_it = fetch_item(&pmaps, &pp, gprobs, gitems, pf_idx); pf_kb = pf_it.kb0; }
+      }
+    };
+    for (int i = 0; i < prefetch_dist; ++i) prefetch_step();
+    for (int idx = worker; idx < n_items; idx += n_workers) {
       const Item it = fetch_item(&pmaps, &pp, gprobs, gitems, idx);
       const TcParams& p = *it.p;
+      const int r0 = it.rb * TILE + rank * BM;    // this CTA's A rows
+      const int c0 = it.cb * TILE + rank * BM;    // the B rows this CTA stages
       const bool share = p.gram && p.same_operand && it.rb == it.cb;
-      // ragged right edge: issue only as many columns as are valid (N in steps of 16)
-      int n_valid = p.n_cols - it.cb * BN;
-      if (n_valid > BN) n_valid = BN;
-      const uint32_t idesc = make_idesc_tf32(BM, (n_valid + 15) & ~15);
-      const uint32_t buf = local_item & 1;
-      const uint32_t use = local_item >> 1;
-      mbar_wait_warp(&tmem_empty[buf], (use & 1) ^ 1, lane);     // epilogue drained this buffer
-      tc_fence_after();
-      const uint32_t d_main = tmem_base + buf * (2 * BN);
-      const uint32_t d_corr = d_main + BN;
+      const int a_rows = p.A.rows, a_br = p.A.br, a_cs = p.A.Cs;
+      const int b_rows = p.B.rows, b_br = p.B.br, b_cs = p.B.Cs;
+      const int segs_a = seg_count(r0, a_rows, a_br);
+      const int segs_b = share ? 0 : seg_count(c0, b_rows, b_br);
+      // bytes landing on the (leader's) full barrier per stage; full boxes always count
+      int sa = segs_a, sb = segs_b;
+      if (PAIR) {
+        sa += seg_count(r0 + (rank ? -BM : BM), a_rows, a_br);
+        if (!share) sb += seg_count(c0 + (rank ? -BM : BM), b_rows, b_br);
+      }
+      const uint32_t tx = ((dbg & 4) ? 1u : 2u) * (uint32_t)(sa * a_br + sb * b_br) * BK * 4u;
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
-        mbar_wait_warp(&full_bar[stage], phase, lane);
+        prefetch_step();
+        long long t0 = (dbg & 1) ? clock64() : 0;
+        if (dbg & 8) mbar_wait(&empty_bar[stage], phase ^ 1);
+        else mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
+        long long t1 = (dbg & 1) ? clock64() : 0;
+        c_wait += t1 - t0;
+        if (!PAIR || rank == 0) mbar_expect_tx_elect(&full_bar[stage], tx);
+        else mbar_arrive_remote_elect(&full_bar[stage], 0);
+        const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+        const int kx0 = kb * BK;
+        for (int s = 0; s < segs_a; ++s) {
+          const int r = r0 + s * a_br;
+          const int t = r / a_cs, c = r - t * a_cs;
+          const uint32_t off = (uint32_t)(s * a_br) * (BK * 4);
+          if (PAIR) {
+            tma_load_2d_2sm_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
+            tma_load_2d_2sm_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
+          } else {
+            tma_load_2d_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
+            if (!(dbg & 4)) tma_load_2d_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
+          }
+        }
+        for (int s = 0; s < segs_b; ++s) {
+          const int r = c0 + s * b_br;
+          const int t = r / b_cs, c = r - t * b_cs;
+          const uint32_t off = (uint32_t)(s * b_br) * (BK * 4);
+          if (PAIR) {
+            tma_load_2d_2sm_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
+            tma_load_2d_2sm_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
+          } else {
+            tma_load_2d_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
+            if (!(dbg & 4)) tma_load_2d_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
+          }
+        }
+        if (dbg & 1) c_issue += clock64() - t1;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    if ((dbg & 1) && lane == 0) {
+      g_dbg_counters[blockIdx.x * 8 + 3] = c_wait;
+      g_dbg_counters[blockIdx.x * 8 + 4] = c_issue;
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (pair: leader CTA only) ============================
+    if (!PAIR || rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t local_item = 0;
+      for (int idx = worker; idx < n_items; idx += n_workers, ++local_item) {
+        const Item it = fetch_item(&pmaps, &pp, gprobs, gitems, idx);
+        const TcParams& p = *it.p;
+        const bool share = p.gram && p.same_operand && it.rb == it.cb;
+        // single-CTA: ragged right edge issues only the valid columns (N in steps of 16)
+        int n_valid = p.n_cols - it.cb * TILE;
+        if (n_valid > TILE) n_valid = TILE;
+        const uint32_t idesc = PAIR ? make_idesc_tf32(256, 256)
+                                    : make_idesc_tf32(BM, (n_valid + 15) & ~15);
+        const uint32_t buf = local_item & 1;
+        const uint32_t use = local_item >> 1;
+        long long ta = (dbg & 1) ? clock64() : 0;
+        mbar_wait_warp(&tmem_empty[buf], (use & 1) ^ 1, lane);   // epilogue drained this buffer
+        if (dbg & 1) c_acc += clock64() - ta;
         tc_fence_after();
-        if (lane == 0) {
+        // single-CTA: [main | corr] x 128 columns per buffer; pair: one 256-column accumulator
+        const uint32_t d_main = tmem_base + buf * 256;
+        const uint32_t d_corr = d_main + 128;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          long long t0 = (dbg & 1) ? clock64() : 0;
+          if (dbg & 8) mbar_wait(&full_bar[stage], phase);
+          else mbar_wait_warp(&full_bar[stage], phase, lane);
+          long long t1 = (dbg & 1) ? clock64() : 0;
+          c_wait += t1 - t0;
+          ++c_kb;
+          tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
           const uint64_t a_hi = make_kmajor_sw128_desc(sbase);
           const uint64_t a_lo = make_kmajor_sw128_desc(sbase + kABytes);
           const uint64_t b_hi = share ? a_hi : make_kmajor_sw128_desc(sbase + 2 * kABytes);
           const uint64_t b_lo = share ? a_lo : make_kmajor_sw128_desc(sbase + 3 * kABytes);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 bytes per K step
-            const uint32_t first = (kb > it.kb0 || k > 0) ? 1u : 0u;
-            tc_mma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, first);
-            tc_mma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-            tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, first);
+          const uint32_t first = kb > it.kb0 ? 1u : 0u;
+          if (PAIR) {
+            tc_mma_kblock_3xtf32_2sm(d_main, a_hi, a_lo, b_hi, b_lo, idesc, first);
+            tc_commit_2sm_mc_elect(&empty_bar[stage]);        // frees the slot in both CTAs
+            if (kb == it.kb1 - 1) tc_commit_2sm_mc_elect(&tmem_full[buf]);
+          } else {
+            if (dbg & 2) tc_mma_kblock_3xtf32(d_main, d_corr, a_hi, a_hi, b_hi, b_hi, idesc, first, 2u);
+            else tc_mma_kblock_3xtf32(d_main, d_corr, a_hi, a_lo, b_hi, b_lo, idesc, first, 0u);
+            tc_commit_elect(&empty_bar[stage]);               // slot free when these retire
+            if (kb == it.kb1 - 1) tc_commit_elect(&tmem_full[buf]);
           }
-          tc_commit(&empty_bar[stage]);                 // smem slot free when these retire
-          if (kb == it.kb1 - 1) tc_commit(&tmem_full[buf]);
+          if (dbg & 1) c_issue += clock64() - t1;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (it.kb1 <= it.kb0) {                               // defensive: empty K range
+          if (PAIR) tc_commit_2sm_mc_elect(&tmem_full[buf]);
+          else tc_commit_elect(&tmem_full[buf]);
+        }
       }
-      if (it.kb1 <= it.kb0 && lane == 0) tc_commit(&tmem_full[buf]);   // defensive: empty K range
-      __syncwarp();
+      if ((dbg & 1) && lane == 0) {
+        g_dbg_counters[blockIdx.x * 8 + 0] = c_wait;
+        g_dbg_counters[blockIdx.x * 8 + 1] = c_issue;
+        g_dbg_counters[blockIdx.x * 8 + 2] = c_acc;
+        g_dbg_counters[blockIdx.x * 8 + 5] = clock64() - t_start;
+        g_dbg_counters[blockIdx.x * 8 + 6] = c_kb;
+      }
     }
   } else {
-    // ============================ epilogue ============================
+    // ============================ epilogue (own 128 accumulator rows) ============================
     const int quad = warp & 3;                         // TMEM lane quadrant of this warp
     uint32_t local_item = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local_item) {
+    for (int idx = worker; idx < n_items; idx += n_workers, ++local_item) {
       const Item it = fetch_item(&pmaps, &pp, gprobs, gitems, idx);
       const TcParams& p = *it.p;
       const uint32_t buf = local_item & 1;
       const uint32_t use = local_item >> 1;
       mbar_wait_warp(&tmem_full[buf], use & 1, lane, 200);
       tc_fence_after();
-      const int row = it.rb * BM + quad * 32 + lane;
+      const int rblk = it.rb * TILE + rank * BM;
+      const int row = rblk + quad * 32 + lane;
       const bool row_ok = row < p.A.rows && it.kb1 > it.kb0;
       float* orow = p.out + (long long)row * p.ld;
       const float alpha = p.alpha;
       const int n_cols = p.n_cols;
       const bool vec = p.vec_red != 0;
+      const bool gram = p.gram != 0;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32], w[32];
-        const uint32_t taddr =
-            tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * BN) + chunk * 32;
+      for (int chunk = 0; chunk < TILE / 32; ++chunk) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + chunk * 32;
         tc_ld32(taddr, v);
-        tc_ld32(taddr + BN, w);
-        tc_wait_ld();
-        const int col0 = it.cb * BN + chunk * 32;
-        // Gram: chunks strictly below the diagonal block of this row carry nothing needed
-        const bool wanted = !p.gram || (col0 + 31 >= it.rb * BM);
+        if (!PAIR) {
+          uint32_t w[32];
+          tc_ld32(taddr + 128, w);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        } else {
+          tc_wait_ld();
+        }
+        const int col0 = it.cb * TILE + chunk * 32;
+        // Gram: chunks strictly left of this CTA's diagonal block carry nothing needed
+        const bool wanted = !gram || (col0 + 31 >= rblk);
         if (row_ok && col0 < n_cols && wanted) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int col = col0 + j;
-            const float x0 = alpha * (__uint_as_float(v[j]) + __uint_as_float(w[j]));
-            const float x1 = alpha * (__uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1]));
-            const float x2 = alpha * (__uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2]));
-            const float x3 = alpha * (__uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3]));
+            const float x0 = alpha * __uint_as_float(v[j]), x1 = alpha * __uint_as_float(v[j + 1]),
+                        x2 = alpha * __uint_as_float(v[j + 2]), x3 = alpha * __uint_as_float(v[j + 3]);
             if (vec && col + 3 < n_cols) {
               red_add_v4(orow + col, x0, x1, x2, x3);
             } else {
@@ -253,17 +385,27 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (!PAIR || rank == 0) {
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      } else {
+        mbar_arrive_remote_elect(&tmem_empty[buf], 0);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();          // the peer may still be reading this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(kTmemCols)
+                   : "memory");
   }
 }
 
@@ -329,10 +471,26 @@ void fill_operand(const Operand& o, int br, TcOperand* d) {
 
 constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 + 256;
 
+int dbg_counters() {
+  static const int d = (getenv("NSGP_DBG_COUNTERS") ? 1 : 0) | (getenv("NSGP_DBG_MMA2") ? 2 : 0) |
+                       (getenv("NSGP_DBG_HALFLOAD") ? 4 : 0) | (getenv("NSGP_DBG_ALLPOLL") ? 8 : 0);
+  return d;
+}
+
+// K blocks the L2 prefetch cursor runs ahead of the loads (NSGP_PREFETCH overrides)
+int prefetch_distance() {
+  static const int d = [] {
+    const char* e = getenv("NSGP_PREFETCH");
+    return e ? atoi(e) : 8;
+  }();
+  return d;
+}
+
+template <bool PAIR>
 int configure_kernel() {
   static bool configured = false;
   if (!configured) {
-    NSGP_CHECK_CUDA(cudaFuncSetAttribute(contraction_tc_kernel,
+    NSGP_CHECK_CUDA(cudaFuncSetAttribute(contraction_tc_kernel<PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes));
     configured = true;
@@ -340,9 +498,68 @@ int configure_kernel() {
   return 0;
 }
 
+// Launch over `n_items` work items with `workers` CTAs (single) or CTA pairs (pair).
+int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProblem* gprobs,
+                  const TcItem* gitems, int n_items, int kind, cudaStream_t stream) {
+  if (n_items <= 0) return 0;
+  ProfScope prof(kind, stream);
+  if (pair) {
+    int rc = configure_kernel<true>();
+    if (rc) return rc;
+    int clusters = sm_count() / 2;
+    if (n_items < clusters) clusters = n_items;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<true>, maps, p, gprobs, gitems,
+                                       n_items, prefetch_distance(), dbg_counters()));
+  } else {
+    int rc = configure_kernel<false>();
+    if (rc) return rc;
+    const int grid = n_items < sm_count() ? n_items : sm_count();
+    contraction_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(
+        maps, p, gprobs, gitems, n_items, prefetch_distance(), dbg_counters());
+  }
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// CTA-pair kernel or single-CTA kernel for a Gram of `rows` rows?  The pair kernel
+// moves half the TMA bytes per output element but pads to 256-row blocks and has one
+// accumulator chain.  Measured (scripts/bench_gram.py, NSGP_DBG_COUNTERS): both kernels
+// are bound by the latency of the 3-stage operand ring (192 KB of smem in flight per
+// SM), and with cta_group::2 the TMA issue rate per SM halves, so the pair kernel ends
+// up at the same speed (1.87 vs 1.88 ms on fpn_convs.0).  Default: single-CTA kernel;
+// NSGP_PAIR_KERNEL=1 selects the pair kernel where it can run, =2 by the cost model.
+bool want_pair(int rows, bool gram, bool same) {
+  static const int force = [] {
+    const char* e = getenv("NSGP_PAIR_KERNEL");       // 0 never (default), 1 always, 2 cost model
+    return e ? atoi(e) : 0;
+  }();
+  static const double ratio = [] {
+    const char* e = getenv("NSGP_PAIR_RATIO");        // cost of a pair unit / single unit
+    return e ? atof(e) : 0.65;
+  }();
+  if (!gram || !same || force == 0) return false;
+  if (force == 1) return true;
+  if (force != 2) return false;
+  const int t1 = ceil_div(rows, 128), t2 = ceil_div(rows, 256);
+  const double units1 = t1 * (t1 + 1) / 2.0, units2 = 4.0 * (t2 * (t2 + 1) / 2);
+  return units2 * ratio <= units1;
+}
+
 // Validates one problem, encodes its tensor maps and fills every field of the
 // parameter block except `splits`.  Returns 1 for an empty problem (nothing to do).
-int build_problem(const ContractionArgs& a, TcProblem* out) {
+int build_problem(const ContractionArgs& a, bool pair, TcProblem* out) {
   NSGP_REQUIRE(a.A.T >= 1 && a.A.T <= kMaxTaps && a.B.T >= 1 && a.B.T <= kMaxTaps,
                "tcgen05 engine: bad tap count");
   NSGP_REQUIRE(a.A.row_pitch % 4 == 0 && a.B.row_pitch % 4 == 0,
@@ -366,8 +583,11 @@ int build_problem(const ContractionArgs& a, TcProblem* out) {
   p.gram = (a.epi == kEpiGramAtomic) ? 1 : 0;
   p.same_operand = (p.gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
                     a.A.rows == a.B.rows) ? 1 : 0;
-  p.tiles_m = ceil_div(a.A.rows, BM);
-  p.tiles_n = ceil_div(a.n_cols, BN);
+  p.pair = pair ? 1 : 0;
+  const int tile = pair ? 256 : 128;
+  p.tiles_m = ceil_div(a.A.rows, tile);
+  p.tiles_n = ceil_div(a.n_cols, tile);
+  NSGP_REQUIRE(!p.gram || p.tiles_m == p.tiles_n, "Gram: operands must have the same rows");
   p.n_tiles = p.gram ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   static const int vec_red = [] {
     const char* e = getenv("NSGP_VEC_RED");
@@ -376,6 +596,19 @@ int build_problem(const ContractionArgs& a, TcProblem* out) {
   p.vec_red = (vec_red && a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
   p.splits = 1;
   return 0;
+}
+
+// K blocks one TMEM accumulator chain may cover.  The tensor core accumulates with
+// truncation (~2^-25.6 relative per accumulate step, measured); the single-CTA kernel
+// keeps hi*hi in its own accumulator (4 steps per K block), the pair kernel has one
+// accumulator for all three products (12 steps per K block).
+int chain_limit(const TcParams& p) {
+  static const int gram_chain = [] {
+    const char* e = getenv("NSGP_CHAIN");             // bring-up override
+    return e ? atoi(e) : kChainGram;
+  }();
+  if (!p.gram) return kChainGemm;
+  return p.pair ? 32 : gram_chain;
 }
 
 }  // namespace
@@ -395,35 +628,23 @@ int sm_count() {
 
 int contraction_tc(const ContractionArgs& a, cudaStream_t stream) {
   TcProblem prob;
-  int rc = build_problem(a, &prob);
+  const bool gram = a.epi == kEpiGramAtomic;
+  const bool same = gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
+                    a.A.rows == a.B.rows;
+  const bool pair = want_pair(a.A.rows, gram, same);
+  int rc = build_problem(a, pair, &prob);
   if (rc == 1) return 0;
   if (rc) return rc;
   TcParams& p = prob.p;
-  NSGP_REQUIRE(!p.gram || p.tiles_m == p.tiles_n, "Gram: operands must have the same rows");
-  // CTA-pair kernel (256x256 tiles): measured (scripts/bench_gram.py) to run at the same
-  // power-capped rate as the single-CTA kernel once barrier polling is cheap, so its
-  // extra tile padding never pays; kept selectable for experiments.
-  static const int force_pair = [] {
-    const char* e = getenv("NSGP_PAIR_KERNEL");       // 1 = use it for every Gram
-    return e ? atoi(e) : 0;
-  }();
-  const bool pair = p.gram && p.same_operand && force_pair == 1;
-  if (pair) {
-    const int t2 = ceil_div(a.A.rows, 256);
-    p.tiles_m = p.tiles_n = t2;
-    p.n_tiles = t2 * (t2 + 1) / 2;
-  }
-  // K splits.  The tensor core accumulates with truncation (~2^-25.6 relative per
-  // accumulate step, measured), so the chain per TMEM accumulator is bounded; beyond
-  // that choose the split count that minimises  waves x (K blocks per item +
-  // per-item overhead) - the last wave of the static round-robin deal is the tail.
-  // Partial tiles are red.add'ed, so splits need no workspace.
-  // GEMM (W += update @ P): one chain per tile up to kChainGemm blocks (d <= 5120), so
-  // every W element takes ONE fp32 rounding like the reference's add_ and the result
-  // is deterministic.
+  // K splits: bound the accumulation chain, then choose the split count that
+  // minimises  waves x (K blocks per item + per-item overhead) - the last wave of the
+  // static round-robin deal is the tail.  Partial tiles are red.add'ed, so splits need
+  // no workspace.  GEMM (W += update @ P): one chain per tile up to kChainGemm blocks
+  // (d <= 5120), so every W element takes ONE fp32 rounding like the reference's add_
+  // and the result is deterministic.
   const int workers = pair ? sm_count() / 2 : sm_count();
   {
-    const int s_min = ceil_div(p.nkb, p.gram ? (pair ? 32 : kChainGram) : kChainGemm);
+    const int s_min = ceil_div(p.nkb, chain_limit(p));
     int s_max = p.nkb / 4 > s_min ? p.nkb / 4 : s_min;
     if (s_max > s_min + 64) s_max = s_min + 64;
     if (!p.gram) s_max = s_min;
@@ -437,25 +658,18 @@ int contraction_tc(const ContractionArgs& a, cudaStream_t stream) {
     }
     p.splits = best_s;
   }
-  if (pair) return launch_tc2_gram(prob.maps, p, stream);
-  rc = configure_kernel();
-  if (rc) return rc;
-  const int items = p.n_tiles * p.splits;
-  const int grid = items < sm_count() ? items : sm_count();
-  ProfScope prof(p.gram ? kProfGram : kProfGemm, stream);
-  contraction_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(prob.maps, p, nullptr, nullptr,
-                                                               items);
-  NSGP_LAUNCHED();
+  return launch_kernel(pair, prob.maps, p, nullptr, nullptr, p.n_tiles * p.splits,
+                       p.gram ? kProfGram : kProfGemm, stream);
+}
+
+int debug_read_counters(unsigned long long* out, int n) {
+  NSGP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_dbg_counters, (size_t)n * sizeof(unsigned long long)));
   return 0;
 }
 
 // ---------------------------------------------------------------- grouped launches
-namespace {
-int chain_splits(const TcParams& p) {
-  return ceil_div(p.nkb, p.gram ? kChainGram : kChainGemm);
-}
-}  // namespace
-
+// A group table holds up to two sub-tables: problems run by the single-CTA kernel and
+// problems run by the CTA-pair kernel (one launch each).
 size_t group_table_bytes(const ContractionArgs* probs, int n) {
   size_t items = 0;
   for (int i = 0; i < n; ++i) {
@@ -463,9 +677,10 @@ size_t group_table_bytes(const ContractionArgs* probs, int n) {
     const int nkb = k_blocks(probs[i].A);
     const bool gram = probs[i].epi == kEpiGramAtomic;
     const size_t tiles = gram ? (size_t)tm * (tm + 1) / 2 : (size_t)tm * tn;
-    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, gram ? kChainGram : kChainGemm);
+    // upper bound for either kernel: 128-tiles with the shortest chain
+    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, gram ? 32 : kChainGemm);
   }
-  return (size_t)n * sizeof(TcProblem) + items * sizeof(TcItem) + 256;
+  return (size_t)n * sizeof(TcProblem) + items * sizeof(TcItem) + 1024;
 }
 
 int group_table_build(const ContractionArgs* probs, int n, int kind, void* table_dev,
@@ -473,19 +688,22 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
   NSGP_REQUIRE(probs && table_dev && info && n >= 0, "group_build: bad arguments");
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
                "group_build: table must be 64-byte aligned");
-  std::vector<TcProblem> hp;
-  hp.reserve(n);
   struct Cost { long long c; TcItem it; };
-  std::vector<Cost> items;
+  std::vector<TcProblem> hp[2];
+  std::vector<Cost> items[2];
   for (int i = 0; i < n; ++i) {
+    const ContractionArgs& a = probs[i];
+    const bool gram = a.epi == kEpiGramAtomic;
+    const bool same = gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
+                      a.A.rows == a.B.rows;
+    const int k = want_pair(a.A.rows, gram, same) ? 1 : 0;
     TcProblem pr;
-    int rc = build_problem(probs[i], &pr);
+    int rc = build_problem(a, k == 1, &pr);
     if (rc == 1) continue;
     if (rc) return rc;
     const TcParams& p = pr.p;
-    NSGP_REQUIRE(!p.gram || p.tiles_m == p.tiles_n, "Gram: operands must have the same rows");
-    const int prob = (int)hp.size();
-    const int splits = chain_splits(p);
+    const int prob = (int)hp[k].size();
+    const int splits = ceil_div(p.nkb, chain_limit(p));
     for (int sp = 0; sp < splits; ++sp) {
       const int kb0 = (int)((long long)p.nkb * sp / splits);
       const int kb1 = (int)((long long)p.nkb * (sp + 1) / splits);
@@ -493,48 +711,54 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
         for (int cb = p.gram ? rb : 0; cb < p.tiles_n; ++cb) {
           Cost c;
           c.it = TcItem{prob, rb, cb, kb0, kb1, 0, 0, 0};
-          // cost ~ K blocks (+ fixed part); diagonal Gram tiles load half the bytes
-          c.c = (long long)(kb1 - kb0) * 8 + 16;
-          items.push_back(c);
+          c.c = (long long)(kb1 - kb0) * 8 + 16;       // ~ K blocks + a fixed part
+          items[k].push_back(c);
         }
     }
-    hp.push_back(pr);
+    hp[k].push_back(pr);
   }
-  // big items first; ties keep (problem, K range, tile) order so that tiles sharing
-  // operand rows of one K range run at the same time (L2 reuse)
-  std::stable_sort(items.begin(), items.end(),
-                   [](const Cost& x, const Cost& y) { return x.c > y.c; });
-  info->n_problems = (int)hp.size();
-  info->n_items = (int)items.size();
+  size_t off = 0;
   info->kind = kind;
-  info->off_items = hp.size() * sizeof(TcProblem);
-  info->bytes = info->off_items + items.size() * sizeof(TcItem);
+  for (int k = 0; k < 2; ++k) {
+    // big items first; ties keep (problem, K range, tile) order so that tiles sharing
+    // operand rows of one K range run at the same time (L2 reuse)
+    std::stable_sort(items[k].begin(), items[k].end(),
+                     [](const Cost& x, const Cost& y) { return x.c > y.c; });
+    SubGroup& sg = info->sub[k];
+    sg.n_problems = (int)hp[k].size();
+    sg.n_items = (int)items[k].size();
+    sg.off_probs = off;
+    sg.off_items = off + hp[k].size() * sizeof(TcProblem);
+    off = (size_t)round_up((long long)(sg.off_items + items[k].size() * sizeof(TcItem)), 64);
+  }
+  info->bytes = off;
   NSGP_REQUIRE(info->bytes <= table_bytes, "group_build: table too small (%zu < %zu)",
                table_bytes, info->bytes);
-  if (info->n_items == 0) return 0;
-  std::vector<TcItem> hi(items.size());
-  for (size_t i = 0; i < items.size(); ++i) hi[i] = items[i].it;
-  NSGP_CHECK_CUDA(cudaMemcpyAsync(table_dev, hp.data(), info->off_items, cudaMemcpyHostToDevice,
-                                  stream));
-  NSGP_CHECK_CUDA(cudaMemcpyAsync((char*)table_dev + info->off_items, hi.data(),
-                                  hi.size() * sizeof(TcItem), cudaMemcpyHostToDevice, stream));
+  for (int k = 0; k < 2; ++k) {
+    const SubGroup& sg = info->sub[k];
+    if (sg.n_items == 0) continue;
+    std::vector<TcItem> hi(items[k].size());
+    for (size_t i = 0; i < items[k].size(); ++i) hi[i] = items[k][i].it;
+    NSGP_CHECK_CUDA(cudaMemcpyAsync((char*)table_dev + sg.off_probs, hp[k].data(),
+                                    hp[k].size() * sizeof(TcProblem), cudaMemcpyHostToDevice,
+                                    stream));
+    NSGP_CHECK_CUDA(cudaMemcpyAsync((char*)table_dev + sg.off_items, hi.data(),
+                                    hi.size() * sizeof(TcItem), cudaMemcpyHostToDevice, stream));
+  }
   return 0;
 }
 
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream) {
-  if (info.n_items == 0) return 0;
-  int rc = configure_kernel();
-  if (rc) return rc;
-  const TcProblem* probs = reinterpret_cast<const TcProblem*>(table_dev);
-  const TcItem* items =
-      reinterpret_cast<const TcItem*>((const char*)table_dev + info.off_items);
-  const int grid = info.n_items < sm_count() ? info.n_items : sm_count();
   static const TcMaps dummy_maps{};
   TcParams dummy{};
-  ProfScope prof(info.kind, stream);
-  contraction_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(dummy_maps, dummy, probs, items,
-                                                               info.n_items);
-  NSGP_LAUNCHED();
+  for (int k = 1; k >= 0; --k) {          // pair sub-table first: it holds the big layers
+    const SubGroup& sg = info.sub[k];
+    if (sg.n_items == 0) continue;
+    const TcProblem* probs = reinterpret_cast<const TcProblem*>((const char*)table_dev + sg.off_probs);
+    const TcItem* items = reinterpret_cast<const TcItem*>((const char*)table_dev + sg.off_items);
+    int rc = launch_kernel(k == 1, dummy_maps, dummy, probs, items, sg.n_items, info.kind, stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -229,6 +229,40 @@ threshold_count_kernel(const float* __restrict__ S, int n, int ld, float thresh,
   if (lane == 0) counts[i] = cnt;
 }
 
+// batched over classes: blockIdx.y = class, per-class extents from a small device table
+__global__ void __launch_bounds__(256)
+threshold_count_batched_kernel(const float* __restrict__ S_all,
+                               const ClassExtent* __restrict__ ext, float thresh,
+                               unsigned char* __restrict__ mask_all,
+                               int* __restrict__ counts_all) {
+  const ClassExtent e = ext[blockIdx.y];
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= e.n) return;
+  const float* S = S_all + e.s_off;
+  unsigned char* mask = mask_all + e.mask_off;
+  int cnt = 0;
+  for (int j = lane; j < e.n; j += 32) {
+    float v = (i <= j) ? S[(long long)i * e.ld + j] : S[(long long)j * e.ld + i];
+    bool m = v >= thresh;
+    mask[(long long)i * e.n + j] = m ? 1 : 0;
+    cnt += m;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts_all[e.row_off + i] = cnt;
+}
+
+int launch_threshold_count_batched(const float* S_all, const ClassExtent* ext_dev, int n_classes,
+                                   int max_n, float thresh, unsigned char* mask_all,
+                                   int* counts_all, cudaStream_t stream) {
+  if (n_classes == 0 || max_n == 0) return 0;
+  dim3 grid(ceil_div(max_n, 8), n_classes);
+  threshold_count_batched_kernel<<<grid, 256, 0, stream>>>(S_all, ext_dev, thresh, mask_all,
+                                                           counts_all);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
 int launch_threshold_count(const float* S, int n, int ld, float thresh, unsigned char* mask,
                            int* counts, float* sim_out, cudaStream_t stream) {
   if (n == 0) return 0;

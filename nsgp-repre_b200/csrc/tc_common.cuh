@@ -31,6 +31,7 @@ struct TcParams {
   int same_operand;               // Gram: B is A
   int vec_red;                    // use red.global.add.v4.f32 in the epilogue
   int gram;                       // 1: upper block-triangle of A*A^T, 0: full A*B^T
+  int pair;                       // tiles are 256 x 256 over a CTA pair (cta_group::2)
 };
 
 // Grouped launches: many problems in one persistent launch.  The table lives in
@@ -164,6 +165,156 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 
+// ---- warp-convergent single-thread issue ------------------------------------------
+// tcgen05.mma / TMA / commit are issued by ONE thread, but putting them inside an
+// `if (lane == 0)` region makes the compiler wrap every one of them in an
+// ELECT + R2UR.BROADCAST + branch loop (uniform-datapath instructions under
+// divergence): ~20 extra instructions per MMA, enough to starve the tensor pipe of
+// 64-cycle MMAs.  These wrappers are executed by the whole (converged) warp with
+// warp-uniform operands and elect the issuing thread inside the asm block.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map,
+                                                  uint64_t* bar, int x, int c) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(c)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::
+      "r"(smem_u32(bar))
+      : "memory");
+}
+// One K block (32 fp32 = 4 K steps of 8) of the 3xTF32 product, 12 MMAs in one asm
+// block: hi*hi -> d_main, lo*hi and hi*lo -> d_corr (d_corr == d_main: one accumulator).
+// Descriptors advance by 2 (32 bytes >> 4) per K step.  `first` = 0 overwrites the
+// accumulators at the first K step.
+__device__ __forceinline__ void tc_mma_kblock_3xtf32(uint32_t d_main, uint32_t d_corr,
+                                                     uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                                     uint64_t b_lo, uint32_t idesc,
+                                                     uint32_t first, uint32_t same_acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pf, pc, pt;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      ".reg .b64 ah, al, bh, bl;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %7, 0;\n\t"            // accumulate into d_main at K step 0?
+      "setp.eq.b32 pc, %8, 1;\n\t"            // same accumulator: corr never overwrites
+      "or.pred pc, pc, pf;\n\t"
+      ".reg .pred ps;\n\t"                    // bring-up: same_acc == 2 skips the hi*lo product
+      "setp.ne.b32 ps, %8, 2;\n\t"
+      "and.pred ps, ps, pe;\n\t"
+      // K step 0
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pc;\n\t"
+      "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, pt;\n\t"
+      // K step 1
+      "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
+      // K step 2
+      "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
+      // K step 3
+      "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
+      "}" ::"r"(d_main),
+      "r"(d_corr), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(first),
+      "r"(same_acc)
+      : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) versions of the same ---------------------------------
+__device__ __forceinline__ void tma_load_2d_2sm_elect(uint32_t dst, const CUtensorMap* map,
+                                                      uint64_t* bar, int x, int c) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(c)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t.reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], m;\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_elect(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t.reg .b32 ra;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "@pe mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(
+          smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// one K block, 12 MMAs over the CTA pair (M = 256), single accumulator
+__device__ __forceinline__ void tc_mma_kblock_3xtf32_2sm(uint32_t d, uint64_t a_hi, uint64_t a_lo,
+                                                         uint64_t b_hi, uint64_t b_lo,
+                                                         uint32_t idesc, uint32_t first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pf, pt;\n\t"
+      ".reg .b64 ah, al, bh, bl;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, %6, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], %2, %3, %5, pf;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %4, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %3, %5, pt;\n\t"
+      "add.u64 ah, %1, 2; add.u64 al, %2, 2; add.u64 bh, %3, 2; add.u64 bl, %4, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], al, bh, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bl, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bh, %5, pt;\n\t"
+      "add.u64 ah, %1, 4; add.u64 al, %2, 4; add.u64 bh, %3, 4; add.u64 bl, %4, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], al, bh, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bl, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bh, %5, pt;\n\t"
+      "add.u64 ah, %1, 6; add.u64 al, %2, 6; add.u64 bh, %3, 6; add.u64 bl, %4, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], al, bh, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bl, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], ah, bh, %5, pt;\n\t"
+      "}" ::"r"(d),
+      "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(first)
+      : "memory");
+}
+
+// TMA prefetch of one box into L2 (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d_elect(const CUtensorMap* map, int x, int c) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(x), "r"(c)
+      : "memory");
+}
+
 // ---- cluster / 2-CTA variants ------------------------------------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same
                                                  // offset in the even CTA of a pair
@@ -216,8 +367,6 @@ int sm_count();
 // chain limits (K blocks accumulated in one TMEM accumulator pair)
 constexpr int kChainGram = 64;
 constexpr int kChainGemm = 160;
-// 2-CTA (cta_group::2) 256x256-tile Gram kernel, contraction_tc2.cu
-int launch_tc2_gram(const TcMaps& maps, const TcParams& p, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace nsgp

@@ -97,18 +97,37 @@ class MultiPrototypeReplay:
                            device=dev)
         cnt_all = pack[mask_pad:mask_pad + 4 * cnt_elems].view(torch.int32)
         pack[mask_pad + 4 * cnt_elems:].view(torch.int32).copy_(rows)
-        need = max(lib.repre_cosine_count_workspace_bytes(n, D) for n in sizes)
-        ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
-            self._ws.device == dev else torch.empty(int(need), dtype=torch.uint8, device=dev)
-        self._ws = ws
-        m_off = c_off = 0
-        for c, n in zip(previous_cls, sizes):
-            check(lib.repre_cosine_count(
-                ptr(feats), D, rows.data_ptr() + 4 * h_off[c], n, float(self.thresh),
-                pack.data_ptr() + m_off, cnt_all.data_ptr() + 4 * c_off, None, ptr(ws),
-                ws.numel(), stream), "repre_cosine_count")
-            m_off += n * n
-            c_off += n
+        if lib.nsgp_get_engine() == 0:
+            # all classes at once: normalise, clear, ONE grouped tcgen05 Gram, threshold
+            import ctypes
+            ncls = len(sizes)
+            sizes_arr = (ctypes.c_int32 * ncls)(*sizes)
+            need = int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D))
+            ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
+                self._ws.device == dev else torch.empty(need, dtype=torch.uint8, device=dev)
+            self._ws = ws
+            consecutive = all(b == a + 1 for a, b in zip(previous_cls, previous_cls[1:]))
+            if consecutive:
+                rows_sel = rows[h_off[previous_cls[0]]:h_off[previous_cls[-1] + 1]]
+            else:
+                rows_sel = torch.cat([rows[h_off[c]:h_off[c + 1]] for c in previous_cls])
+            check(lib.repre_cosine_count_batched(
+                ptr(feats), D, ptr(rows_sel), sizes_arr, ncls, float(self.thresh),
+                pack.data_ptr(), cnt_all.data_ptr(), ptr(ws), ws.numel(), stream),
+                "repre_cosine_count_batched")
+        else:
+            need = max(lib.repre_cosine_count_workspace_bytes(n, D) for n in sizes)
+            ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
+                self._ws.device == dev else torch.empty(int(need), dtype=torch.uint8, device=dev)
+            self._ws = ws
+            m_off = c_off = 0
+            for c, n in zip(previous_cls, sizes):
+                check(lib.repre_cosine_count(
+                    ptr(feats), D, rows.data_ptr() + 4 * h_off[c], n, float(self.thresh),
+                    pack.data_ptr() + m_off, cnt_all.data_ptr() + 4 * c_off, None, ptr(ws),
+                    ws.numel(), stream), "repre_cosine_count")
+                m_off += n * n
+                c_off += n
         host = pack.cpu().numpy()                                   # the one sync
         h_cnt = host[mask_pad:mask_pad + 4 * cnt_elems].view(np.int32)
         h_rows_np = host[mask_pad + 4 * cnt_elems:].view(np.int32)
