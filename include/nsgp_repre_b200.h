@@ -61,7 +61,9 @@ int nsgp_profile_read(int kind, double* ms_total /* host */,
  *   ld     = leading dimension (elements) of the accumulator, = round_up(d_int,4) */
 typedef struct {
   int d, d_int, taps, ld;
-  size_t acc_bytes;        /* ld * d_int * 4: zero it once before the first call */
+  int kind;                /* 0: tap-major upper block-triangle of the d_int x d_int Gram
+                              1: autocorrelation layout (3x3 s1 p1): 29 running C x C matrices */
+  size_t acc_bytes;        /* zero it once before the first call */
   size_t workspace_bytes;  /* scratch for one accumulate call */
 } nsgp_cov_layout_t;
 

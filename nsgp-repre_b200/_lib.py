@@ -19,7 +19,7 @@ c_void_p, c_int, c_size_t, c_float, c_double = C.c_void_p, C.c_int, C.c_size_t, 
 
 
 class CovLayout(C.Structure):
-    _fields_ = [("d", c_int), ("d_int", c_int), ("taps", c_int), ("ld", c_int),
+    _fields_ = [("d", c_int), ("d_int", c_int), ("taps", c_int), ("ld", c_int), ("kind", c_int),
                 ("acc_bytes", c_size_t), ("workspace_bytes", c_size_t)]
 
 

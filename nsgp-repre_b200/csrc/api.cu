@@ -108,8 +108,15 @@ int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, 
   out->d = g.d;
   out->d_int = g.d_int;
   out->taps = g.T;
-  out->ld = (int)round_up(g.d_int, 4);
-  out->acc_bytes = (size_t)out->ld * g.d_int * sizeof(float);
+  if (g.mode == kModeAutocorr) {
+    out->kind = 1;
+    out->ld = (int)round_up(g.C, 4);
+    out->acc_bytes = (size_t)kAcMats * g.C * out->ld * sizeof(float);
+  } else {
+    out->kind = 0;
+    out->ld = (int)round_up(g.d_int, 4);
+    out->acc_bytes = (size_t)out->ld * g.d_int * sizeof(float);
+  }
   out->workspace_bytes = stage_bytes(g) + 1024;
   return 0;
 }
@@ -119,6 +126,7 @@ int nsgp_cov_linear_layout(int d, nsgp_cov_layout_t* out) {
   out->d = d;
   out->d_int = d;
   out->taps = 1;
+  out->kind = 0;
   out->ld = (int)round_up(d, 4);
   out->acc_bytes = (size_t)out->ld * d * sizeof(float);
   out->workspace_bytes = (size_t)round_up(d, 4) * sizeof(float) + 256;
@@ -158,17 +166,18 @@ int nsgp_cov_conv2d_contract(int C, int H, int W, int kh, int kw, int sh, int sw
   int rc = cov_conv2d_setup(C, H, W, kh, kw, sh, sw, ph, pw, const_cast<void*>(workspace),
                             workspace_bytes, &g, &stage);
   if (rc) return rc;
-  ContractionArgs a{};
-  a.A = conv_operand(g, stage);
-  a.B = a.A;
-  a.out = acc;
-  a.ld = (int)round_up(g.d_int, 4);
-  a.n_cols = a.A.rows;
-  a.alpha = 1.f;
-  a.epi = kEpiGramAtomic;
-  int tiles_1d = ceil_div(a.A.rows, 128);
-  a.splits = pick_splits(tiles_1d * (tiles_1d + 1) / 2, k_blocks(a.A));
-  return contraction(a, (cudaStream_t)stream_);
+  ContractionArgs probs[kMaxConvProblems];
+  int n = 0;
+  conv_problems(g, stage, acc, probs, &n);
+  for (int i = 0; i < n; ++i) {
+    if (probs[i].epi == kEpiGramAtomic) {
+      int tiles_1d = ceil_div(probs[i].A.rows, 128);
+      probs[i].splits = pick_splits(tiles_1d * (tiles_1d + 1) / 2, k_blocks(probs[i].A));
+    }
+    rc = contraction(probs[i], (cudaStream_t)stream_);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int nsgp_cov_conv2d_accumulate(const float* x, int B, int C, int H, int W, int kh, int kw,
@@ -198,6 +207,10 @@ int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* L, float* cov_o
                       int accumulate, void* stream_) {
   NSGP_REQUIRE(acc && L && cov_out, "cov_finalize: null pointer");
   NSGP_REQUIRE(L->taps >= 1 && L->d % L->taps == 0, "cov_finalize: bad layout");
+  if (L->kind == 1) {
+    NSGP_REQUIRE(L->taps == 9, "cov_finalize: autocorrelation layout needs 9 taps");
+    return launch_cov_finalize_autocorr(acc, cov_out, L->d / 9, accumulate, (cudaStream_t)stream_);
+  }
   return launch_cov_finalize(acc, L->ld, cov_out, L->d / L->taps, L->taps, accumulate,
                              (cudaStream_t)stream_);
 }
@@ -385,46 +398,40 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
 }
 
 // ---- grouped covariance contraction (deferred mode of the hooks) ----------------
-static int cov_job_args(const nsgp_cov_job_t& j, ContractionArgs* out) {
+static int cov_job_problems(const nsgp_cov_job_t& j, std::vector<ContractionArgs>* out) {
   ConvGeom g;
   float* stage;
   int rc = cov_conv2d_setup(j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw,
                             const_cast<void*>(j.workspace), j.workspace_bytes, &g, &stage);
   if (rc) return rc;
   NSGP_REQUIRE(j.acc != nullptr, "cov_group: null accumulator");
-  ContractionArgs a{};
-  a.A = conv_operand(g, stage);
-  a.B = a.A;
-  a.out = j.acc;
-  a.ld = (int)round_up(g.d_int, 4);
-  a.n_cols = a.A.rows;
-  a.alpha = 1.f;
-  a.epi = kEpiGramAtomic;
-  a.splits = 1;
-  *out = a;
+  ContractionArgs probs[kMaxConvProblems];
+  int n = 0;
+  conv_problems(g, stage, j.acc, probs, &n);
+  out->insert(out->end(), probs, probs + n);
   return 0;
 }
 
 size_t nsgp_cov_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs) {
   if (!jobs || n_jobs <= 0) return 1024;
-  std::vector<ContractionArgs> probs(n_jobs);
+  std::vector<ContractionArgs> probs;
   for (int i = 0; i < n_jobs; ++i)
-    if (cov_job_args(jobs[i], &probs[i])) return 0;
-  return group_table_bytes(probs.data(), n_jobs) + 256;
+    if (cov_job_problems(jobs[i], &probs)) return 0;
+  return group_table_bytes(probs.data(), (int)probs.size()) + 256;
 }
 
 int nsgp_cov_group_build(const nsgp_cov_job_t* jobs, int n_jobs, void* table_dev,
                          size_t table_bytes, nsgp_group_t* group, void* stream_) {
   NSGP_REQUIRE(jobs && table_dev && group && n_jobs > 0, "cov_group_build: bad arguments");
   NSGP_REQUIRE(g_engine == 0, "cov_group_build: groups need the tcgen05 engine");
-  std::vector<ContractionArgs> probs(n_jobs);
+  std::vector<ContractionArgs> probs;
   for (int i = 0; i < n_jobs; ++i) {
-    int rc = cov_job_args(jobs[i], &probs[i]);
+    int rc = cov_job_problems(jobs[i], &probs);
     if (rc) return rc;
   }
   GroupInfo gi{};
-  int rc = group_table_build(probs.data(), n_jobs, kProfGram, table_dev, table_bytes, &gi,
-                             (cudaStream_t)stream_);
+  int rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table_dev, table_bytes,
+                             &gi, (cudaStream_t)stream_);
   if (rc) return rc;
   group_to_abi(gi, group);
   return 0;

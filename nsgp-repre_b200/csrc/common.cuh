@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace nsgp {
@@ -99,7 +100,8 @@ struct ContractionArgs {
   int n_cols;       // valid output columns (= B.rows)
   float alpha;
   int epi;          // EpiMode
-  int splits;       // split-K factor (Gram only)
+  int splits;       // split-K factor (SIMT engine, Gram only)
+  int chain;        // tcgen05 engine: K blocks per accumulator chain (0 = default for epi)
 };
 
 // grouped contraction (tcgen05 engine only): a host-side list of problems that is

@@ -584,6 +584,7 @@ int build_problem(const ContractionArgs& a, bool pair, TcProblem* out) {
   p.same_operand = (p.gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
                     a.A.rows == a.B.rows) ? 1 : 0;
   p.pair = pair ? 1 : 0;
+  p.chain = a.chain;
   const int tile = pair ? 256 : 128;
   p.tiles_m = ceil_div(a.A.rows, tile);
   p.tiles_n = ceil_div(a.n_cols, tile);
@@ -607,6 +608,7 @@ int chain_limit(const TcParams& p) {
     const char* e = getenv("NSGP_CHAIN");             // bring-up override
     return e ? atoi(e) : kChainGram;
   }();
+  if (p.chain > 0) return p.pair && p.chain > 32 ? 32 : p.chain;
   if (!p.gram) return kChainGemm;
   return p.pair ? 32 : gram_chain;
 }
@@ -678,7 +680,7 @@ size_t group_table_bytes(const ContractionArgs* probs, int n) {
     const bool gram = probs[i].epi == kEpiGramAtomic;
     const size_t tiles = gram ? (size_t)tm * (tm + 1) / 2 : (size_t)tm * tn;
     // upper bound for either kernel: 128-tiles with the shortest chain
-    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, gram ? 32 : kChainGemm);
+    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, (gram || probs[i].chain > 0) ? 32 : kChainGemm);
   }
   return (size_t)n * sizeof(TcProblem) + items * sizeof(TcItem) + 1024;
 }

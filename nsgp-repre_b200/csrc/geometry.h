@@ -9,7 +9,27 @@ enum StageMode : int {
   kModeImplicit = 0,  // kw column-shifted copies per row phase; row taps are TMA y offsets
   kModeFlat = 1,      // 1x1, pad 0: K = Hout*Wout flattened, no halo, no waste
   kModeExplicit = 2,  // explicit im2col rows in reference order (fallback)
+  kModeAutocorr = 3,  // 3x3 s1 p1: spatial autocorrelation blocks + edge corrections
 };
+
+// Autocorrelation layout (3x3, stride 1, pad 1).  With m the batch-averaged map and
+// zero padding, the covariance block of taps (i,j),(i',j') is
+//     G = R_D - [i=i'=0] RowE(bottom, dx) - [i=i'=2] RowE(top, dx)
+//             - [j=j'=0] ColE(right, dy)  - [j=j'=2] ColE(left, dy)  + [corner tap, same tap] Corner
+// with D = (dy,dx) = (i'-i, j'-j),  R_D[c,c'] = sum_{u,v} m[c][u][v] m[c'][u+dy][v+dx]  the
+// spatial autocorrelation at displacement D, and RowE / ColE / Corner the same sums
+// restricted to one edge row / edge column / corner pixel (derivation in DESIGN.md; a
+// numpy check is tests/test_oracle_golden.py::test_autocorrelation_identity).  Only 13
+// displacements occur in the upper triangle, so a layer costs 12.5 C x C x K GEMM blocks
+// instead of the 40.5 of the tap-pair Gram: 3.2x fewer tensor FLOPs for the same result.
+// Accumulator = 29 running C x C matrices; nsgp_cov_finalize assembles the d x d matrix.
+constexpr int kAcR = 13, kAcMats = 29;
+constexpr int kAcRowBottom = 13, kAcRowTop = 16, kAcColRight = 19, kAcColLeft = 22,
+              kAcCorner = 25;
+// index of R_(dy,dx) for dy in {0,1,2}: (0,0) (0,1) (0,2) (1,-2..2) (2,-2..2)
+static inline __host__ __device__ int ac_ridx(int dy, int dx) {
+  return dy == 0 ? dx : 3 + (dy - 1) * 5 + (dx + 2);
+}
 
 // Implicit layout.  TMA needs the innermost (column) coordinate 16-byte aligned, so
 // a +-1 column tap shift cannot be a coordinate.  Instead every kernel column j gets
@@ -53,6 +73,18 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
   g.d = C * kh * kw;
   g.ncopy = 1; g.nrowphase = 1;
   const bool one_by_one = (kh == 1 && kw == 1 && ph == 0 && pw == 0);
+  static const bool no_autocorr = getenv("NSGP_NO_AUTOCORR") != nullptr;   // bring-up switch
+  if (!no_autocorr && kh == 3 && kw == 3 && sh == 1 && sw == 1 && ph == 1 && pw == 1 &&
+      C % 8 == 0 && H >= 3 && W >= 3) {
+    g.mode = kModeAutocorr;
+    g.T = 9; g.Cs = C; g.ncopy = 3;
+    g.Hs = H + 2;                                  // two zero rows below
+    g.Ws = (int)round_up(W + 2, 4);                // >= two zero columns on the right
+    g.Ht = 0;
+    g.d_int = kAcMats * C;
+    *out = g;
+    return 0;
+  }
   if (one_by_one && C % 8 == 0) {
     g.mode = kModeFlat;
     g.T = 1; g.Cs = C;
@@ -83,7 +115,14 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
   return 0;
 }
 
+// autocorr extras: edge columns (2 sides x 3 row shifts, pitch Hc) and corner pixels
+static inline int ac_col_pitch(const ConvGeom& g) { return (int)round_up(g.H + 2, 4); }
+static inline long long ac_colbuf_off(const ConvGeom& g) { return 3LL * g.C * g.Hs * g.Ws; }
+static inline long long ac_cornerbuf_off(const ConvGeom& g) {
+  return ac_colbuf_off(g) + 6LL * g.C * ac_col_pitch(g);
+}
 static inline long long stage_hl_stride(const ConvGeom& g) {
+  if (g.mode == kModeAutocorr) return round_up(ac_cornerbuf_off(g) + 16LL * g.C, 4);
   return (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
 }
 static inline size_t stage_bytes(const ConvGeom& g) {
@@ -130,7 +169,74 @@ static inline Operand matrix_operand(const float* hi, const float* lo, int rows,
   return o;
 }
 
+// The contraction problems of one staged conv input: one Gram for the tap-pair layouts,
+// 29 small-N GEMMs for the autocorrelation layout.  acc: the layer's accumulator.
+static inline void conv_problems(const ConvGeom& g, const float* stage, float* acc,
+                                 ContractionArgs* out, int* n_out) {
+  if (g.mode != kModeAutocorr) {
+    ContractionArgs a{};
+    a.A = conv_operand(g, stage);
+    a.B = a.A;
+    a.out = acc;
+    a.ld = (int)round_up(g.d_int, 4);
+    a.n_cols = a.A.rows;
+    a.alpha = 1.f;
+    a.epi = kEpiGramAtomic;
+    a.splits = 1;
+    out[0] = a;
+    *n_out = 1;
+    return;
+  }
+  const int C = g.C, ldc = (int)round_up(C, 4);
+  const long long hl = stage_hl_stride(g), plane = (long long)C * g.Hs * g.Ws;
+  const int pitch = g.Hs * g.Ws, Kmain = g.H * g.Ws;
+  const int Hc = ac_col_pitch(g);
+  int n = 0;
+  auto mat = [&](int idx) { return acc + (long long)idx * C * ldc; };
+  auto add = [&](const float* a_base, const float* b_base, int K, int ld, float* dst, bool gram) {
+    ContractionArgs a{};
+    a.A = matrix_operand(a_base, a_base + hl, C, K, ld);
+    a.B = matrix_operand(b_base, b_base + hl, C, K, ld);
+    a.out = dst;
+    a.ld = ldc;
+    a.n_cols = C;
+    a.alpha = 1.f;
+    a.epi = gram ? kEpiGramAtomic : kEpiGemmRmw;
+    a.splits = 1;
+    a.chain = 64;
+    out[n++] = a;
+  };
+  // R_(dy,dx)
+  for (int dy = 0; dy <= 2; ++dy)
+    for (int dx = (dy == 0 ? 0 : -2); dx <= 2; ++dx) {
+      const float* a_base = stage + (dx < 0 ? -dx : 0) * plane;
+      const float* b_base = stage + (dx > 0 ? dx : 0) * plane + (long long)dy * g.Ws;
+      add(a_base, b_base, Kmain, pitch, mat(ac_ridx(dy, dx)), dy == 0 && dx == 0);
+    }
+  // edge rows: bottom (u = H-1) and top (u = 0), dx = 0..2
+  for (int e = 0; e < 2; ++e) {
+    const long long row = (long long)(e == 0 ? g.H - 1 : 0) * g.Ws;
+    for (int dx = 0; dx <= 2; ++dx)
+      add(stage + row, stage + dx * plane + row, g.Ws, pitch,
+          mat((e == 0 ? kAcRowBottom : kAcRowTop) + dx), false);
+  }
+  // edge columns: right (v = W-1) and left (v = 0), dy = 0..2
+  const float* cb = stage + ac_colbuf_off(g);
+  for (int e = 0; e < 2; ++e)
+    for (int dy = 0; dy <= 2; ++dy)
+      add(cb + (long long)(e * 3) * C * Hc, cb + (long long)(e * 3 + dy) * C * Hc, Hc, Hc,
+          mat((e == 0 ? kAcColRight : kAcColLeft) + dy), false);
+  // corner pixels of the four corner taps
+  const float* kb = stage + ac_cornerbuf_off(g);
+  for (int q = 0; q < 4; ++q)
+    add(kb + (long long)q * C * 4, kb + (long long)q * C * 4, 4, 4, mat(kAcCorner + q), false);
+  *n_out = n;
+}
+constexpr int kMaxConvProblems = kAcMats;
+
 int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B, cudaStream_t s);
+int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,
+                                 cudaStream_t s);
 int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,
                       cudaStream_t s);
 int launch_cov_finalize(const float* acc, int ld, float* out, int C, int T, int accumulate,

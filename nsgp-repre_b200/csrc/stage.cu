@@ -178,6 +178,154 @@ stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, i
 }
 
 // ---------------------------------------------------------------------------
+// Autocorrelation layout (3x3 s1 p1, geometry.h): three column-shifted copies of the
+// zero-extended batch mean, copy_s[c][r][x] = m~[c][r][x+s], r < H+2, x < Ws, plus the
+// edge-column and corner-pixel buffers of the boundary corrections.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                      int W, int Hs, int Ws, int B, long long hl_stride) {
+  const long long plane = (long long)C * Hs * Ws;
+  const long long total = plane * 3;
+  const long long img = (long long)C * H * W;
+  const float fb = (float)B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int xs = (int)(idx % Ws);
+    long long rest = idx / Ws;
+    int r = (int)(rest % Hs);
+    rest /= Hs;
+    int c = (int)(rest % C);
+    int s = (int)(rest / C);
+    int xx = xs + s;
+    float v = 0.f;
+    if (r < H && xx < W) {
+      const float* p = x + ((long long)c * H + r) * W + xx;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int b = 0; b < B; ++b) acc += __ldg(p + (long long)b * img);
+      v = acc / fb;
+    }
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    stage[idx] = hi;
+    stage[idx + hl_stride] = lo;
+  }
+}
+
+// W % 4 == 0, 16-byte aligned input: one thread per aligned float4 of a staged row.
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                          int W, int B, long long hl_stride) {
+  const int Hs = H + 2, Ws = W + 4, W4 = Ws >> 2;
+  const long long total = (long long)C * Hs * W4;
+  const long long img = (long long)C * H * W;
+  const long long plane = (long long)C * Hs * Ws;
+  const float fb = (float)B;
+  const int lane = threadIdx.x & 31;
+  const long long total_r = (total + 31) / 32 * 32;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_r;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const bool live = idx < total;
+    int x4 = 0, r = 0, c = 0;
+    if (live) {
+      x4 = (int)(idx % W4);
+      long long rest = idx / W4;
+      r = (int)(rest % Hs);
+      c = (int)(rest / Hs);
+    }
+    const bool data = live && r < H && x4 * 4 < W;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = x + ((long long)c * H + r) * W + x4 * 4;
+    if (data) {
+      int b = 0;
+      for (; b + B_UNROLL <= B; b += B_UNROLL) {
+        float4 v[B_UNROLL];
+#pragma unroll
+        for (int u = 0; u < B_UNROLL; ++u) v[u] = ldg_stream4(p + (long long)(b + u) * img);
+#pragma unroll
+        for (int u = 0; u < B_UNROLL; ++u) { m.x += v[u].x; m.y += v[u].y; m.z += v[u].z; m.w += v[u].w; }
+      }
+      for (; b < B; ++b) {
+        float4 v = ldg_stream4(p + (long long)b * img);
+        m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+      }
+      m.x /= fb; m.y /= fb; m.z /= fb; m.w /= fb;
+    }
+    // the next two means of the same row come from the next lane (or an extra load at
+    // the warp edge; zero past the row end)
+    float n0 = __shfl_down_sync(0xffffffffu, m.x, 1);
+    float n1 = __shfl_down_sync(0xffffffffu, m.y, 1);
+    const bool next_data = data && (x4 + 1) * 4 < W;
+    if (!next_data) {
+      n0 = n1 = 0.f;
+    } else if (lane == 31) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int b = 0; b < B; ++b) {
+        s0 += __ldg(p + 4 + (long long)b * img);
+        s1 += __ldg(p + 5 + (long long)b * img);
+      }
+      n0 = s0 / fb; n1 = s1 / fb;
+    }
+    if (live) {
+      float* o = stage + ((long long)c * Hs + r) * Ws + x4 * 4;
+      split_store4(o, o + hl_stride, m.x, m.y, m.z, m.w);                          // shift 0
+      split_store4(o + plane, o + plane + hl_stride, m.y, m.z, m.w, n0);          // shift 1
+      split_store4(o + 2 * plane, o + 2 * plane + hl_stride, m.z, m.w, n0, n1);   // shift 2
+    }
+  }
+}
+
+// edge columns colbuf[side][shift][c][u] = m~[c][u+shift][side ? 0 : W-1] (pitch Hc) and
+// corner pixels cornerbuf[q][c][0] (pitch 4): q = 0 (H-1,W-1), 1 (H-1,0), 2 (0,W-1), 3 (0,0)
+__global__ void __launch_bounds__(256)
+stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ colbuf,
+                            float* __restrict__ cornerbuf, int C, int H, int W, int Hc, int B,
+                            long long hl_stride) {
+  const long long n_col = 6LL * C * Hc, n_cor = 16LL * C;
+  const long long img = (long long)C * H * W;
+  const float fb = (float)B;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_col + n_cor;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c, y, xx;
+    bool valid;
+    float* dst;
+    if (idx < n_col) {
+      int u = (int)(idx % Hc);
+      long long rest = idx / Hc;
+      c = (int)(rest % C);
+      int ss = (int)(rest / C);
+      int side = ss / 3, shift = ss - side * 3;
+      y = u + shift;
+      xx = side ? 0 : W - 1;
+      valid = y < H;
+      dst = colbuf + idx;
+    } else {
+      long long j = idx - n_col;
+      int e = (int)(j & 3);
+      c = (int)((j >> 2) % C);
+      int q = (int)((j >> 2) / C);
+      y = (q < 2) ? H - 1 : 0;
+      xx = (q & 1) ? 0 : W - 1;
+      valid = e == 0;
+      dst = cornerbuf + j;
+    }
+    float v = 0.f;
+    if (valid) {
+      const float* p = x + ((long long)c * H + y) * W + xx;
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) acc += __ldg(p + (long long)b * img);
+      v = acc / fb;
+    }
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    dst[0] = hi;
+    dst[hl_stride] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Explicit im2col fallback (any kernel size / dilation-free conv whose channel
 // count does not fit the implicit path, e.g. the 7x7 stem with Cin = 3).
 // Rows are written directly in the reference's (Cin, kh, kw) order.
@@ -223,6 +371,29 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
   const long long img = (long long)g.C * g.H * g.W;
   const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && img % 4 == 0;
   ProfScope prof(kProfStage, stream);
+  if (g.mode == kModeAutocorr) {
+    if (aligned && g.W % 4 == 0) {
+      long long n = (long long)g.C * g.Hs * (g.Ws / 4);
+      int blocks = (int)((n + 255) / 256);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      stage_autocorr_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl);
+    } else {
+      long long n = (long long)g.C * g.Hs * g.Ws * 3;
+      int blocks = (int)((n + 255) / 256);
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      stage_autocorr_kernel<<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, g.Hs, g.Ws, B, hl);
+    }
+    NSGP_LAUNCHED();
+    const int Hc = ac_col_pitch(g);
+    long long ne = 6LL * g.C * Hc + 16LL * g.C;
+    int eb = (int)((ne + 255) / 256);
+    if (eb > 148 * 8) eb = 148 * 8;
+    stage_autocorr_edges_kernel<<<eb, 256, 0, stream>>>(x, stage + ac_colbuf_off(g),
+                                                        stage + ac_cornerbuf_off(g), g.C, g.H,
+                                                        g.W, Hc, B, hl);
+    NSGP_LAUNCHED();
+    return 0;
+  }
   if (g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && aligned && (g.H * g.W) % 4 == 0) {
     long long n4 = (long long)g.C * g.H * g.W / 4;
     int blocks = (int)((n4 + 255) / 256);
@@ -309,6 +480,50 @@ cov_finalize_kernel(const float* __restrict__ acc, int ld, float* __restrict__ o
     if (accumulate) v += out[idx];
     out[idx] = v;
   }
+}
+
+// Autocorrelation layout -> reference-order dense symmetric covariance (geometry.h).
+__global__ void __launch_bounds__(256)
+cov_finalize_autocorr_kernel(const float* __restrict__ acc, float* __restrict__ out, int C,
+                             int ldc, int accumulate) {
+  const int d = C * 9;
+  const long long total = (long long)d * d;
+  const long long mat = (long long)C * ldc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % d), row = (int)(idx / d);
+    int a = row / 9, ta = row - a * 9, b = col / 9, tb = col - b * 9;
+    if (ta > tb) { int t = ta; ta = tb; tb = t; t = a; a = b; b = t; }   // transpose
+    const int i = ta / 3, j = ta - i * 3, i2 = tb / 3, j2 = tb - i2 * 3;
+    const int dy = i2 - i, dx = j2 - j;
+    const long long e = (long long)a * ldc + b;
+    float v;
+    if (dy == 0 && dx == 0) {            // R_0 is a Gram: only its upper block tiles exist
+      const int lo_i = a < b ? a : b, hi_i = a < b ? b : a;
+      v = acc[(long long)lo_i * ldc + hi_i];
+    } else {
+      v = acc[ac_ridx(dy, dx) * mat + e];
+    }
+    if (i == i2 && i == 0) v -= acc[(kAcRowBottom + dx) * mat + e];
+    if (i == i2 && i == 2) v -= acc[(kAcRowTop + dx) * mat + e];
+    if (j == j2 && j == 0) v -= acc[(kAcColRight + dy) * mat + e];
+    if (j == j2 && j == 2) v -= acc[(kAcColLeft + dy) * mat + e];
+    if (ta == tb && i != 1 && j != 1)
+      v += acc[(kAcCorner + (i == 0 ? 0 : 2) + (j == 0 ? 0 : 1)) * mat + e];
+    if (accumulate) v += out[idx];
+    out[idx] = v;
+  }
+}
+
+int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,
+                                 cudaStream_t stream) {
+  const long long total = 81LL * C * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cov_finalize_autocorr_kernel<<<blocks, 256, 0, stream>>>(acc, out, C, (int)round_up(C, 4),
+                                                          accumulate);
+  NSGP_LAUNCHED();
+  return 0;
 }
 
 int launch_cov_finalize(const float* acc, int ld, float* out, int C, int T, int accumulate,

@@ -32,6 +32,7 @@ struct TcParams {
   int vec_red;                    // use red.global.add.v4.f32 in the epilogue
   int gram;                       // 1: upper block-triangle of A*A^T, 0: full A*B^T
   int pair;                       // tiles are 256 x 256 over a CTA pair (cta_group::2)
+  int chain;                      // K blocks per accumulator chain (0: default)
 };
 
 // Grouped launches: many problems in one persistent launch.  The table lives in

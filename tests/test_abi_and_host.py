@@ -29,9 +29,13 @@ def test_library_exports_every_header_symbol():
 def test_layout_queries_are_host_only():
     from nsgp_repre_b200._lib import lib, CovLayout
     L = CovLayout()
-    # 3x3 s1 p1, Cin=256 at 50x84: implicit taps
+    # 3x3 s1 p1, Cin=256 at 50x84: autocorrelation layout, 29 running C x C matrices
     assert lib.nsgp_cov_conv2d_layout(256, 50, 84, 3, 3, 1, 1, 1, 1, L) == 0
-    assert (L.d, L.d_int, L.taps) == (2304, 2304, 9)
+    assert (L.d, L.d_int, L.taps, L.kind, L.ld) == (2304, 29 * 256, 9, 1, 256)
+    assert L.acc_bytes == 29 * 256 * 256 * 4
+    # 3x3 s2 p1: tap-pair layout with column-shifted copies
+    assert lib.nsgp_cov_conv2d_layout(256, 50, 84, 3, 3, 2, 2, 1, 1, L) == 0
+    assert (L.d, L.d_int, L.taps, L.kind) == (2304, 2304, 9, 0)
     # 7x7 s2 p3 stem, Cin=3 -> explicit im2col fallback, rows padded to 8
     assert lib.nsgp_cov_conv2d_layout(3, 64, 96, 7, 7, 2, 2, 3, 3, L) == 0
     assert (L.d, L.d_int, L.taps) == (147, 152, 1)

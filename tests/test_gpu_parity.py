@@ -97,6 +97,9 @@ GEOMS = [
     (3, 64, 96, 7, 2, 3, 2),      # stem, explicit im2col, d = 147
     (64, 17, 23, 1, 1, 0, 4),     # d = 64 < one tile
     (8, 9, 11, 3, 1, 1, 2),       # tiny
+    (16, 3, 3, 3, 1, 1, 2),       # smallest map the autocorrelation layout takes
+    (24, 12, 16, 3, 1, 1, 3),     # W % 4 == 0: vectorised autocorrelation staging, Cin = 24
+    (8, 2, 9, 3, 1, 1, 2),        # H < 3: falls back to the tap-pair layout
     (16, 12, 40, 5, 1, 2, 2),     # 25 taps -> explicit fallback
 ]
 

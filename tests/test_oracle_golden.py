@@ -101,6 +101,42 @@ def test_prototypes_match_reference(golden_dir):
     assert rel_fro(protos2, g["protos2"]) < 1e-6
 
 
+def test_autocorrelation_identity():
+    """The identity behind the B200 covariance kernel for 3x3 s1 p1 convs (csrc/geometry.h):
+    the unfold Gram of the reference (nsrunner_roi_replay.py:908-930) equals spatial
+    autocorrelation blocks R_(dy,dx) minus edge-row / edge-column sums plus corner terms."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    C, H, W = 4, 5, 6
+    m = rng.standard_normal((C, H, W))
+    ref = O.cov_conv2d(torch.from_numpy(m)[None], (3, 3), (1, 1), (1, 1)).numpy()
+
+    def px(u, v):
+        return m[:, u, v] if 0 <= u < H and 0 <= v < W else np.zeros(C)
+
+    def corr(points, dy, dx):
+        return sum(np.outer(m[:, u, v], px(u + dy, v + dx)) for u, v in points)
+
+    allp = [(u, v) for u in range(H) for v in range(W)]
+    G = np.zeros((9 * C, 9 * C))
+    for t in range(9):
+        for t2 in range(t, 9):
+            i, j, i2, j2 = t // 3, t % 3, t2 // 3, t2 % 3
+            dy, dx = i2 - i, j2 - j
+            g = corr(allp, dy, dx)
+            if i == i2 and i != 1:
+                g -= corr([(H - 1 if i == 0 else 0, v) for v in range(W)], dy, dx)
+            if j == j2 and j != 1:
+                g -= corr([(u, W - 1 if j == 0 else 0) for u in range(H)], dy, dx)
+            if t == t2 and i != 1 and j != 1:
+                g += corr([(H - 1 if i == 0 else 0, W - 1 if j == 0 else 0)], 0, 0)
+            for c in range(C):
+                for c2 in range(C):
+                    G[c * 9 + t, c2 * 9 + t2] = g[c, c2]
+                    G[c2 * 9 + t2, c * 9 + t] = g[c, c2]
+    assert np.abs(G - ref).max() < 1e-10
+
+
 def test_replay_loss_double_softmax():
     torch.manual_seed(0)
     score = torch.randn(7, 21)
