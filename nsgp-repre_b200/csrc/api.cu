@@ -98,6 +98,16 @@ int nsgp_profile_read(int kind, double* ms_total, unsigned long long* launches) 
 }
 
 // ---------------------------------------------------------------- covariance
+// Per-layer group table (autocorrelation layout: 29 problems -> one launch) kept behind
+// the staged operand in the same workspace.
+static size_t layer_table_bytes(const ConvGeom& g) {
+  if (g.mode != kModeAutocorr) return 0;
+  ContractionArgs probs[kMaxConvProblems];
+  int n = 0;
+  conv_problems(g, nullptr, nullptr, probs, &n);
+  return group_table_bytes(probs, n) + 1024;
+}
+
 int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
                            nsgp_cov_layout_t* out) {
   NSGP_REQUIRE(out != nullptr, "layout: out is null");
@@ -117,7 +127,7 @@ int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, 
     out->ld = (int)round_up(g.d_int, 4);
     out->acc_bytes = (size_t)out->ld * g.d_int * sizeof(float);
   }
-  out->workspace_bytes = stage_bytes(g) + 1024;
+  out->workspace_bytes = stage_bytes(g) + 1024 + layer_table_bytes(g);
   return 0;
 }
 
@@ -169,6 +179,15 @@ int nsgp_cov_conv2d_contract(int C, int H, int W, int kh, int kw, int sh, int sw
   ContractionArgs probs[kMaxConvProblems];
   int n = 0;
   conv_problems(g, stage, acc, probs, &n);
+  if (n > 1 && g_engine == 0) {
+    // one persistent launch for all problems of the layer
+    char* table = align_up((char*)stage + stage_bytes(g), 256);
+    const size_t room = (size_t)(((const char*)workspace + workspace_bytes) - table);
+    GroupInfo gi{};
+    rc = group_table_build(probs, n, kProfGram, table, room, &gi, (cudaStream_t)stream_);
+    if (rc) return rc;
+    return group_launch(table, gi, (cudaStream_t)stream_);
+  }
   for (int i = 0; i < n; ++i) {
     if (probs[i].epi == kEpiGramAtomic) {
       int tiles_1d = ceil_div(probs[i].A.rows, 128);
@@ -398,7 +417,8 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
 }
 
 // ---- grouped covariance contraction (deferred mode of the hooks) ----------------
-static int cov_job_problems(const nsgp_cov_job_t& j, std::vector<ContractionArgs>* out) {
+static int cov_job_problems(const nsgp_cov_job_t& j, int l2_group,
+                            std::vector<ContractionArgs>* out) {
   ConvGeom g;
   float* stage;
   int rc = cov_conv2d_setup(j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw,
@@ -407,7 +427,7 @@ static int cov_job_problems(const nsgp_cov_job_t& j, std::vector<ContractionArgs
   NSGP_REQUIRE(j.acc != nullptr, "cov_group: null accumulator");
   ContractionArgs probs[kMaxConvProblems];
   int n = 0;
-  conv_problems(g, stage, j.acc, probs, &n);
+  conv_problems(g, stage, j.acc, probs, &n, l2_group);
   out->insert(out->end(), probs, probs + n);
   return 0;
 }
@@ -416,7 +436,7 @@ size_t nsgp_cov_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs) {
   if (!jobs || n_jobs <= 0) return 1024;
   std::vector<ContractionArgs> probs;
   for (int i = 0; i < n_jobs; ++i)
-    if (cov_job_problems(jobs[i], &probs)) return 0;
+    if (cov_job_problems(jobs[i], i + 1, &probs)) return 0;
   return group_table_bytes(probs.data(), (int)probs.size()) + 256;
 }
 
@@ -426,7 +446,7 @@ int nsgp_cov_group_build(const nsgp_cov_job_t* jobs, int n_jobs, void* table_dev
   NSGP_REQUIRE(g_engine == 0, "cov_group_build: groups need the tcgen05 engine");
   std::vector<ContractionArgs> probs;
   for (int i = 0; i < n_jobs; ++i) {
-    int rc = cov_job_problems(jobs[i], &probs);
+    int rc = cov_job_problems(jobs[i], i + 1, &probs);
     if (rc) return rc;
   }
   GroupInfo gi{};

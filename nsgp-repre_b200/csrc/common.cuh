@@ -102,6 +102,9 @@ struct ContractionArgs {
   int epi;          // EpiMode
   int splits;       // split-K factor (SIMT engine, Gram only)
   int chain;        // tcgen05 engine: K blocks per accumulator chain (0 = default for epi)
+  int l2_group;     // grouped launches: problems with the same non-zero id read the same
+                    // operand planes - their items are ordered K-range-major so that
+                    // one K range of all of them is in flight together (L2 reuse)
 };
 
 // grouped contraction (tcgen05 engine only): a host-side list of problems that is

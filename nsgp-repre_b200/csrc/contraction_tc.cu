@@ -690,7 +690,7 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
   NSGP_REQUIRE(probs && table_dev && info && n >= 0, "group_build: bad arguments");
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
                "group_build: table must be 64-byte aligned");
-  struct Cost { long long c; TcItem it; };
+  struct Cost { long long c; int grp, split; TcItem it; };
   std::vector<TcProblem> hp[2];
   std::vector<Cost> items[2];
   for (int i = 0; i < n; ++i) {
@@ -714,6 +714,8 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
           Cost c;
           c.it = TcItem{prob, rb, cb, kb0, kb1, 0, 0, 0};
           c.c = (long long)(kb1 - kb0) * 8 + 16;       // ~ K blocks + a fixed part
+          c.grp = a.l2_group > 0 ? a.l2_group : -(i + 1);
+          c.split = sp;
           items[k].push_back(c);
         }
     }
@@ -724,8 +726,12 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
   for (int k = 0; k < 2; ++k) {
     // big items first; ties keep (problem, K range, tile) order so that tiles sharing
     // operand rows of one K range run at the same time (L2 reuse)
-    std::stable_sort(items[k].begin(), items[k].end(),
-                     [](const Cost& x, const Cost& y) { return x.c > y.c; });
+    // ... and problems that share operand planes (l2_group) walk their K ranges together
+    std::stable_sort(items[k].begin(), items[k].end(), [](const Cost& x, const Cost& y) {
+      if (x.c != y.c) return x.c > y.c;
+      if (x.grp != y.grp) return x.grp < y.grp;
+      return x.split < y.split;
+    });
     SubGroup& sg = info->sub[k];
     sg.n_problems = (int)hp[k].size();
     sg.n_items = (int)items[k].size();

@@ -79,7 +79,11 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
     g.mode = kModeAutocorr;
     g.T = 9; g.Cs = C; g.ncopy = 3;
     g.Hs = H + 2;                                  // two zero rows below
-    g.Ws = (int)round_up(W + 2, 4);                // >= two zero columns on the right
+    static const int ws_align = [] {
+      const char* e = getenv("NSGP_WS_ALIGN");      // bring-up: row pitch alignment (floats)
+      return e ? atoi(e) : 4;
+    }();
+    g.Ws = (int)round_up(W + 2, ws_align);         // >= two zero columns on the right
     g.Ht = 0;
     g.d_int = kAcMats * C;
     *out = g;
@@ -172,7 +176,7 @@ static inline Operand matrix_operand(const float* hi, const float* lo, int rows,
 // The contraction problems of one staged conv input: one Gram for the tap-pair layouts,
 // 29 small-N GEMMs for the autocorrelation layout.  acc: the layer's accumulator.
 static inline void conv_problems(const ConvGeom& g, const float* stage, float* acc,
-                                 ContractionArgs* out, int* n_out) {
+                                 ContractionArgs* out, int* n_out, int l2_group = 1) {
   if (g.mode != kModeAutocorr) {
     ContractionArgs a{};
     a.A = conv_operand(g, stage);
@@ -204,6 +208,7 @@ static inline void conv_problems(const ConvGeom& g, const float* stage, float* a
     a.epi = gram ? kEpiGramAtomic : kEpiGemmRmw;
     a.splits = 1;
     a.chain = 64;
+    a.l2_group = l2_group;
     out[n++] = a;
   };
   // R_(dy,dx)

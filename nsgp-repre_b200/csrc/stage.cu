@@ -372,7 +372,7 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
   const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && img % 4 == 0;
   ProfScope prof(kProfStage, stream);
   if (g.mode == kModeAutocorr) {
-    if (aligned && g.W % 4 == 0) {
+    if (aligned && g.W % 4 == 0 && g.Ws == g.W + 4) {
       long long n = (long long)g.C * g.Hs * (g.Ws / 4);
       int blocks = (int)((n + 255) / 256);
       if (blocks > 148 * 16) blocks = 148 * 16;
