@@ -604,7 +604,7 @@ int repre_cosine_count_batched(const float* F, int D, const int32_t* rows, const
     mask_off += (size_t)n * n;
   }
   GroupInfo gi{};
-  rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table, table_bytes, &gi,
+  rc = group_table_build(probs.data(), (int)probs.size(), kProfRepre, table, table_bytes, &gi,
                          stream);
   if (rc) return rc;
   NSGP_CHECK_CUDA(cudaMemcpyAsync(ext_dev, ext.data(), ext.size() * sizeof(ClassExtent),
