@@ -121,7 +121,8 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* peer_full = tmem_empty + 2;          // pair: "the peer's half of stage s landed"
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(peer_full + STAGES);
 
   constexpr int TILE = PAIR ? 256 : 128;         // tile edge in rows / columns
   const int warp = threadIdx.x >> 5;
@@ -134,8 +135,9 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PAIR ? 2 : 1);     // pair: leader's expect_tx + the peer's arrive
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&peer_full[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -216,13 +218,9 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
       const int b_rows = p.B.rows, b_br = p.B.br, b_cs = p.B.Cs;
       const int segs_a = seg_count(r0, a_rows, a_br);
       const int segs_b = share ? 0 : seg_count(c0, b_rows, b_br);
-      // bytes landing on the (leader's) full barrier per stage; full boxes always count
-      int sa = segs_a, sb = segs_b;
-      if (PAIR) {
-        sa += seg_count(r0 + (rank ? -BM : BM), a_rows, a_br);
-        if (!share) sb += seg_count(c0 + (rank ? -BM : BM), b_rows, b_br);
-      }
-      const uint32_t tx = ((dbg & 4) ? 1u : 2u) * (uint32_t)(sa * a_br + sb * b_br) * BK * 4u;
+      // bytes landing on this CTA's full barrier per stage; full boxes always count
+      const uint32_t tx =
+          ((dbg & 4) ? 1u : 2u) * (uint32_t)(segs_a * a_br + segs_b * b_br) * BK * 4u;
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
         prefetch_step();
         long long t0 = (dbg & 1) ? clock64() : 0;
@@ -230,33 +228,22 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
         else mbar_wait_warp(&empty_bar[stage], phase ^ 1, lane);
         long long t1 = (dbg & 1) ? clock64() : 0;
         c_wait += t1 - t0;
-        if (!PAIR || rank == 0) mbar_expect_tx_elect(&full_bar[stage], tx);
-        else mbar_arrive_remote_elect(&full_bar[stage], 0);
+        mbar_expect_tx_elect(&full_bar[stage], tx);
         const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
         const int kx0 = kb * BK;
         for (int s = 0; s < segs_a; ++s) {
           const int r = r0 + s * a_br;
           const int t = r / a_cs, c = r - t * a_cs;
           const uint32_t off = (uint32_t)(s * a_br) * (BK * 4);
-          if (PAIR) {
-            tma_load_2d_2sm_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
-            tma_load_2d_2sm_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
-          } else {
-            tma_load_2d_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
-            if (!(dbg & 4)) tma_load_2d_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
-          }
+          tma_load_2d_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
+          if (!(dbg & 4)) tma_load_2d_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
         }
         for (int s = 0; s < segs_b; ++s) {
           const int r = c0 + s * b_br;
           const int t = r / b_cs, c = r - t * b_cs;
           const uint32_t off = (uint32_t)(s * b_br) * (BK * 4);
-          if (PAIR) {
-            tma_load_2d_2sm_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
-            tma_load_2d_2sm_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
-          } else {
-            tma_load_2d_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
-            if (!(dbg & 4)) tma_load_2d_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
-          }
+          tma_load_2d_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
+          if (!(dbg & 4)) tma_load_2d_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
         }
         if (dbg & 1) c_issue += clock64() - t1;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -293,6 +280,7 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
           long long t0 = (dbg & 1) ? clock64() : 0;
           if (dbg & 8) mbar_wait(&full_bar[stage], phase);
           else mbar_wait_warp(&full_bar[stage], phase, lane);
+          if (PAIR) mbar_wait_warp(&peer_full[stage], phase, lane);
           long long t1 = (dbg & 1) ? clock64() : 0;
           c_wait += t1 - t0;
           ++c_kb;
@@ -327,6 +315,19 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
         g_dbg_counters[blockIdx.x * 8 + 2] = c_acc;
         g_dbg_counters[blockIdx.x * 8 + 5] = clock64() - t_start;
         g_dbg_counters[blockIdx.x * 8 + 6] = c_kb;
+      }
+    } else {
+      // pair, peer CTA: forward "my half of the stage has landed" to the leader's barrier
+      // (plain per-CTA TMA + this hop measured faster than cta_group::2 TMA whose issue
+      // rate per SM is half)
+      uint32_t stage = 0, phase = 0;
+      for (int idx = worker; idx < n_items; idx += n_workers) {
+        const Item it = fetch_item(&pmaps, &pp, gprobs, gitems, idx);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait_warp(&full_bar[stage], phase, lane);
+          mbar_arrive_remote_elect(&peer_full[stage], 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else {
@@ -533,28 +534,27 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
   return 0;
 }
 
-// CTA-pair kernel or single-CTA kernel for a Gram of `rows` rows?  The pair kernel
-// moves half the TMA bytes per output element but pads to 256-row blocks and has one
-// accumulator chain.  Measured (scripts/bench_gram.py, NSGP_DBG_COUNTERS): both kernels
-// are bound by the latency of the 3-stage operand ring (192 KB of smem in flight per
-// SM), and with cta_group::2 the TMA issue rate per SM halves, so the pair kernel ends
-// up at the same speed (1.87 vs 1.88 ms on fpn_convs.0).  Default: single-CTA kernel;
-// NSGP_PAIR_KERNEL=1 selects the pair kernel where it can run, =2 by the cost model.
-bool want_pair(int rows, bool gram, bool same) {
+// CTA-pair kernel or single-CTA kernel?  The pair kernel moves half the operand bytes
+// per output element (256 x 256 tile over two SMs) but pads to 256-row blocks and has
+// one accumulator chain.  Measured (scripts/bench_gram.py, NSGP_DBG_COUNTERS): both
+// kernels are bound by operand delivery into the 3-stage ring, and the pair kernel is
+// ~15 % faster per issued FLOP once its TMA is the plain per-CTA form with the peer
+// forwarding readiness (cta_group::2 TMA issues at half the rate per SM).  Default:
+// pair for covariance problems whose rows are a multiple of 256 (no padding waste);
+// NSGP_PAIR_KERNEL=0 never, 1 every same-operand Gram, 3 everything with > 128 rows.
+bool want_pair(const ContractionArgs& a) {
   static const int force = [] {
-    const char* e = getenv("NSGP_PAIR_KERNEL");       // 0 never (default), 1 always, 2 cost model
-    return e ? atoi(e) : 0;
+    const char* e = getenv("NSGP_PAIR_KERNEL");
+    return e ? atoi(e) : -1;
   }();
-  static const double ratio = [] {
-    const char* e = getenv("NSGP_PAIR_RATIO");        // cost of a pair unit / single unit
-    return e ? atof(e) : 0.65;
-  }();
-  if (!gram || !same || force == 0) return false;
-  if (force == 1) return true;
-  if (force != 2) return false;
-  const int t1 = ceil_div(rows, 128), t2 = ceil_div(rows, 256);
-  const double units1 = t1 * (t1 + 1) / 2.0, units2 = 4.0 * (t2 * (t2 + 1) / 2);
-  return units2 * ratio <= units1;
+  const bool gram = a.epi == kEpiGramAtomic;
+  const bool same = gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
+                    a.A.rows == a.B.rows;
+  if (force == 0) return false;
+  if (force == 3) return a.A.rows > 128;
+  if (force == 1) return gram && same;
+  // default: autocorrelation-layout problems (they carry an l2_group) on 256-multiples
+  return a.l2_group > 0 && a.A.rows % 256 == 0 && a.n_cols % 256 == 0 && a.A.K >= 1024;
 }
 
 // Validates one problem, encodes its tensor maps and fills every field of the
@@ -630,10 +630,7 @@ int sm_count() {
 
 int contraction_tc(const ContractionArgs& a, cudaStream_t stream) {
   TcProblem prob;
-  const bool gram = a.epi == kEpiGramAtomic;
-  const bool same = gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
-                    a.A.rows == a.B.rows;
-  const bool pair = want_pair(a.A.rows, gram, same);
+  const bool pair = want_pair(a);
   int rc = build_problem(a, pair, &prob);
   if (rc == 1) return 0;
   if (rc) return rc;
@@ -695,10 +692,7 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
   std::vector<Cost> items[2];
   for (int i = 0; i < n; ++i) {
     const ContractionArgs& a = probs[i];
-    const bool gram = a.epi == kEpiGramAtomic;
-    const bool same = gram && a.A.base == a.B.base && a.A.hl_stride == a.B.hl_stride &&
-                      a.A.rows == a.B.rows;
-    const int k = want_pair(a.A.rows, gram, same) ? 1 : 0;
+    const int k = want_pair(a) ? 1 : 0;
     TcProblem pr;
     int rc = build_problem(a, k == 1, &pr);
     if (rc == 1) continue;
