@@ -128,7 +128,24 @@ typedef struct {
   const float* pt_lo;
   float* u_hi;             /* scratch, cout rows of pitch round_up(d,4) each: staged update */
   float* u_lo;
+  /* Low-rank form (r > 0):  W += scale * (update - (update @ U) @ U^T)  with U (d x r) the
+   * kept-out top eigenvectors, i.e. P = scale * (I - U U^T) - the same projector as the
+   * dense V0 V0^T (/ ||P||_F for 'backbone' names, SGD_NSCL.py:270-285) without the d x d
+   * matrix: 4*cout*d*r instead of 2*cout*d*d FLOPs.  pt_hi / pt_lo are unused then. */
+  int r;
+  float scale;
+  const float* ut_hi;      /* U^T: r rows of pitch round_up(d,4) (nsgp_projector_prepare_lowrank) */
+  const float* ut_lo;
+  const float* un_hi;      /* U:   d rows of pitch round_up(r,4) */
+  const float* un_lo;
+  float* t;                /* scratch T = update @ U: cout rows of pitch round_up(r,4), fp32 ... */
+  float* t_hi;             /* ... and its tf32 split; all T of a step live in one arena */
+  float* t_lo;
 } nsgp_proj_layer_t;
+
+/* ut/un (hi, lo) = tf32 splits of U^T and U for the low-rank form.  U: (d x r) row-major. */
+int nsgp_projector_prepare_lowrank(const float* U, int d, int r, float* ut_hi, float* ut_lo,
+                                   float* un_hi, float* un_lo, void* stream);
 
 size_t nsgp_sgd_step_workspace_bytes(int n_tensors, int n_layers);
 
@@ -154,8 +171,11 @@ typedef struct {
 
 typedef struct {
   int n_tensors, total_chunks, all_have_buf;
-  size_t off_chunks, off_group;
-  nsgp_group_t group;
+  size_t off_chunks, off_group, off_group2;
+  nsgp_group_t group;      /* dense projections and T = update @ U of the low-rank layers */
+  nsgp_group_t group2;     /* W -= scale * T @ U^T of the low-rank layers */
+  float* t_arena;          /* [T | T_hi | T_lo], t_elems floats each (low-rank layers) */
+  size_t t_elems;
   size_t bytes;
 } nsgp_sgd_plan_t;
 
@@ -163,6 +183,7 @@ size_t nsgp_sgd_plan_bytes(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                            const nsgp_proj_layer_t* layers, int n_layers);
 int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                         const nsgp_proj_layer_t* layers, int n_layers,
+                        float* t_arena, size_t t_elems,
                         void* plan_dev /* 256-byte aligned */, size_t plan_bytes,
                         nsgp_sgd_plan_t* plan /* host, out */, void* stream);
 int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,

@@ -30,7 +30,9 @@ class SgdTensor(C.Structure):
 
 class ProjLayer(C.Structure):
     _fields_ = [("cout", c_int), ("d", c_int), ("pt_hi", c_void_p), ("pt_lo", c_void_p),
-                ("u_hi", c_void_p), ("u_lo", c_void_p)]
+                ("u_hi", c_void_p), ("u_lo", c_void_p), ("r", c_int), ("scale", c_float),
+                ("ut_hi", c_void_p), ("ut_lo", c_void_p), ("un_hi", c_void_p),
+                ("un_lo", c_void_p), ("t", c_void_p), ("t_hi", c_void_p), ("t_lo", c_void_p)]
 
 
 class Group(C.Structure):
@@ -40,8 +42,9 @@ class Group(C.Structure):
 
 class SgdPlan(C.Structure):
     _fields_ = [("n_tensors", c_int), ("total_chunks", c_int), ("all_have_buf", c_int),
-                ("off_chunks", c_size_t), ("off_group", c_size_t), ("group", Group),
-                ("bytes", c_size_t)]
+                ("off_chunks", c_size_t), ("off_group", c_size_t), ("off_group2", c_size_t),
+                ("group", Group), ("group2", Group), ("t_arena", c_void_p),
+                ("t_elems", c_size_t), ("bytes", c_size_t)]
 
 
 class CovJob(C.Structure):
@@ -75,7 +78,10 @@ SIGNATURES = {
                                    c_void_p, c_size_t, c_void_p]),
     "nsgp_sgd_plan_bytes": (c_size_t, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int]),
     "nsgp_sgd_plan_build": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
-                                    c_void_p, c_size_t, C.POINTER(SgdPlan), c_void_p]),
+                                    c_void_p, c_size_t, c_void_p, c_size_t, C.POINTER(SgdPlan),
+                                    c_void_p]),
+    "nsgp_projector_prepare_lowrank": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p]),
     "nsgp_sgd_plan_step": (c_int, [C.POINTER(SgdTensor), c_int, C.POINTER(ProjLayer), c_int,
                                    c_void_p, C.POINTER(SgdPlan), c_double, c_double, c_double,
                                    c_double, c_int, c_void_p]),

@@ -235,6 +235,17 @@ int nsgp_cov_finalize(const float* acc, const nsgp_cov_layout_t* L, float* cov_o
 }
 
 // ---------------------------------------------------------------- projection
+int nsgp_projector_prepare_lowrank(const float* U, int d, int r, float* ut_hi, float* ut_lo,
+                                   float* un_hi, float* un_lo, void* stream_) {
+  NSGP_REQUIRE(U && ut_hi && ut_lo && un_hi && un_lo && d > 0 && r > 0,
+               "projector_prepare_lowrank: bad arguments");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // U^T (r x pitch(d)): transpose + split;  U (d x pitch(r)): split with padded pitch
+  int rc = launch_transpose_split_rect(U, ut_hi, ut_lo, d, r, (int)round_up(d, 4), stream);
+  if (rc) return rc;
+  return launch_split_pitched(U, un_hi, un_lo, d, r, (int)round_up(r, 4), stream);
+}
+
 int nsgp_projector_prepare(const float* P, int d, float* pt_hi, float* pt_lo, void* stream_) {
   NSGP_REQUIRE(P && pt_hi && pt_lo && d > 0, "projector_prepare: bad arguments");
   return launch_transpose_split(P, pt_hi, pt_lo, d, (int)round_up(d, 4), (cudaStream_t)stream_);
@@ -259,6 +270,12 @@ static int sgd_tables(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                    "sgd_step: tensor %d: cout*d != numel", i);
       d.u_hi = L.u_hi; d.u_lo = L.u_lo;
       d.d = L.d; d.ldu = (int)round_up(L.d, 4);
+      d.apply = L.r > 0 ? L.scale : 0.f;
+      if (L.r > 0)
+        NSGP_REQUIRE(L.ut_hi && L.ut_lo && L.un_hi && L.un_lo && L.t && L.t_hi && L.t_lo,
+                     "sgd_step: tensor %d: low-rank projection needs U, U^T and T buffers", i);
+      else
+        NSGP_REQUIRE(L.pt_hi && L.pt_lo, "sgd_step: tensor %d: dense projection needs P^T", i);
     }
     (*host)[i] = d;
     (*chunk_start)[i] = total;
@@ -287,15 +304,37 @@ static GroupInfo group_from_abi(const nsgp_group_t& g) {
   return gi;
 }
 
+// first GEMM of a protected layer: dense  W += update @ P,  low-rank  T += update @ U
 static ContractionArgs proj_args(const nsgp_proj_layer_t& L, float* w) {
   ContractionArgs a{};
   const int ldk = (int)round_up(L.d, 4);
   a.A = matrix_operand(L.u_hi, L.u_lo, L.cout, L.d, ldk);
-  a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
+  a.alpha = 1.f;
+  a.epi = kEpiGemmRmw;
+  a.splits = 1;
+  if (L.r > 0) {
+    a.B = matrix_operand(L.ut_hi, L.ut_lo, L.r, L.d, ldk);
+    a.out = L.t;
+    a.ld = (int)round_up(L.r, 4);
+    a.n_cols = L.r;
+  } else {
+    a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
+    a.out = w;
+    a.ld = L.d;
+    a.n_cols = L.d;
+  }
+  return a;
+}
+// second GEMM of a low-rank layer:  W += -scale * T @ U^T
+static ContractionArgs proj_args2(const nsgp_proj_layer_t& L, float* w) {
+  ContractionArgs a{};
+  const int ldr = (int)round_up(L.r, 4);
+  a.A = matrix_operand(L.t_hi, L.t_lo, L.cout, L.r, ldr);
+  a.B = matrix_operand(L.un_hi, L.un_lo, L.d, L.r, ldr);
   a.out = w;
   a.ld = L.d;
   a.n_cols = L.d;
-  a.alpha = 1.f;
+  a.alpha = -L.scale;
   a.epi = kEpiGemmRmw;
   a.splits = 1;
   return a;
@@ -333,33 +372,55 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   if (rc) return rc;
   for (int i = 0; i < n_tensors; ++i) {
     if (tensors[i].layer < 0) continue;
-    rc = contraction(proj_args(layers[tensors[i].layer], tensors[i].w), stream);
+    const nsgp_proj_layer_t& L = layers[tensors[i].layer];
+    if (L.r > 0) {
+      const size_t te = (size_t)L.cout * round_up(L.r, 4);
+      NSGP_CHECK_CUDA(cudaMemsetAsync(L.t, 0, te * sizeof(float), stream));
+    }
+    rc = contraction(proj_args(L, tensors[i].w), stream);
     if (rc) return rc;
+    if (L.r > 0) {
+      const size_t te = (size_t)L.cout * round_up(L.r, 4);
+      rc = launch_split(L.t, L.t_hi, L.t_lo, (long long)te, stream);
+      if (rc) return rc;
+      rc = contraction(proj_args2(L, tensors[i].w), stream);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
 
 // ---- prepared plan: tables uploaded once, two launches per step ---------------
 static void proj_problems(const nsgp_sgd_tensor_t* tensors, int n_tensors,
-                          const nsgp_proj_layer_t* layers, std::vector<ContractionArgs>* out) {
-  for (int i = 0; i < n_tensors; ++i)
-    if (tensors[i].layer >= 0) out->push_back(proj_args(layers[tensors[i].layer], tensors[i].w));
+                          const nsgp_proj_layer_t* layers, std::vector<ContractionArgs>* out,
+                          std::vector<ContractionArgs>* out2) {
+  for (int i = 0; i < n_tensors; ++i) {
+    if (tensors[i].layer < 0) continue;
+    const nsgp_proj_layer_t& L = layers[tensors[i].layer];
+    out->push_back(proj_args(L, tensors[i].w));
+    if (L.r > 0) out2->push_back(proj_args2(L, tensors[i].w));
+  }
 }
 
 size_t nsgp_sgd_plan_bytes(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                            const nsgp_proj_layer_t* layers, int n_layers) {
   if (!tensors || n_tensors <= 0) return 1024;
-  std::vector<ContractionArgs> probs;
+  std::vector<ContractionArgs> probs, probs2;
   for (int i = 0; i < n_tensors; ++i)
-    if (tensors[i].layer >= 0 && tensors[i].layer < n_layers && layers)
-      probs.push_back(proj_args(layers[tensors[i].layer], tensors[i].w));
-  return nsgp_sgd_step_workspace_bytes(n_tensors, n_layers) + 1024 +
-         group_table_bytes(probs.data(), (int)probs.size());
+    if (tensors[i].layer >= 0 && tensors[i].layer < n_layers && layers) {
+      const nsgp_proj_layer_t& L = layers[tensors[i].layer];
+      probs.push_back(proj_args(L, tensors[i].w));
+      if (L.r > 0) probs2.push_back(proj_args2(L, tensors[i].w));
+    }
+  return nsgp_sgd_step_workspace_bytes(n_tensors, n_layers) + 2048 +
+         group_table_bytes(probs.data(), (int)probs.size()) +
+         group_table_bytes(probs2.data(), (int)probs2.size());
 }
 
 int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
-                        const nsgp_proj_layer_t* layers, int n_layers, void* plan_dev,
-                        size_t plan_bytes, nsgp_sgd_plan_t* plan, void* stream_) {
+                        const nsgp_proj_layer_t* layers, int n_layers, float* t_arena,
+                        size_t t_elems, void* plan_dev, size_t plan_bytes,
+                        nsgp_sgd_plan_t* plan, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSGP_REQUIRE(tensors && plan_dev && plan && n_tensors > 0, "sgd_plan_build: bad arguments");
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(plan_dev) & 255) == 0,
@@ -372,19 +433,34 @@ int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   const size_t off_group =
       round_up((long long)(off_chunks + (size_t)(n_tensors + 1) * sizeof(int)), 256);
   NSGP_REQUIRE(off_group <= plan_bytes, "sgd_plan_build: plan buffer too small");
-  std::vector<ContractionArgs> probs;
-  proj_problems(tensors, n_tensors, layers, &probs);
-  GroupInfo gi{};
+  std::vector<ContractionArgs> probs, probs2;
+  proj_problems(tensors, n_tensors, layers, &probs, &probs2);
+  for (int i = 0; i < n_layers; ++i)
+    if (layers[i].r > 0)
+      NSGP_REQUIRE(t_arena && layers[i].t >= t_arena &&
+                       layers[i].t + (size_t)layers[i].cout * round_up(layers[i].r, 4) <=
+                           t_arena + t_elems,
+                   "sgd_plan_build: layer %d: T must live inside the T arena", i);
+  GroupInfo gi{}, gi2{};
   int rc = group_table_build(probs.data(), (int)probs.size(), kProfGemm,
                              (char*)plan_dev + off_group, plan_bytes - off_group, &gi, stream);
+  if (rc) return rc;
+  const size_t off_group2 = round_up((long long)(off_group + gi.bytes), 256);
+  NSGP_REQUIRE(off_group2 <= plan_bytes, "sgd_plan_build: plan buffer too small");
+  rc = group_table_build(probs2.data(), (int)probs2.size(), kProfGemm,
+                         (char*)plan_dev + off_group2, plan_bytes - off_group2, &gi2, stream);
   if (rc) return rc;
   plan->n_tensors = n_tensors;
   plan->total_chunks = 0;
   plan->all_have_buf = 0;
   plan->off_chunks = off_chunks;
   plan->off_group = off_group;
+  plan->off_group2 = off_group2;
   group_to_abi(gi, &plan->group);
-  plan->bytes = off_group + gi.bytes;
+  group_to_abi(gi2, &plan->group2);
+  plan->t_arena = t_arena;
+  plan->t_elems = t_elems;
+  plan->bytes = off_group2 + gi2.bytes;
   return 0;
 }
 
@@ -413,7 +489,16 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                            (float)momentum, (float)(1.0 - dampening), (float)weight_decay,
                            nesterov, stream);
   if (rc) return rc;
-  return group_launch((const char*)plan_dev + plan->off_group, group_from_abi(plan->group), stream);
+  const bool lowrank = plan->group2.n_items[0] + plan->group2.n_items[1] > 0;
+  if (lowrank)
+    NSGP_CHECK_CUDA(cudaMemsetAsync(plan->t_arena, 0, plan->t_elems * sizeof(float), stream));
+  rc = group_launch((const char*)plan_dev + plan->off_group, group_from_abi(plan->group), stream);
+  if (rc || !lowrank) return rc;
+  rc = launch_split(plan->t_arena, plan->t_arena + plan->t_elems,
+                    plan->t_arena + 2 * plan->t_elems, (long long)plan->t_elems, stream);
+  if (rc) return rc;
+  return group_launch((const char*)plan_dev + plan->off_group2, group_from_abi(plan->group2),
+                      stream);
 }
 
 // ---- grouped covariance contraction (deferred mode of the hooks) ----------------

@@ -684,7 +684,7 @@ size_t group_table_bytes(const ContractionArgs* probs, int n) {
 
 int group_table_build(const ContractionArgs* probs, int n, int kind, void* table_dev,
                       size_t table_bytes, GroupInfo* info, cudaStream_t stream) {
-  NSGP_REQUIRE(probs && table_dev && info && n >= 0, "group_build: bad arguments");
+  NSGP_REQUIRE((probs || n == 0) && table_dev && info && n >= 0, "group_build: bad arguments");
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
                "group_build: table must be 64-byte aligned");
   struct Cost { long long c; int grp, split; TcItem it; };

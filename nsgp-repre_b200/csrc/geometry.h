@@ -249,5 +249,11 @@ int launch_cov_finalize(const float* acc, int ld, float* out, int C, int T, int 
 int launch_split(const float* src, float* hi, float* lo, long long n, cudaStream_t s);
 int launch_transpose_split(const float* src, float* hi, float* lo, int d, int ld_dst,
                            cudaStream_t s);
+// src (rows x cols) row-major -> hi/lo of its transpose (cols rows of pitch ld_dst)
+int launch_transpose_split_rect(const float* src, float* hi, float* lo, int rows, int cols,
+                                int ld_dst, cudaStream_t s);
+// src (rows x cols) row-major -> hi/lo with row pitch ld_dst (pad columns zeroed)
+int launch_split_pitched(const float* src, float* hi, float* lo, int rows, int cols, int ld_dst,
+                         cudaStream_t s);
 
 }  // namespace nsgp

@@ -52,6 +52,7 @@ sgd_prologue_kernel(const SgdTensorDev* __restrict__ tensors,
       if (t.ldu != t.d) { long long r = i / t.d; o = r * t.ldu + (i - r * t.d); }
       t.u_hi[o] = h;
       t.u_lo[o] = l;
+      if (t.apply != 0.f) t.w[i] = w + t.apply * upd;
     } else {
       t.w[i] = w + upd;
     }

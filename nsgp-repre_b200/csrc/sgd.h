@@ -12,7 +12,7 @@ struct SgdTensorDev {
   int first;     // state just created: buf = grad (SGD_NSCL.py:405-406)
   int d;         // protected: row length of update.view(cout, d); staged pitch is ldu
   int ldu;
-  int pad;
+  float apply;   // protected, low-rank form: also w += apply * update here (0: stage only)
 };
 int launch_sgd_prologue(const SgdTensorDev* tensors_dev, const int* chunk_start_dev,
                         int n_tensors, int total_chunks, float lr, float momentum,

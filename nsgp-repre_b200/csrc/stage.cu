@@ -575,6 +575,62 @@ transpose_split_kernel(const float* __restrict__ src, float* __restrict__ hi,
   }
 }
 
+__global__ void __launch_bounds__(256)
+transpose_split_rect_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                            float* __restrict__ lo, int rows, int cols, int ld_dst) {
+  __shared__ float tile[32][33];
+  int bx = blockIdx.x * 32, by = blockIdx.y * 32;       // bx over cols, by over rows
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int row = by + r, col = bx + tx;
+    tile[r][tx] = (row < rows && col < cols) ? src[(long long)row * cols + col] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int orow = bx + r, ocol = by + tx;                   // transposed: (col, row)
+    if (orow < cols && ocol < rows) {
+      float h, l;
+      tf32_split(tile[tx][r], h, l);
+      hi[(long long)orow * ld_dst + ocol] = h;
+      lo[(long long)orow * ld_dst + ocol] = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_pitched_kernel(const float* __restrict__ src, float* __restrict__ hi,
+                     float* __restrict__ lo, int rows, int cols, int ld_dst) {
+  long long total = (long long)rows * ld_dst;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % ld_dst);
+    long long r = i / ld_dst;
+    float h = 0.f, l = 0.f;
+    if (c < cols) tf32_split(src[r * cols + c], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int launch_transpose_split_rect(const float* src, float* hi, float* lo, int rows, int cols,
+                                int ld_dst, cudaStream_t stream) {
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  transpose_split_rect_kernel<<<grid, 256, 0, stream>>>(src, hi, lo, rows, cols, ld_dst);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int launch_split_pitched(const float* src, float* hi, float* lo, int rows, int cols, int ld_dst,
+                         cudaStream_t stream) {
+  long long total = (long long)rows * ld_dst;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_pitched_kernel<<<blocks, 256, 0, stream>>>(src, hi, lo, rows, cols, ld_dst);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
 int launch_split(const float* src, float* hi, float* lo, long long n, cudaStream_t stream) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -46,6 +46,10 @@ class SGDNSCL(Optimizer):
         self._stage = {}        # name -> (u_hi, u_lo)
         self._workspace = None
         self._plans = {}        # group index -> (signature, device buffer, SgdPlan)
+        self._lowrank = {}      # name -> (P tensor, P._version, U (d,r), scale) from get_transforms
+        self._lowrank_prepared = {}
+        self._t_arena = None
+        self.lowrank_max_ratio = 0.25   # use G - (G U) U^T while r <= ratio * d
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -113,9 +117,18 @@ class SGDNSCL(Optimizer):
                 ind = self.adaptive_threshold(self.eigens[n]["eigen_value"], offset=offset)
                 basis = self.eigens[n]["eigen_vector"][:, ind]
                 transform = torch.mm(basis, basis.transpose(1, 0))
+                scale = 1.0
                 if "backbone" in n:
-                    transform = transform / torch.norm(transform)
+                    nrm = torch.norm(transform)
+                    transform = transform / nrm
+                    scale = 1.0 / float(nrm)
                 self.transforms[n] = transform.detach()
+                # the same projector in low-rank form: P = scale * (I - U U^T), U = the
+                # kept-out (large-sigma) eigenvectors; used by step() while this tensor
+                # stays in place and r is small
+                kept_out = self.eigens[n]["eigen_vector"][:, ~ind].contiguous()
+                self._lowrank[n] = (self.transforms[n], self.transforms[n]._version,
+                                    kept_out, scale)
 
     # ---------------------------------------------------------------------- step
     def _prepare(self, name: str, P: torch.Tensor):
@@ -136,6 +149,32 @@ class SGDNSCL(Optimizer):
               "nsgp_projector_prepare")
         self._prepared[name] = (key, hi, lo)
         return hi, lo
+
+    def _prepare_lowrank(self, name: str, P: torch.Tensor):
+        """(r, scale, ut_hi, ut_lo, un_hi, un_lo) when ``P`` is still the tensor that
+        ``get_transforms`` built and its rank deficit is small, else None (dense form)."""
+        lr = self._lowrank.get(name)
+        if lr is None or lr[0] is not P or lr[1] != P._version:
+            return None
+        U, scale = lr[2], lr[3]
+        d, r = U.shape
+        if r == 0 or r > self.lowrank_max_ratio * d:
+            return None
+        hit = self._lowrank_prepared.get(name)
+        if hit is not None and hit[0] is U:
+            return hit[1]
+        ld_d, ld_r = (d + 3) // 4 * 4, (r + 3) // 4 * 4
+        ut_hi = torch.empty(r, ld_d, dtype=torch.float32, device=U.device)
+        ut_lo = torch.empty_like(ut_hi)
+        un_hi = torch.empty(d, ld_r, dtype=torch.float32, device=U.device)
+        un_lo = torch.empty_like(un_hi)
+        check(lib.nsgp_projector_prepare_lowrank(ptr(U), d, r, ptr(ut_hi), ptr(ut_lo),
+                                                 ptr(un_hi), ptr(un_lo),
+                                                 _lib.current_stream(U.device)),
+              "nsgp_projector_prepare_lowrank")
+        out = (r, scale, ut_hi, ut_lo, un_hi, un_lo)
+        self._lowrank_prepared[name] = (U, out)
+        return out
 
     def _staging(self, name: str, p: torch.Tensor):
         st = self._stage.get(name)
@@ -162,6 +201,7 @@ class SGDNSCL(Optimizer):
             n_t = len(params)
             tensors = (SgdTensor * n_t)()
             layers = []
+            t_need = []             # (layer index, T elements) of the low-rank layers
             device = params[0].device
             for i, (n, p) in enumerate(zip(names, params)):
                 grad = p.grad.data          # AttributeError when grad is None, like :75
@@ -192,13 +232,33 @@ class SGDNSCL(Optimizer):
                     if P.shape[0] != dd:
                         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied "
                                            "(%dx%d and %dx%d)" % (cout, dd, P.shape[0], P.shape[1]))
-                    hi, lo = self._prepare(n, P)
                     u_hi, u_lo = self._staging(n, p)
-                    L = ProjLayer(cout, dd, hi.data_ptr(), lo.data_ptr(),
-                                  u_hi.data_ptr(), u_lo.data_ptr())
+                    low = self._prepare_lowrank(n, P)
+                    if low is None:
+                        hi, lo = self._prepare(n, P)
+                        L = ProjLayer(cout, dd, hi.data_ptr(), lo.data_ptr(),
+                                      u_hi.data_ptr(), u_lo.data_ptr())
+                    else:
+                        r, scale, ut_hi, ut_lo, un_hi, un_lo = low
+                        L = ProjLayer(cout, dd, None, None, u_hi.data_ptr(), u_lo.data_ptr(),
+                                      r, scale, ut_hi.data_ptr(), ut_lo.data_ptr(),
+                                      un_hi.data_ptr(), un_lo.data_ptr())
+                        t_need.append((len(layers), cout * ((r + 3) // 4 * 4)))
                     t.layer = len(layers)
                     layers.append(L)
             n_l = len(layers)
+            # one arena [T | T_hi | T_lo] for the low-rank layers
+            t_elems = sum(e for _, e in t_need)
+            if t_elems:
+                if self._t_arena is None or self._t_arena.numel() != 3 * t_elems or \
+                        self._t_arena.device != device:
+                    self._t_arena = torch.empty(3 * t_elems, dtype=torch.float32, device=device)
+                base, off = self._t_arena.data_ptr(), 0
+                for li, e in t_need:
+                    layers[li].t = base + 4 * off
+                    layers[li].t_hi = base + 4 * (t_elems + off)
+                    layers[li].t_lo = base + 4 * (2 * t_elems + off)
+                    off += e
             layer_arr = (ProjLayer * max(n_l, 1))(*layers)
             stream = _lib.current_stream(device)
             hyper = (float(group["lr"]), float(group["momentum"]), float(group["dampening"]),
@@ -215,7 +275,8 @@ class SGDNSCL(Optimizer):
                 continue
             # prepared plan: rebuilt only when a weight / projector pointer or a shape changes
             sig = (tuple((t.w, t.numel, t.layer) for t in tensors),
-                   tuple((L.cout, L.d, L.pt_hi, L.pt_lo, L.u_hi, L.u_lo) for L in layers))
+                   tuple((L.cout, L.d, L.pt_hi, L.pt_lo, L.u_hi, L.u_lo, L.r, L.scale, L.ut_hi,
+                          L.un_hi, L.t) for L in layers))
             gi = id(group)
             hit = self._plans.get(gi)
             if hit is None or hit[0] != sig:
@@ -224,8 +285,9 @@ class SGDNSCL(Optimizer):
                     hit[1].device == device else \
                     torch.empty(need, dtype=torch.uint8, device=device)
                 plan = SgdPlan()
-                check(lib.nsgp_sgd_plan_build(tensors, n_t, layer_arr, n_l, ptr(buf),
-                                              buf.numel(), ctypes.byref(plan), stream),
+                check(lib.nsgp_sgd_plan_build(tensors, n_t, layer_arr, n_l,
+                                              ptr(self._t_arena) if t_elems else None, t_elems,
+                                              ptr(buf), buf.numel(), ctypes.byref(plan), stream),
                       "nsgp_sgd_plan_build")
                 hit = (sig, buf, plan)
                 self._plans[gi] = hit

@@ -272,6 +272,42 @@ def test_projected_update_r50_shapes(pkg, engine):
         assert rel_fro(p, zref[n]) < TOL, n
 
 
+@pytest.mark.parametrize("name", ["backbone.layer3.0.conv2.weight", "neck.fpn_convs.1.conv.weight"])
+def test_lowrank_projection_equals_dense(pkg, engine, name):
+    """step() after get_transforms uses W += s*(upd - (upd U) U^T) with U the kept-out
+    eigenvectors; it must equal the dense ``update @ P`` of the reference (SGD_NSCL.py:85-95)
+    with P built by the reference's own recipe (fp32 SVD, oracle), 'backbone' scale included."""
+    d, cout = 1152, 256
+    cov = synth.decaying_cov(d, 11, rank=23)
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(cout, 128, 3, 3, generator=g)
+    kw = dict(lr=0.02, momentum=0.9, weight_decay=1e-4)
+    # fp64 run of the reference recipe = the truth line (SURVEY.md App. C.4); the fp32 SVD
+    # the reference itself runs carries ~1e-4 of its own noise at d = 1152
+    s, v = O.eigens(cov.double())
+    P_ref = O.transform(s, v, name, 0.0)
+    s32, v32 = O.eigens(cov)
+    assert rel_fro(O.transform(s32, v32, name, 0.0), P_ref) < 3e-4
+    ref = {name: torch.zeros(cout, 128, 3, 3, dtype=torch.float64)}
+    O.sgd_nscl_step(ref, {name: grad.double()}, {}, {name: P_ref.double()}, svd=True, **kw)
+    outs = []
+    for ratio in (0.25, 0.0):                  # low-rank form, then forced dense form
+        p = torch.nn.Parameter(torch.zeros(cout, 128, 3, 3, device="cuda"))
+        opt = pkg.SGDNSCL([p], svd=True, **kw)
+        opt.lowrank_max_ratio = ratio
+        opt.param_groups[0]["names"] = [name]
+        opt.get_eigens({name: cov.cuda()})
+        opt.get_transforms(offset=0.0)
+        assert rel_fro(opt.transforms[name], P_ref) < TOL
+        p.grad = grad.clone().cuda()
+        opt.step()
+        used_lowrank = opt._t_arena is not None
+        assert used_lowrank == (ratio > 0)
+        assert rel_fro(p, ref[name]) < TOL, ratio
+        outs.append(p.detach().clone())
+    assert rel_fro(outs[0], outs[1]) < 2e-5
+
+
 # ----------------------------------------------------------------------- prototypes
 def test_prototypes_match_reference_fixture(pkg, engine, golden_dir):
     g = _load(golden_dir, "prototypes.pt")
