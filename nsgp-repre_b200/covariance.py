@@ -40,7 +40,9 @@ class _JobSet:
     """One forward's worth of staged layers for the grouped launch."""
 
     def __init__(self):
-        self.jobs = []          # [key, geometry tuple, workspace tensor, layer accumulator]
+        self.jobs = []          # [key, geometry, workspace, layer accumulator, alias-of index]
+        self.seen = {}          # this forward: (input identity, geometry) -> job index
+        self.keep = []          # this forward: staged input tensors
         self.pos = 0
         self.sig = None
         self.table = None
@@ -138,16 +140,26 @@ class CovarianceHooks:
         main = torch.cuda.current_stream(dev)
         if js.pos == 0 and js.done is not None:
             main.wait_event(js.done)          # the set's previous launch must be finished
-        if js.pos < len(js.jobs) and js.jobs[js.pos][0] == key and js.jobs[js.pos][1] == geom \
-                and js.jobs[js.pos][2].device == dev and js.jobs[js.pos][3] is la:
-            ws = js.jobs[js.pos][2]
+        # the same tensor with the same geometry earlier in this forward (e.g. the stage
+        # output that feeds both layerN.0.conv1 and the FPN lateral conv): stage it once
+        ident = (x.data_ptr(), x._version, tuple(x.shape), geom, B)
+        src = js.seen.get(ident)
+        pos = js.pos
+        st = js.jobs[pos] if pos < len(js.jobs) else None
+        if st is not None and st[0] == key and st[1] == geom and st[2].device == dev and \
+                st[3] is la and st[4] == src:
+            ws = st[2]
         else:
-            del js.jobs[js.pos:]
-            ws = torch.empty(int(layout.workspace_bytes), dtype=torch.uint8, device=dev)
-            js.jobs.append([key, geom, ws, la])
+            del js.jobs[pos:]
+            ws = js.jobs[src][2] if src is not None else \
+                torch.empty(int(layout.workspace_bytes), dtype=torch.uint8, device=dev)
+            js.jobs.append([key, geom, ws, la, src])
             js.sig = None
-        check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(), main.cuda_stream),
-              "nsgp_cov_conv2d_stage")
+        if src is None:
+            check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(),
+                                            main.cuda_stream), "nsgp_cov_conv2d_stage")
+            js.seen[ident] = pos
+            js.keep.append(x)                 # keeps the storage (and its address) alive
         js.pos += 1
         la.calls += 1
 
@@ -158,6 +170,8 @@ class CovarianceHooks:
         if js.pos == 0:
             return
         del js.jobs[js.pos:]
+        js.seen.clear()
+        js.keep.clear()
         dev = js.jobs[0][2].device
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev)
@@ -167,7 +181,7 @@ class CovarianceHooks:
         if js.sig is None:
             n = len(js.jobs)
             arr = (CovJob * n)()
-            for i, (key, geom, ws, la) in enumerate(js.jobs):
+            for i, (key, geom, ws, la, _alias) in enumerate(js.jobs):
                 j = arr[i]
                 (j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw) = geom
                 j.acc, j.workspace, j.workspace_bytes = la.acc.data_ptr(), ws.data_ptr(), ws.numel()

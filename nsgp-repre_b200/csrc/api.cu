@@ -127,7 +127,8 @@ int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, 
     out->ld = (int)round_up(g.d_int, 4);
     out->acc_bytes = (size_t)out->ld * g.d_int * sizeof(float);
   }
-  out->workspace_bytes = stage_bytes(g) + 1024 + layer_table_bytes(g);
+  out->workspace_bytes = stage_bytes(g) + 1024 + layer_table_bytes(g) +
+                         mean_scratch_elems(g) * sizeof(float) + 256;
   return 0;
 }
 
@@ -164,7 +165,14 @@ int nsgp_cov_conv2d_stage(const float* x, int B, int C, int H, int W, int kh, in
   float* stage;
   int rc = cov_conv2d_setup(C, H, W, kh, kw, sh, sw, ph, pw, workspace, workspace_bytes, &g, &stage);
   if (rc) return rc;
-  return launch_stage_conv(x, stage, g, B, (cudaStream_t)stream_);
+  // [staged operand | per-layer group table | batch-mean scratch]
+  float* mean = nullptr;
+  if (mean_scratch_elems(g) > 0) {
+    char* m = align_up((char*)stage + stage_bytes(g) + layer_table_bytes(g), 256);
+    if (m + mean_scratch_elems(g) * sizeof(float) <= (char*)workspace + workspace_bytes)
+      mean = reinterpret_cast<float*>(m);
+  }
+  return launch_stage_conv(x, stage, g, B, mean, (cudaStream_t)stream_);
 }
 
 int nsgp_cov_conv2d_contract(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,

@@ -239,7 +239,15 @@ static inline void conv_problems(const ConvGeom& g, const float* stage, float* a
 }
 constexpr int kMaxConvProblems = kAcMats;
 
-int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B, cudaStream_t s);
+int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
+                      float* mean_scratch, cudaStream_t s);
+// scratch (floats) for the batch mean of the gather layouts' two-pass staging
+static inline size_t mean_scratch_elems(const ConvGeom& g) {
+  const bool vec_flat = g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && (g.H * g.W) % 4 == 0;
+  const bool vec_ac = g.mode == kModeAutocorr && g.W % 4 == 0 && g.Ws == g.W + 4;
+  if (vec_flat || vec_ac) return 0;
+  return (size_t)round_up((long long)g.C * g.H * g.W, 4);
+}
 int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,
                                  cudaStream_t s);
 int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,

@@ -12,53 +12,6 @@ namespace nsgp {
 // unfolding), splits into tf32 hi/lo and writes both copies.  Halo / padding
 // elements are written as zeros, so the workspace needs no memset.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
-                  int B, long long hl_stride) {
-  const long long plane_elems = (long long)g.Cs * g.Hs * g.Ws;
-  const long long total = plane_elems * g.ncopy;
-  const long long img = (long long)g.C * g.H * g.W;
-  const float fb = (float)B;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int xs = (int)(idx % g.Ws);
-    long long rest = idx / g.Ws;
-    int r = (int)(rest % g.Hs);
-    rest /= g.Hs;
-    int c = (int)(rest % g.Cs);
-    int copy = (int)(rest / g.Cs);
-    int y, xx;
-    bool valid;
-    if (g.mode == kModeFlat) {
-      int k = xs;
-      valid = k < g.Hout * g.Wout;
-      int oy = k / g.Wout, ox = k - oy * g.Wout;
-      y = oy * g.sh;
-      xx = ox * g.sw;
-    } else {
-      int p = copy / g.kw, j = copy - p * g.kw;
-      y = g.sh * (r - g.Ht) + g.rowphase_py[p];
-      xx = g.sw * xs - g.pw + j;
-      valid = (xs < g.Wout) && (y >= 0) && (y < g.H) && (xx >= 0) && (xx < g.W);
-    }
-    float v = 0.f;
-    if (valid) {
-      const float* p = x + ((long long)c * g.H + y) * g.W + xx;
-      float s = 0.f;
-#pragma unroll 4
-      for (int b = 0; b < B; ++b) s += __ldg(p + (long long)b * img);
-      v = s / fb;
-    }
-    float hi, lo;
-    tf32_split(v, hi, lo);
-    stage[idx] = hi;
-    stage[idx + hl_stride] = lo;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Fast paths (same staged layout as stage_conv_kernel, 128-bit loads and stores).
-// ---------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 v;
   asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -76,6 +29,63 @@ __device__ __forceinline__ void split_store4(float* hi, float* lo, float a, floa
   *reinterpret_cast<float4*>(lo) = l;
 }
 
+__global__ void __launch_bounds__(256)
+stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
+                  int B, long long hl_stride) {
+  // one thread per aligned group of 4 staged columns (Ws % 4 == 0): the row decode is
+  // paid once per float4 and both planes are written with 128-bit stores
+  const int W4 = g.Ws >> 2;
+  const long long total = (long long)g.Cs * g.Hs * g.ncopy * W4;
+  const long long img = (long long)g.C * g.H * g.W;
+  const float fb = (float)B;
+  const int HWout = g.Hout * g.Wout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x4 = (int)(idx % W4);
+    long long rest = idx / W4;
+    const int r = (int)(rest % g.Hs);
+    rest /= g.Hs;
+    const int c = (int)(rest % g.Cs);
+    const int copy = (int)(rest / g.Cs);
+    int p = 0, j = 0, y = 0;
+    bool row_ok = true;
+    if (g.mode != kModeFlat) {
+      p = copy / g.kw; j = copy - p * g.kw;
+      y = g.sh * (r - g.Ht) + g.rowphase_py[p];
+      row_ok = (y >= 0) && (y < g.H);
+    }
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int xs = x4 * 4 + e;
+      int yy, xx;
+      bool valid;
+      if (g.mode == kModeFlat) {
+        valid = xs < HWout;
+        const int oy = xs / g.Wout, ox = xs - oy * g.Wout;
+        yy = oy * g.sh;
+        xx = ox * g.sw;
+      } else {
+        yy = y;
+        xx = g.sw * xs - g.pw + j;
+        valid = row_ok && (xs < g.Wout) && (xx >= 0) && (xx < g.W);
+      }
+      float acc = 0.f;
+      if (valid) {
+        const float* q = x + ((long long)c * g.H + yy) * g.W + xx;
+        for (int b = 0; b < B; ++b) acc += __ldg(q + (long long)b * img);
+        acc /= fb;
+      }
+      v[e] = acc;
+    }
+    float* o = stage + (((long long)copy * g.Cs + c) * g.Hs + r) * g.Ws + x4 * 4;
+    split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fast paths (same staged layout as stage_conv_kernel, 128-bit loads and stores).
+// ---------------------------------------------------------------------------
 // 1x1 stride-1 conv input with H*W % 4 == 0: the staged plane is the batch mean of
 // x itself.  One thread per float4.
 template <int B_UNROLL>
@@ -101,6 +111,35 @@ stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, lo
     }
     split_store4(stage + i * 4, stage + i * 4 + hl_stride, s.x / inv_div, s.y / inv_div,
                  s.z / inv_div, s.w / inv_div);
+  }
+}
+
+// Batch mean of x (B, n) -> out (n), n % 4 == 0, 16-byte aligned: first pass of the
+// two-pass staging used by the layouts whose second pass is a gather (stride-2 tap
+// copies, odd widths, the explicit stem): the gather then reads 1/B of the data.
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+batch_mean_vec_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int B,
+                      long long img) {
+  const float fb = (float)B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float* p = x + i * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int b = 0;
+    for (; b + B_UNROLL <= B; b += B_UNROLL) {
+      float4 v[B_UNROLL];
+#pragma unroll
+      for (int u = 0; u < B_UNROLL; ++u) v[u] = ldg_stream4(p + (long long)(b + u) * img);
+#pragma unroll
+      for (int u = 0; u < B_UNROLL; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; b < B; ++b) {
+      float4 v = ldg_stream4(p + (long long)b * img);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i * 4) =
+        make_float4(s.x / fb, s.y / fb, s.z / fb, s.w / fb);
   }
 }
 
@@ -334,37 +373,42 @@ stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ col
 __global__ void __launch_bounds__(256)
 stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stage,
                            ConvGeom g, int B, long long hl_stride) {
-  const long long total = (long long)g.Cs * g.Ws;
+  // blockIdx.y = im2col row (c, i, j) - uniform per block; threads over groups of 4 K columns
   const long long img = (long long)g.C * g.H * g.W;
   const int taps = g.kh * g.kw;
   const int d = g.C * taps;
   const int K = g.Hout * g.Wout;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(idx % g.Ws);
-    int row = (int)(idx / g.Ws);
-    float v = 0.f;
-    if (row < d && k < K) {
-      int c = row / taps, t = row - c * taps;
-      int i = t / g.kw, j = t - i * g.kw;
-      int oy = k / g.Wout, ox = k - oy * g.Wout;
-      int y = oy * g.sh - g.ph + i, xx = ox * g.sw - g.pw + j;
-      if (y >= 0 && y < g.H && xx >= 0 && xx < g.W) {
-        const float* p = x + ((long long)c * g.H + y) * g.W + xx;
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += __ldg(p + (long long)b * img);
-        v = s / (float)B;
+  const int row = blockIdx.y;
+  const int c = row / taps, t = row - c * taps;
+  const int i = t / g.kw, j = t - i * g.kw;
+  const bool row_ok = row < d;
+  const float fb = (float)B;
+  const int W4 = g.Ws >> 2;
+  for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < W4; k4 += gridDim.x * blockDim.x) {
+    float v[4];
+    int k = k4 * 4;
+    int oy = k / g.Wout, ox = k - oy * g.Wout;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float acc = 0.f;
+      if (row_ok && k + e < K) {
+        const int y = oy * g.sh - g.ph + i, xx = ox * g.sw - g.pw + j;
+        if (y >= 0 && y < g.H && xx >= 0 && xx < g.W) {
+          const float* q = x + ((long long)c * g.H + y) * g.W + xx;
+          for (int b = 0; b < B; ++b) acc += __ldg(q + (long long)b * img);
+          acc /= fb;
+        }
       }
+      v[e] = acc;
+      if (++ox == g.Wout) { ox = 0; ++oy; }
     }
-    float hi, lo;
-    tf32_split(v, hi, lo);
-    stage[idx] = hi;
-    stage[idx + hl_stride] = lo;
+    float* o = stage + (long long)row * g.Ws + k;
+    split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
 }
 
 int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
-                      cudaStream_t stream) {
+                      float* mean_scratch, cudaStream_t stream) {
   long long total = (g.mode == kModeExplicit) ? (long long)g.Cs * g.Ws
                                               : (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
   long long hl = stage_hl_stride(g);
@@ -378,10 +422,21 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
       if (blocks > 148 * 16) blocks = 148 * 16;
       stage_autocorr_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl);
     } else {
+      const float* src = x;
+      int Bg = B;
+      if (B > 1 && aligned && mean_scratch != nullptr) {
+        long long n4 = img / 4;
+        int mb = (int)((n4 + 255) / 256);
+        if (mb > 148 * 16) mb = 148 * 16;
+        batch_mean_vec_kernel<8><<<mb, 256, 0, stream>>>(x, mean_scratch, n4, B, img);
+        NSGP_LAUNCHED();
+        src = mean_scratch;
+        Bg = 1;
+      }
       long long n = (long long)g.C * g.Hs * g.Ws * 3;
       int blocks = (int)((n + 255) / 256);
       if (blocks > 148 * 32) blocks = 148 * 32;
-      stage_autocorr_kernel<<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, g.Hs, g.Ws, B, hl);
+      stage_autocorr_kernel<<<blocks, 256, 0, stream>>>(src, stage, g.C, g.H, g.W, g.Hs, g.Ws, Bg, hl);
     }
     NSGP_LAUNCHED();
     const int Hc = ac_col_pitch(g);
@@ -406,13 +461,31 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
     if (blocks > 148 * 16) blocks = 148 * 16;
     stage_3x3s1_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl);
   } else {
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    if (blocks < 1) blocks = 1;
-    if (g.mode == kModeExplicit)
-      stage_conv_explicit_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
-    else
-      stage_conv_kernel<<<blocks, 256, 0, stream>>>(x, stage, g, B, hl);
+    // gather layouts: average the batch first (vectorised), then gather from the mean -
+    // unless the gather touches only a fraction of the input (strided 1x1)
+    const float* src = x;
+    int Bg = B;
+    const bool sparse = g.mode == kModeFlat && g.sh * g.sw > 1;
+    if (B > 1 && aligned && mean_scratch != nullptr && !sparse) {
+      long long n4 = img / 4;
+      int mb = (int)((n4 + 255) / 256);
+      if (mb > 148 * 16) mb = 148 * 16;
+      batch_mean_vec_kernel<8><<<mb, 256, 0, stream>>>(x, mean_scratch, n4, B, img);
+      NSGP_LAUNCHED();
+      src = mean_scratch;
+      Bg = 1;
+    }
+    if (g.mode == kModeExplicit) {
+      int bx = ceil_div(g.Ws / 4, 256);
+      if (bx > 64) bx = 64;
+      dim3 grid(bx, g.Cs);
+      stage_conv_explicit_kernel<<<grid, 256, 0, stream>>>(src, stage, g, Bg, hl);
+    } else {
+      int blocks = (int)((total / 4 + 255) / 256);
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      if (blocks < 1) blocks = 1;
+      stage_conv_kernel<<<blocks, 256, 0, stream>>>(src, stage, g, Bg, hl);
+    }
   }
   NSGP_LAUNCHED();
   return 0;
