@@ -9,6 +9,8 @@ sm_100a kernels reached through the C ABI of ``include/nsgp_repre_b200.h``:
 * ``optim.SGDNSCL``                - mmdet/engine/optimizers/SGD_NSCL.py:15
 * ``prototypes.MultiPrototypeReplay`` / ``StandardMultiPrototypeReplayHead``
   - mmdet/models/roi_heads/standard_roi_replay_head.py:375
+* ``rois``                         - all_gather_different_shape + the cal_rois tail
+  (mmdet/engine/runner/nsrunner_roi_replay.py:73-105, 815-865)
 * ``registry``                     - registers the above into mmengine / mmdet
   when those packages are importable.
 
@@ -21,4 +23,5 @@ from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
 from .covariance import CovarianceHooks, BRNullSpaceCovariance  # noqa: F401
 from .optim import SGDNSCL  # noqa: F401
 from .prototypes import MultiPrototypeReplay, StandardMultiPrototypeReplayHead  # noqa: F401
+from .rois import all_gather_different_shape, RoIHarvest  # noqa: F401
 from . import registry  # noqa: F401

@@ -100,3 +100,34 @@ def test_shard_batches():
     from nsgp_repre_b200.dist import shard_batches
     got = sorted(sum((shard_batches(11, r, 4) for r in range(4)), []))
     assert got == list(range(11))
+
+
+def test_roi_harvest_single_process_merge_and_reserve(tmp_path):
+    """cal_rois tail (nsrunner_roi_replay.py:825-865) without a process group: reserve N
+    rows per class with one permutation per class shared by the six tensors, prepend the
+    previous task's rois_etc.pth, keep the list-of-6 on-disk format."""
+    from nsgp_repre_b200.rois import RoIHarvest
+    g = torch.Generator().manual_seed(0)
+    M = 40
+    cls = torch.randint(0, 4, (M,), generator=g)
+    feats = torch.randn(M, 16, generator=g)
+    h = RoIHarvest()
+    h.add(feats[:25], cls[:25], torch.ones(25), torch.zeros(25, 4), torch.ones(25, 4),
+          torch.arange(25 * 5, dtype=torch.float32).view(25, 5))
+    h.add(feats[25:], cls[25:], torch.ones(15), torch.zeros(15, 4), torch.ones(15, 4),
+          torch.arange(15 * 5, dtype=torch.float32).view(15, 5))
+    prev = tmp_path / "t_1"
+    prev.mkdir()
+    old = [torch.zeros(3, 16), torch.full((3,), 9, dtype=torch.int64), torch.ones(3),
+           torch.zeros(3, 4), torch.ones(3, 4), torch.zeros(3, 5)]
+    torch.save(old, str(prev / "rois_etc.pth"))
+    out = h.finish(work_dir=str(tmp_path), previous_dir=str(prev), task_id=2,
+                   reserve_per_class=2, num_classes=4, generator=torch.Generator().manual_seed(1))
+    assert len(out) == 6 and out[0].shape == (3 + 8, 16)
+    assert out[1][:3].tolist() == [9, 9, 9] and out[1][3:].tolist() == [0, 0, 1, 1, 2, 2, 3, 3]
+    # the same rows were picked for every tensor: features of row i belong to class out[1][i]
+    for i in range(3, 11):
+        src = (feats == out[0][i]).all(dim=1).nonzero().flatten()
+        assert src.numel() == 1 and int(cls[src]) == int(out[1][i])
+    again = torch.load(str(tmp_path / "rois_etc.pth"))
+    assert isinstance(again, list) and len(again) == 6 and torch.equal(again[0], out[0])

@@ -43,6 +43,21 @@ def _worker(rank, world, port, ret):
     D.all_reduce_sum_(t)
     ok &= bool((t[0] == 3).all() and (t[1] == 30).all())
     ok &= D.max_over_ranks(float(rank), "cpu") == 1.0
+    # variable-length gather (nsrunner_roi_replay.py:73-105): rank r holds r+2 rows
+    from nsgp_repre_b200.rois import all_gather_different_shape, RoIHarvest
+    mine_t = torch.arange((rank + 2) * 3, dtype=torch.float32).view(rank + 2, 3) + 100 * rank
+    parts = all_gather_different_shape(mine_t)
+    ok &= len(parts) == world
+    for r in range(world):
+        want = torch.arange((r + 2) * 3, dtype=torch.float32).view(r + 2, 3) + 100 * r
+        ok &= bool(torch.equal(parts[r], want))
+    # cal_rois tail: gather -> list of 6 in rank order
+    h = RoIHarvest()
+    n = rank + 2
+    h.add(torch.full((n, 8), float(rank)), torch.full((n,), rank, dtype=torch.int64),
+          torch.ones(n), torch.zeros(n, 4), torch.ones(n, 4), torch.zeros(n, 5))
+    res = h.finish()
+    ok &= len(res) == 6 and res[0].shape == (5, 8) and res[1].tolist() == [0, 0, 1, 1, 1]
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
