@@ -265,6 +265,17 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 while the
+    # job runs (NCCL prints its version there) goes to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -348,9 +359,11 @@ def main():
         return proto.staged()
 
     def hot_step():
+        # the three phases are independent; RePRE goes first because its one host sync
+        # (greedy cover on the host) would otherwise wait behind the grouped covariance launch
+        repre_step(feats_d, labels_d)
         cov_pass()
         sgd_step()
-        repre_step(feats_d, labels_d)
 
     def barrier():
         if world > 1:
@@ -568,9 +581,9 @@ def main():
                                            "projection": proj_flops / 1e9},
             "projector_build_s": projector_build_s, "protected_layers": n_protected,
             "layer_input_bytes": input_bytes}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    emit(line)
 
 
 if __name__ == "__main__":
