@@ -164,8 +164,9 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
  * changes (gradient and momentum pointers may change freely between steps). */
 typedef struct {
   int kind;
-  int n_problems[2], n_items[2];   /* [0] single-CTA kernel, [1] CTA-pair (cta_group::2) kernel */
-  size_t off_probs[2], off_items[2];
+  int n_problems[3], n_items[3];   /* [0] single-CTA kernel, [1] CTA-pair (cta_group::2) kernel,
+                                      [2] sliding-window autocorrelation kernel */
+  size_t off_probs[3], off_items[3];
   size_t bytes;
 } nsgp_group_t;
 
@@ -272,6 +273,17 @@ int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int 
 /* bring-up: per-CTA wait/issue cycle counters of the last tcgen05 contraction launched
  * with NSGP_DBG_COUNTERS=1 in the environment (8 counters per CTA, host buffer) */
 int nsgp_debug_read_counters(unsigned long long* out /* host */, int n);
+
+/* bring-up: cycles one CTA per SM needs for `iters` K blocks of tcgen05 MMAs on
+ * shared-memory-resident operands (mode: see csrc/mma_rate.cu); out_dev: n_ctas u64 */
+int nsgp_debug_mma_rate(int mode, int iters, unsigned long long* out_dev /* device */,
+                        int n_ctas, void* stream);
+
+/* bring-up: cycles per CTA for `iters` 64 KB TMA stages (4 boxes of 128 rows x 128 B) with
+ * `depth` stages in flight, from a (rows x K) fp32 matrix of the given row pitch */
+int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
+                         int depth, unsigned long long* out_dev /* device */, int n_ctas,
+                         void* stream);
 
 /* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);

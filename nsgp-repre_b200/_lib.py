@@ -36,8 +36,8 @@ class ProjLayer(C.Structure):
 
 
 class Group(C.Structure):
-    _fields_ = [("kind", c_int), ("n_problems", c_int * 2), ("n_items", c_int * 2),
-                ("off_probs", c_size_t * 2), ("off_items", c_size_t * 2), ("bytes", c_size_t)]
+    _fields_ = [("kind", c_int), ("n_problems", c_int * 3), ("n_items", c_int * 3),
+                ("off_probs", c_size_t * 3), ("off_items", c_size_t * 3), ("bytes", c_size_t)]
 
 
 class SgdPlan(C.Structure):
@@ -108,6 +108,9 @@ SIGNATURES = {
     "repre_kmeans_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
     "nsgp_debug_read_counters": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
+    "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
+    "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_int, c_void_p]),
     "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
 }

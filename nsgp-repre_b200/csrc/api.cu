@@ -105,7 +105,7 @@ static size_t layer_table_bytes(const ConvGeom& g) {
   ContractionArgs probs[kMaxConvProblems];
   int n = 0;
   conv_problems(g, nullptr, nullptr, probs, &n);
-  return group_table_bytes(probs, n) + 1024;
+  return group_table_bytes(probs, n) + 1024 + autocorr_table_bytes(&g, 1) + 256;
 }
 
 int nsgp_cov_conv2d_layout(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
@@ -142,6 +142,58 @@ int nsgp_cov_linear_layout(int d, nsgp_cov_layout_t* out) {
   out->acc_bytes = (size_t)out->ld * d * sizeof(float);
   out->workspace_bytes = (size_t)round_up(d, 4) * sizeof(float) + 256;
   return 0;
+}
+
+// Group table of a set of staged layers: generic problems (single-CTA / pair kernel) and,
+// for the autocorrelation layers, the 13 R blocks through the sliding-window kernel.
+static int cov_layers_group_build(const ConvGeom* geoms, float* const* stages, float* const* accs,
+                                  int n, void* table_dev, size_t table_bytes, GroupInfo* gi,
+                                  cudaStream_t stream) {
+  std::vector<ContractionArgs> probs;
+  std::vector<ConvGeom> ac_g;
+  std::vector<const float*> ac_s;
+  std::vector<float*> ac_a;
+  for (int i = 0; i < n; ++i) {
+    ContractionArgs p[kMaxConvProblems];
+    int np = 0;
+    conv_problems(geoms[i], stages[i], accs[i], p, &np, i + 1);
+    if (geoms[i].mode == kModeAutocorr && geoms[i].tiled) {
+      ac_g.push_back(geoms[i]);             // R blocks go to the sliding-window kernel
+      ac_s.push_back(stages[i]);
+      ac_a.push_back(accs[i]);
+    }
+    probs.insert(probs.end(), p, p + np);
+  }
+  int rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table_dev, table_bytes,
+                             gi, stream);
+  if (rc) return rc;
+  if (!ac_g.empty()) {
+    const size_t off = (size_t)round_up((long long)gi->bytes, 256);
+    NSGP_REQUIRE(off <= table_bytes, "cov group: table too small");
+    SubGroup sg{};
+    rc = autocorr_table_build(ac_g.data(), ac_s.data(), ac_a.data(), (int)ac_g.size(),
+                              (char*)table_dev + off, table_bytes - off, &sg, stream);
+    if (rc) return rc;
+    sg.off_probs += off;
+    sg.off_items += off;
+    gi->sub[2] = sg;
+    gi->bytes = sg.off_items + (size_t)sg.n_items * 32;
+  }
+  return 0;
+}
+
+static size_t cov_layers_group_bytes(const ConvGeom* geoms, int n) {
+  std::vector<ContractionArgs> probs;
+  std::vector<ConvGeom> ac_g;
+  for (int i = 0; i < n; ++i) {
+    ContractionArgs p[kMaxConvProblems];
+    int np = 0;
+    conv_problems(geoms[i], nullptr, nullptr, p, &np, i + 1);
+    probs.insert(probs.end(), p, p + np);
+    if (geoms[i].mode == kModeAutocorr && geoms[i].tiled) ac_g.push_back(geoms[i]);
+  }
+  return group_table_bytes(probs.data(), (int)probs.size()) + 512 +
+         autocorr_table_bytes(ac_g.data(), (int)ac_g.size());
 }
 
 static int cov_conv2d_setup(int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
@@ -188,11 +240,12 @@ int nsgp_cov_conv2d_contract(int C, int H, int W, int kh, int kw, int sh, int sw
   int n = 0;
   conv_problems(g, stage, acc, probs, &n);
   if (n > 1 && g_engine == 0) {
-    // one persistent launch for all problems of the layer
+    // one or two persistent launches for all problems of the layer
     char* table = align_up((char*)stage + stage_bytes(g), 256);
     const size_t room = (size_t)(((const char*)workspace + workspace_bytes) - table);
     GroupInfo gi{};
-    rc = group_table_build(probs, n, kProfGram, table, room, &gi, (cudaStream_t)stream_);
+    float* stage_p = stage;
+    rc = cov_layers_group_build(&g, &stage_p, &acc, 1, table, room, &gi, (cudaStream_t)stream_);
     if (rc) return rc;
     return group_launch(table, gi, (cudaStream_t)stream_);
   }
@@ -295,7 +348,7 @@ static int sgd_tables(const nsgp_sgd_tensor_t* tensors, int n_tensors,
 
 static void group_to_abi(const GroupInfo& gi, nsgp_group_t* g) {
   g->kind = gi.kind;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     g->n_problems[k] = gi.sub[k].n_problems;
     g->n_items[k] = gi.sub[k].n_items;
     g->off_probs[k] = gi.sub[k].off_probs;
@@ -306,7 +359,7 @@ static void group_to_abi(const GroupInfo& gi, nsgp_group_t* g) {
 static GroupInfo group_from_abi(const nsgp_group_t& g) {
   GroupInfo gi{};
   gi.kind = g.kind;
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 3; ++k)
     gi.sub[k] = SubGroup{g.n_problems[k], g.n_items[k], g.off_probs[k], g.off_items[k]};
   gi.bytes = g.bytes;
   return gi;
@@ -510,41 +563,42 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
 }
 
 // ---- grouped covariance contraction (deferred mode of the hooks) ----------------
-static int cov_job_problems(const nsgp_cov_job_t& j, int l2_group,
-                            std::vector<ContractionArgs>* out) {
-  ConvGeom g;
-  float* stage;
-  int rc = cov_conv2d_setup(j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw,
-                            const_cast<void*>(j.workspace), j.workspace_bytes, &g, &stage);
-  if (rc) return rc;
-  NSGP_REQUIRE(j.acc != nullptr, "cov_group: null accumulator");
-  ContractionArgs probs[kMaxConvProblems];
-  int n = 0;
-  conv_problems(g, stage, j.acc, probs, &n, l2_group);
-  out->insert(out->end(), probs, probs + n);
+static int cov_jobs_setup(const nsgp_cov_job_t* jobs, int n_jobs, std::vector<ConvGeom>* geoms,
+                          std::vector<float*>* stages, std::vector<float*>* accs) {
+  for (int i = 0; i < n_jobs; ++i) {
+    const nsgp_cov_job_t& j = jobs[i];
+    ConvGeom g;
+    float* stage;
+    int rc = cov_conv2d_setup(j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw,
+                              const_cast<void*>(j.workspace), j.workspace_bytes, &g, &stage);
+    if (rc) return rc;
+    NSGP_REQUIRE(j.acc != nullptr, "cov_group: null accumulator");
+    geoms->push_back(g);
+    stages->push_back(stage);
+    accs->push_back(j.acc);
+  }
   return 0;
 }
 
 size_t nsgp_cov_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs) {
   if (!jobs || n_jobs <= 0) return 1024;
-  std::vector<ContractionArgs> probs;
-  for (int i = 0; i < n_jobs; ++i)
-    if (cov_job_problems(jobs[i], i + 1, &probs)) return 0;
-  return group_table_bytes(probs.data(), (int)probs.size()) + 256;
+  std::vector<ConvGeom> geoms;
+  std::vector<float*> stages, accs;
+  if (cov_jobs_setup(jobs, n_jobs, &geoms, &stages, &accs)) return 0;
+  return cov_layers_group_bytes(geoms.data(), n_jobs) + 256;
 }
 
 int nsgp_cov_group_build(const nsgp_cov_job_t* jobs, int n_jobs, void* table_dev,
                          size_t table_bytes, nsgp_group_t* group, void* stream_) {
   NSGP_REQUIRE(jobs && table_dev && group && n_jobs > 0, "cov_group_build: bad arguments");
   NSGP_REQUIRE(g_engine == 0, "cov_group_build: groups need the tcgen05 engine");
-  std::vector<ContractionArgs> probs;
-  for (int i = 0; i < n_jobs; ++i) {
-    int rc = cov_job_problems(jobs[i], i + 1, &probs);
-    if (rc) return rc;
-  }
+  std::vector<ConvGeom> geoms;
+  std::vector<float*> stages, accs;
+  int rc = cov_jobs_setup(jobs, n_jobs, &geoms, &stages, &accs);
+  if (rc) return rc;
   GroupInfo gi{};
-  int rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table_dev, table_bytes,
-                             &gi, (cudaStream_t)stream_);
+  rc = cov_layers_group_build(geoms.data(), stages.data(), accs.data(), n_jobs, table_dev,
+                              table_bytes, &gi, (cudaStream_t)stream_);
   if (rc) return rc;
   group_to_abi(gi, group);
   return 0;
@@ -760,8 +814,22 @@ int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int 
 }
 
 int nsgp_debug_read_counters(unsigned long long* out, int n) {
-  NSGP_REQUIRE(out && n > 0 && n <= 160 * 8, "debug_read_counters: bad arguments");
+  NSGP_REQUIRE(out && n != 0 && n <= 160 * 8 && n >= -160 * 8, "debug_read_counters: bad arguments");
+  if (n < 0) return debug_read_ac_counters(out, -n);     // autocorrelation kernel's counters
   return debug_read_counters(out, n);
+}
+
+int nsgp_debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_ctas,
+                        void* stream_) {
+  NSGP_REQUIRE(out_dev && iters > 0 && n_ctas > 0, "debug_mma_rate: bad arguments");
+  return debug_mma_rate(mode, iters, out_dev, n_ctas, (cudaStream_t)stream_);
+}
+
+int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
+                         int depth, unsigned long long* out_dev, int n_ctas, void* stream_) {
+  NSGP_REQUIRE(base && out_dev, "tma_probe: null pointer");
+  return debug_tma_probe(base, pitch_elems, K, rows, iters, depth, out_dev, n_ctas,
+                         (cudaStream_t)stream_);
 }
 
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream_) {

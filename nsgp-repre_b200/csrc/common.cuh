@@ -114,7 +114,8 @@ struct SubGroup {
   size_t off_probs, off_items;
 };
 struct GroupInfo {
-  SubGroup sub[2];                 // [0] single-CTA kernel, [1] CTA-pair kernel
+  SubGroup sub[3];                 // [0] single-CTA kernel, [1] CTA-pair kernel,
+                                   // [2] sliding-window autocorrelation kernel
   int kind;                        // ProfKind of the launches (kProfGram / kProfGemm)
   size_t bytes;
 };
@@ -124,6 +125,20 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream);
 
 int debug_read_counters(unsigned long long* out, int n);
+int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
+                    int depth, unsigned long long* out_dev, int n_ctas, cudaStream_t stream);
+int debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_ctas,
+                   cudaStream_t stream);
+
+// sliding-window autocorrelation kernel (contraction_ac.cu)
+struct ConvGeom;
+bool autocorr_kernel_enabled();
+int debug_read_ac_counters(unsigned long long* out, int n);
+size_t autocorr_table_bytes(const ConvGeom* geoms, int n);
+int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, float* const* accs,
+                         int n, void* table_dev, size_t table_bytes, SubGroup* sg,
+                         cudaStream_t stream);
+int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream);
 
 // engines
 int contraction_simt(const ContractionArgs& a, cudaStream_t stream);

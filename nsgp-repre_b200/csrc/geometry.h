@@ -50,6 +50,10 @@ struct ConvGeom {
   int rowphase_py[kMaxTaps];   // py of row-phase slot p
   int Hs, Ws;   // staged plane height / pitch
   int Ht;       // top halo in plane rows
+  int tiled;    // autocorr: copies stored tile-major (128 channels x 32 columns = 16 KB
+                // contiguous per (copy, channel block, row, column strip)) for the
+                // sliding-window kernel; TMA of contiguous tiles sustains > 2x the bytes/cycle
+                // of 128 scattered 128-byte rows (scripts/tma_probe.py)
   int d;        // true covariance dimension C*kh*kw
   int d_int;    // internal accumulator dimension (T*Cs)
 };
@@ -86,6 +90,7 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
     g.Ws = (int)round_up(W + 2, ws_align);         // >= two zero columns on the right
     g.Ht = 0;
     g.d_int = kAcMats * C;
+    g.tiled = (g_engine == 0 && autocorr_kernel_enabled()) ? 1 : 0;
     *out = g;
     return 0;
   }
@@ -121,7 +126,18 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
 
 // autocorr extras: edge columns (2 sides x 3 row shifts, pitch Hc) and corner pixels
 static inline int ac_col_pitch(const ConvGeom& g) { return (int)round_up(g.H + 2, 4); }
-static inline long long ac_colbuf_off(const ConvGeom& g) { return 3LL * g.C * g.Hs * g.Ws; }
+static inline int ac_cblocks(const ConvGeom& g) { return ceil_div(g.C, 128); }
+static inline int ac_strips(const ConvGeom& g) { return ceil_div(g.W, 32); }
+static inline int ac_row_pitch(const ConvGeom& g) { return (int)round_up(g.W, 4); }
+// tiled: [3 copies x cblocks x Hs rows x strips] tiles of 4096 floats, then the two edge
+// rows of the three copies in plain layout (for the edge-row GEMMs)
+static inline long long ac_main_elems(const ConvGeom& g) {
+  return g.tiled ? 3LL * ac_cblocks(g) * g.Hs * ac_strips(g) * 4096 : 3LL * g.C * g.Hs * g.Ws;
+}
+static inline long long ac_rowbuf_off(const ConvGeom& g) { return ac_main_elems(g); }
+static inline long long ac_colbuf_off(const ConvGeom& g) {
+  return ac_main_elems(g) + (g.tiled ? 6LL * g.C * ac_row_pitch(g) : 0);
+}
 static inline long long ac_cornerbuf_off(const ConvGeom& g) {
   return ac_colbuf_off(g) + 6LL * g.C * ac_col_pitch(g);
 }
@@ -211,8 +227,9 @@ static inline void conv_problems(const ConvGeom& g, const float* stage, float* a
     a.l2_group = l2_group;
     out[n++] = a;
   };
-  // R_(dy,dx)
-  for (int dy = 0; dy <= 2; ++dy)
+  // R_(dy,dx): generic GEMM problems over the plane layout; with the tiled layout they
+  // are computed by the sliding-window kernel instead (contraction_ac.cu)
+  for (int dy = 0; dy <= 2 && !g.tiled; ++dy)
     for (int dx = (dy == 0 ? 0 : -2); dx <= 2; ++dx) {
       const float* a_base = stage + (dx < 0 ? -dx : 0) * plane;
       const float* b_base = stage + (dx > 0 ? dx : 0) * plane + (long long)dy * g.Ws;
@@ -220,6 +237,14 @@ static inline void conv_problems(const ConvGeom& g, const float* stage, float* a
     }
   // edge rows: bottom (u = H-1) and top (u = 0), dx = 0..2
   for (int e = 0; e < 2; ++e) {
+    if (g.tiled) {
+      const int Wr = ac_row_pitch(g);
+      const float* rb = stage + ac_rowbuf_off(g) + (long long)e * 3 * g.C * Wr;
+      for (int dx = 0; dx <= 2; ++dx)
+        add(rb, rb + (long long)dx * g.C * Wr, g.W, Wr,
+            mat((e == 0 ? kAcRowBottom : kAcRowTop) + dx), false);
+      continue;
+    }
     const long long row = (long long)(e == 0 ? g.H - 1 : 0) * g.Ws;
     for (int dx = 0; dx <= 2; ++dx)
       add(stage + row, stage + dx * plane + row, g.Ws, pitch,
@@ -244,7 +269,7 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
 // scratch (floats) for the batch mean of the gather layouts' two-pass staging
 static inline size_t mean_scratch_elems(const ConvGeom& g) {
   const bool vec_flat = g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && (g.H * g.W) % 4 == 0;
-  const bool vec_ac = g.mode == kModeAutocorr && g.W % 4 == 0 && g.Ws == g.W + 4;
+  const bool vec_ac = g.mode == kModeAutocorr && g.W % 4 == 0 && (g.tiled || g.Ws == g.W + 4);
   if (vec_flat || vec_ac) return 0;
   return (size_t)round_up((long long)g.C * g.H * g.W, 4);
 }

@@ -221,24 +221,36 @@ stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, i
 // zero-extended batch mean, copy_s[c][r][x] = m~[c][r][x+s], r < H+2, x < Ws, plus the
 // edge-column and corner-pixel buffers of the boundary corrections.
 // ---------------------------------------------------------------------------
+// tiled: destination of element (copy s, channel c, row r, column xs) in the tile-major
+// layout: tile ((s*CB + c/128)*Hs + r)*NS + xs/32, 128 channels x 32 columns per tile
+__device__ __forceinline__ long long ac_tiled_off(int s, int c, int r, int xs, int CB, int Hs,
+                                                  int NS) {
+  const long long tile = ((long long)(s * CB + (c >> 7)) * Hs + r) * NS + (xs >> 5);
+  return tile * 4096 + (long long)(c & 127) * 32 + (xs & 31);
+}
+
 __global__ void __launch_bounds__(256)
 stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                      int W, int Hs, int Ws, int B, long long hl_stride) {
-  const long long plane = (long long)C * Hs * Ws;
-  const long long total = plane * 3;
+                      int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
+                      float* __restrict__ rowbuf) {
+  // plane layout: [3][C][Hs][Ws];  tiled layout: [3][CB*128][Hs][NS*32] tile-major, plus the
+  // two edge rows of every copy in plain layout rowbuf[e][s][c][Wr]
+  const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Wr = (W + 3) & ~3;
+  const int Cc = tiled ? CB * 128 : C, Wc = tiled ? NS * 32 : Ws;
+  const long long total = 3LL * Cc * Hs * Wc;
   const long long img = (long long)C * H * W;
   const float fb = (float)B;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int xs = (int)(idx % Ws);
-    long long rest = idx / Ws;
+    int xs = (int)(idx % Wc);
+    long long rest = idx / Wc;
     int r = (int)(rest % Hs);
     rest /= Hs;
-    int c = (int)(rest % C);
-    int s = (int)(rest / C);
+    int c = (int)(rest % Cc);
+    int s = (int)(rest / Cc);
     int xx = xs + s;
     float v = 0.f;
-    if (r < H && xx < W) {
+    if (c < C && r < H && xx < W) {
       const float* p = x + ((long long)c * H + r) * W + xx;
       float acc = 0.f;
 #pragma unroll 4
@@ -247,8 +259,19 @@ stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, in
     }
     float hi, lo;
     tf32_split(v, hi, lo);
-    stage[idx] = hi;
-    stage[idx + hl_stride] = lo;
+    const long long o = tiled ? ac_tiled_off(s, c, r, xs, CB, Hs, NS) : idx;
+    stage[o] = hi;
+    stage[o + hl_stride] = lo;
+    if (tiled && c < C && xs < Wr && (r == 0 || r == H - 1)) {
+      if (r == H - 1) {
+        const long long q = ((long long)(0 * 3 + s) * C + c) * Wr + xs;
+        rowbuf[q] = hi; rowbuf[q + hl_stride] = lo;
+      }
+      if (r == 0) {
+        const long long q = ((long long)(1 * 3 + s) * C + c) * Wr + xs;
+        rowbuf[q] = hi; rowbuf[q + hl_stride] = lo;
+      }
+    }
   }
 }
 
@@ -256,9 +279,12 @@ stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, in
 template <int B_UNROLL>
 __global__ void __launch_bounds__(256)
 stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                          int W, int B, long long hl_stride) {
-  const int Hs = H + 2, Ws = W + 4, W4 = Ws >> 2;
-  const long long total = (long long)C * Hs * W4;
+                          int W, int B, long long hl_stride, int tiled,
+                          float* __restrict__ rowbuf) {
+  const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Wr = W;      // W % 4 == 0 here
+  const int Hs = H + 2, Ws = tiled ? NS * 32 : W + 4, W4 = Ws >> 2;
+  const int Cc = tiled ? CB * 128 : C;
+  const long long total = (long long)Cc * Hs * W4;
   const long long img = (long long)C * H * W;
   const long long plane = (long long)C * Hs * Ws;
   const float fb = (float)B;
@@ -274,7 +300,7 @@ stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage
       r = (int)(rest % Hs);
       c = (int)(rest / Hs);
     }
-    const bool data = live && r < H && x4 * 4 < W;
+    const bool data = live && c < C && r < H && x4 * 4 < W;
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* p = x + ((long long)c * H + r) * W + x4 * 4;
     if (data) {
@@ -307,11 +333,29 @@ stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage
       }
       n0 = s0 / fb; n1 = s1 / fb;
     }
-    if (live) {
+    if (live && !tiled) {
       float* o = stage + ((long long)c * Hs + r) * Ws + x4 * 4;
       split_store4(o, o + hl_stride, m.x, m.y, m.z, m.w);                          // shift 0
       split_store4(o + plane, o + plane + hl_stride, m.y, m.z, m.w, n0);          // shift 1
       split_store4(o + 2 * plane, o + 2 * plane + hl_stride, m.z, m.w, n0, n1);   // shift 2
+    } else if (live) {
+      float* o0 = stage + ac_tiled_off(0, c, r, x4 * 4, CB, Hs, NS);
+      float* o1 = stage + ac_tiled_off(1, c, r, x4 * 4, CB, Hs, NS);
+      float* o2 = stage + ac_tiled_off(2, c, r, x4 * 4, CB, Hs, NS);
+      split_store4(o0, o0 + hl_stride, m.x, m.y, m.z, m.w);
+      split_store4(o1, o1 + hl_stride, m.y, m.z, m.w, n0);
+      split_store4(o2, o2 + hl_stride, m.z, m.w, n0, n1);
+      if (c < C && x4 * 4 < Wr && (r == 0 || r == H - 1)) {
+        // edge rows of the three copies, plain layout (pitch Wr)
+        for (int e = 0; e < 2; ++e) {
+          if (r != (e == 0 ? H - 1 : 0)) continue;
+          float* q = rowbuf + ((long long)(e * 3) * C + c) * Wr + x4 * 4;
+          const long long cs = (long long)C * Wr;
+          split_store4(q, q + hl_stride, m.x, m.y, m.z, m.w);
+          split_store4(q + cs, q + cs + hl_stride, m.y, m.z, m.w, n0);
+          split_store4(q + 2 * cs, q + 2 * cs + hl_stride, m.z, m.w, n0, n1);
+        }
+      }
     }
   }
 }
@@ -416,11 +460,14 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
   const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && img % 4 == 0;
   ProfScope prof(kProfStage, stream);
   if (g.mode == kModeAutocorr) {
-    if (aligned && g.W % 4 == 0 && g.Ws == g.W + 4) {
-      long long n = (long long)g.C * g.Hs * (g.Ws / 4);
+    float* rowbuf = stage + ac_rowbuf_off(g);
+    if (aligned && g.W % 4 == 0 && (g.tiled || g.Ws == g.W + 4)) {
+      long long n = g.tiled ? (long long)ac_cblocks(g) * 128 * g.Hs * (ac_strips(g) * 8)
+                            : (long long)g.C * g.Hs * (g.Ws / 4);
       int blocks = (int)((n + 255) / 256);
       if (blocks > 148 * 16) blocks = 148 * 16;
-      stage_autocorr_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl);
+      stage_autocorr_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, g.C, g.H, g.W, B, hl,
+                                                              g.tiled, rowbuf);
     } else {
       const float* src = x;
       int Bg = B;
@@ -433,10 +480,12 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
         src = mean_scratch;
         Bg = 1;
       }
-      long long n = (long long)g.C * g.Hs * g.Ws * 3;
+      long long n = g.tiled ? 3LL * ac_cblocks(g) * 128 * g.Hs * ac_strips(g) * 32
+                            : (long long)g.C * g.Hs * g.Ws * 3;
       int blocks = (int)((n + 255) / 256);
       if (blocks > 148 * 32) blocks = 148 * 32;
-      stage_autocorr_kernel<<<blocks, 256, 0, stream>>>(src, stage, g.C, g.H, g.W, g.Hs, g.Ws, Bg, hl);
+      stage_autocorr_kernel<<<blocks, 256, 0, stream>>>(src, stage, g.C, g.H, g.W, g.Hs, g.Ws, Bg,
+                                                       hl, g.tiled, rowbuf);
     }
     NSGP_LAUNCHED();
     const int Hc = ac_col_pitch(g);

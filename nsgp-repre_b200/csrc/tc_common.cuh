@@ -216,27 +216,29 @@ __device__ __forceinline__ void tc_mma_kblock_3xtf32(uint32_t d_main, uint32_t d
       "setp.ne.b32 pf, %7, 0;\n\t"            // accumulate into d_main at K step 0?
       "setp.eq.b32 pc, %8, 1;\n\t"            // same accumulator: corr never overwrites
       "or.pred pc, pc, pf;\n\t"
-      ".reg .pred ps;\n\t"                    // bring-up: same_acc == 2 skips the hi*lo product
-      "setp.ne.b32 ps, %8, 2;\n\t"
+      ".reg .pred ps, pq;\n\t"                // bring-up: same_acc == 2 skips the hi*lo product,
+      "setp.lt.u32 ps, %8, 2;\n\t"            //           same_acc == 3 both cross products
       "and.pred ps, ps, pe;\n\t"
+      "setp.ne.b32 pq, %8, 3;\n\t"
+      "and.pred pq, pq, pe;\n\t"
       // K step 0
       "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %4, %6, pf;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pc;\n\t"
+      "@pq tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, pc;\n\t"
       "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, pt;\n\t"
       // K step 1
       "add.u64 ah, %2, 2; add.u64 al, %3, 2; add.u64 bh, %4, 2; add.u64 bl, %5, 2;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@pq tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
       "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
       // K step 2
       "add.u64 ah, %2, 4; add.u64 al, %3, 4; add.u64 bh, %4, 4; add.u64 bl, %5, 4;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@pq tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
       "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
       // K step 3
       "add.u64 ah, %2, 6; add.u64 al, %3, 6; add.u64 bh, %4, 6; add.u64 bl, %5, 6;\n\t"
       "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %6, pt;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
+      "@pq tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, pt;\n\t"
       "@ps tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, pt;\n\t"
       "}" ::"r"(d_main),
       "r"(d_corr), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(first),

@@ -44,3 +44,13 @@ if os.environ.get("NSGP_DBG_COUNTERS"):
           (tot, c[:, 0].mean(), 100 * c[:, 0].mean() / tot, c[:, 1].mean(), 100 * c[:, 1].mean() / tot,
            c[:, 2].mean(), 100 * c[:, 2].mean() / tot, c[:, 3].mean(), 100 * c[:, 3].mean() / tot,
            c[:, 4].mean(), 100 * c[:, 4].mean() / tot, c[:, 6].mean(), tot / max(1, c[:, 6].mean())))
+if os.environ.get("NSGP_DBG_COUNTERS"):
+    buf = (ctypes.c_ulonglong * n)()
+    _lib.check(_lib.lib.nsgp_debug_read_counters(buf, -n), "counters")
+    c = np.array(list(buf), dtype=np.float64).reshape(148, 8)
+    tot = c[:, 7].mean()
+    if tot > 0:
+        st = max(1.0, c[:, 4].mean())
+        print("AC kernel per-CTA mean cycles: total %.0f, %.0f row steps -> %.0f cycles/step (MMA ideal 2304) | MMA warp: wait-A %.0f%% wait-B %.0f%% wait-epilogue %.0f%% issue %.0f%% | producer: wait-B-slot %.0f%% wait-A-slot %.0f%%" %
+              (tot, st, tot / st, 100 * c[:, 0].mean() / tot, 100 * c[:, 1].mean() / tot, 100 * c[:, 2].mean() / tot,
+               100 * c[:, 3].mean() / tot, 100 * c[:, 5].mean() / tot, 100 * c[:, 6].mean() / tot))
