@@ -285,6 +285,10 @@ int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int ro
                          int depth, unsigned long long* out_dev /* device */, int n_ctas,
                          void* stream);
 
+/* bring-up: n_ctas blocks of `threads` threads holding `smem` bytes of shared memory for
+ * `cycles` SM clocks, no memory traffic (co-residency probe, scripts/overlap_probe.py) */
+int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, void* stream);
+
 /* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
 

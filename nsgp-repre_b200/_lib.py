@@ -111,6 +111,7 @@ SIGNATURES = {
     "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                                      c_int, c_void_p]),
+    "nsgp_debug_occupy": (c_int, [c_int, c_size_t, C.c_longlong, c_int, c_void_p]),
     "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
 }

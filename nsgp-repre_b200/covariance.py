@@ -117,7 +117,11 @@ class CovarianceHooks:
     # ------------------------------------------------------------- side stream
     def _side_stream(self, device):
         if self._side is None or self._side.device != device:
-            self._side = torch.cuda.Stream(device=device)
+            # high priority: the persistent contraction kernel gets its CTAs placed as soon
+            # as blocks of the staging kernels (caller's stream) retire
+            import os
+            prio = -1 if os.environ.get("NSGP_SIDE_PRIO", "1") != "0" else 0
+            self._side = torch.cuda.Stream(device=device, priority=prio)
         return self._side
 
     def _ring_slot(self, nbytes: int, device):

@@ -825,6 +825,12 @@ int nsgp_debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_
   return debug_mma_rate(mode, iters, out_dev, n_ctas, (cudaStream_t)stream_);
 }
 
+int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, void* stream_) {
+  NSGP_REQUIRE(threads > 0 && threads <= 1024 && n_ctas > 0 && smem <= 227 * 1024,
+               "debug_occupy: bad arguments");
+  return debug_occupy(threads, smem, cycles, n_ctas, (cudaStream_t)stream_);
+}
+
 int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
                          int depth, unsigned long long* out_dev, int n_ctas, void* stream_) {
   NSGP_REQUIRE(base && out_dev, "tma_probe: null pointer");

@@ -33,7 +33,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int SA = 3;                       // A ring stages
+constexpr int SA = 3;                       // A ring stages (upper bound; run-time value `sa`)
 constexpr int SB = 4;                       // B ring stages (3 in the window + 1 in flight)
 constexpr uint32_t kPlane = BM * BK * 4;    // 16 KB: one hi or lo plane of a tile
 constexpr uint32_t kTile = 2 * kPlane;      // hi | lo
@@ -80,13 +80,13 @@ __device__ unsigned long long g_ac_counters[160 * 8];
 
 __global__ void __launch_bounds__(kThreadsAc, 1)
 autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict__ items,
-                   int n_items, int dbg) {
+                   int n_items, int dbg, int sa_n) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;                          // SA tiles
-  uint8_t* b_ring = smem + SA * kTile;             // SB tiles
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + (SA + SB) * kTile);
+  uint8_t* b_ring = smem + sa_n * kTile;           // SB tiles
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + (sa_n + SB) * kTile);
   uint64_t* a_empty = a_full + SA;
   uint64_t* b_full = a_empty + SA;
   uint64_t* b_empty = b_full + SB;
@@ -150,7 +150,7 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
       } else {
         const long long tile0 = ((long long)(sa * p.tiles + it.rb) * p.Hs + it.u0) * p.NS + st;
         for (int j = 0; j < n; ++j) {
-          const uint32_t s = cnt % SA, par = (cnt / SA) & 1;
+          const uint32_t s = cnt % sa_n, par = (cnt / sa_n) & 1;
           long long q0 = dbg ? clock64() : 0;
           mbar_wait_warp(&a_empty[s], par ^ 1, lane);
           if (dbg) c1 += clock64() - q0;
@@ -189,7 +189,7 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
         mbar_wait_warp(&b_full[c % SB], (c / SB) & 1, lane);
       }
       for (int j = 0; j < n; ++j) {
-        const uint32_t as = a_cnt % SA, ap = (a_cnt / SA) & 1;
+        const uint32_t as = a_cnt % sa_n, ap = (a_cnt / sa_n) & 1;
         const uint32_t b2 = b_cnt + 2;
         long long q1 = dbg ? clock64() : 0;
         mbar_wait_warp(&a_full[as], ap, lane);
@@ -410,6 +410,14 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
 
 int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream) {
   if (sg.n_items == 0) return 0;
+  // A-ring depth: 3 stages fill the SM; NSGP_AC_SA=2 (192 KB of ring) leaves ~34 KB for the
+  // L1 of co-resident staging kernels - measured equal end to end (scripts/overlap_probe.py:
+  // what the staging kernels lose next to this kernel is L1 capacity for loads in flight)
+  static const int sa_n = [] {
+    const char* e = getenv("NSGP_AC_SA");
+    return (e && e[0] == '2') ? 2 : 3;
+  }();
+  const size_t smem_bytes = (size_t)(sa_n + SB) * kTile + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     NSGP_CHECK_CUDA(cudaFuncSetAttribute(autocorr_tc_kernel,
@@ -422,7 +430,7 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   const int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
   ProfScope prof(kProfGram, stream);
   static const int dbg = getenv("NSGP_DBG_COUNTERS") ? 1 : 0;
-  autocorr_tc_kernel<<<grid, kThreadsAc, kSmemAc, stream>>>(probs, items, sg.n_items, dbg);
+  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n);
   NSGP_LAUNCHED();
   return 0;
 }

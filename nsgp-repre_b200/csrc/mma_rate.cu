@@ -148,6 +148,25 @@ int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, i
   return 0;
 }
 
+// Holds `threads` threads and `smem` bytes of shared memory on every SM for `cycles`
+// clocks without touching memory: separates the occupancy / L1-carve-out cost that a
+// persistent contraction kernel imposes on co-running HBM-bound kernels from the
+// bandwidth contention (scripts/overlap_probe.py).
+__global__ void occupy_kernel(long long cycles, int has_smem) {
+  extern __shared__ uint8_t occ_smem[];
+  if (has_smem && threadIdx.x == 0) occ_smem[0] = 1;
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) __nanosleep(200);
+}
+
+int debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, cudaStream_t stream) {
+  NSGP_CHECK_CUDA(cudaFuncSetAttribute(occupy_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+  occupy_kernel<<<n_ctas, threads, smem, stream>>>(cycles, smem > 0 ? 1 : 0);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
 int debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_ctas,
                    cudaStream_t stream) {
   const size_t smem = 6 * 16384 + 1024;

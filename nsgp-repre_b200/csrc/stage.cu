@@ -451,8 +451,36 @@ stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stag
   }
 }
 
+// The staging kernels use no shared memory, but the persistent contraction kernels they
+// overlap with need the maximum carve-out: an SM only changes its L1/shared split when it
+// is idle, so a staging kernel with the default (L1-heavy) preference keeps the
+// contraction CTAs waiting until whole SMs drain.  Ask for the same split everywhere.
+static void stage_prefer_shared_carveout() {
+  static const bool once = [] {
+    // measured: slower on its own (5.6 -> 6.1 ms per covariance pass) and no better when
+    // overlapped (5.0 -> 5.2 ms), so it is opt-in
+    const char* e = getenv("NSGP_STAGE_CARVEOUT");
+    if (!(e && e[0] == '1')) return true;
+    const int co = cudaSharedmemCarveoutMaxShared;
+#define NSGP_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
+    NSGP_CARVE(stage_conv_kernel);
+    NSGP_CARVE(stage_flat_vec_kernel<8>);
+    NSGP_CARVE(batch_mean_vec_kernel<8>);
+    NSGP_CARVE(stage_3x3s1_vec_kernel<8>);
+    NSGP_CARVE(stage_autocorr_kernel);
+    NSGP_CARVE(stage_autocorr_vec_kernel<8>);
+    NSGP_CARVE(stage_autocorr_edges_kernel);
+    NSGP_CARVE(stage_conv_explicit_kernel);
+#undef NSGP_CARVE
+    cudaGetLastError();
+    return true;
+  }();
+  (void)once;
+}
+
 int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
                       float* mean_scratch, cudaStream_t stream) {
+  stage_prefer_shared_carveout();
   long long total = (g.mode == kModeExplicit) ? (long long)g.Cs * g.Ws
                                               : (long long)g.Cs * g.Hs * g.Ws * g.ncopy;
   long long hl = stage_hl_stride(g);

@@ -23,16 +23,18 @@ def run(mode, join_each):
     for _ in range(2):
         one()
     hooks.join(); torch.cuda.synchronize()
-    _lib.profile_read(); _lib.profile_enable(True)
+    _lib.profile_read(); _lib.profile_enable(os.environ.get("NOPROF") is None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     t0 = time.perf_counter()
     e0.record()
     for _ in range(reps):
         one()
+    issue = (time.perf_counter() - t0) / reps * 1e3
     hooks.join()
     e1.record(); torch.cuda.synchronize()
     host = (time.perf_counter() - t0) / reps * 1e3
+    print("host issue time per pass: %.2f ms" % issue)
     _lib.profile_enable(False)
     prof = _lib.profile_read()
     ms = e0.elapsed_time(e1) / reps
@@ -40,6 +42,7 @@ def run(mode, join_each):
           (mode, join_each, ms, host, flops / ms / 1e9, prof["gram"][0] / reps, prof["gram"][1] / reps,
            prof["stage"][0] / reps))
 
-for mode in ("immediate", "overlap", "grouped"):
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ("immediate", "overlap", "grouped")
+for mode in modes:
     for je in (1, 0):
         run(mode, je)
