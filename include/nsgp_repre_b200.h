@@ -209,6 +209,24 @@ int nsgp_cov_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs,
                          nsgp_group_t* group /* host, out */, void* stream);
 int nsgp_group_launch(const void* table_dev, const nsgp_group_t* group /* host */, void* stream);
 
+/* Deferred staging (a1): the layer inputs of a whole forward (the jobs' `workspace`s are the
+ * per-layer staged operands, as for nsgp_cov_conv2d_stage) staged by ONE launch - two when a
+ * gather layout first needs the batch mean - instead of 1-3 short launches per layer.  The
+ * table is built once per set of layer geometries and batch size B; every launch takes the
+ * current input pointers xs[n_jobs] (host array of 16-byte aligned device pointers, each a
+ * contiguous (B,Cin,H,W) fp32 tensor that must not change until the launch has run). */
+typedef struct {
+  int n_jobs, B;
+  int n_items[2];
+  size_t off_jobs, off_items[2], off_xs, bytes;
+} nsgp_stage_group_t;
+size_t nsgp_cov_stage_group_bytes(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B);
+int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B,
+                               void* table_dev /* 64-byte aligned */, size_t table_bytes,
+                               nsgp_stage_group_t* out /* host */, void* stream);
+int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg /* host */,
+                                const void* const* xs /* host */, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * a9/a10/a11  RePRE prototypes
  *   replaces the prototype build of StandardMultiPrototypeReplayHead.__init__
@@ -284,6 +302,13 @@ int nsgp_debug_mma_rate(int mode, int iters, unsigned long long* out_dev /* devi
 int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
                          int depth, unsigned long long* out_dev /* device */, int n_ctas,
                          void* stream);
+
+/* bring-up: with NSGP_TIMELINE=1 in the environment the grouped staging kernel (kind 2) and
+ * the two covariance contraction kernels (kind 0 generic, kind 10 sliding-window) record
+ * {first block start, last block end} in globaltimer ns per launch; returns the number of
+ * launches copied to out[2*i], out[2*i+1], kinds[i] and resets the log */
+int nsgp_debug_timeline_read(unsigned long long* out /* host */, int* kinds /* host */,
+                             int max_slots);
 
 /* bring-up: n_ctas blocks of `threads` threads holding `smem` bytes of shared memory for
  * `cycles` SM clocks, no memory traffic (co-residency probe, scripts/overlap_probe.py) */

@@ -47,6 +47,11 @@ class SgdPlan(C.Structure):
                 ("t_elems", c_size_t), ("bytes", c_size_t)]
 
 
+class StageGroup(C.Structure):
+    _fields_ = [("n_jobs", c_int), ("B", c_int), ("n_items", c_int * 2), ("off_jobs", c_size_t),
+                ("off_items", c_size_t * 2), ("off_xs", c_size_t), ("bytes", c_size_t)]
+
+
 class CovJob(C.Structure):
     _fields_ = [("Cin", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
                 ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int),
@@ -88,6 +93,11 @@ SIGNATURES = {
     "nsgp_cov_group_bytes": (c_size_t, [C.POINTER(CovJob), c_int]),
     "nsgp_cov_group_build": (c_int, [C.POINTER(CovJob), c_int, c_void_p, c_size_t,
                                      C.POINTER(Group), c_void_p]),
+    "nsgp_cov_stage_group_bytes": (c_size_t, [C.POINTER(CovJob), c_int, c_int]),
+    "nsgp_cov_stage_group_build": (c_int, [C.POINTER(CovJob), c_int, c_int, c_void_p, c_size_t,
+                                           C.POINTER(StageGroup), c_void_p]),
+    "nsgp_cov_stage_group_launch": (c_int, [c_void_p, C.POINTER(StageGroup),
+                                            C.POINTER(c_void_p), c_void_p]),
     "nsgp_group_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p]),
     "repre_class_index": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
@@ -111,6 +121,7 @@ SIGNATURES = {
     "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                                      c_int, c_void_p]),
+    "nsgp_debug_timeline_read": (c_int, [C.POINTER(C.c_ulonglong), C.POINTER(c_int), c_int]),
     "nsgp_debug_occupy": (c_int, [c_int, c_size_t, C.c_longlong, c_int, c_void_p]),
     "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, check, ptr, CovLayout, CovJob, Group
+from ._lib import lib, check, ptr, CovLayout, CovJob, Group, StageGroup
 
 
 class _LayerAcc:
@@ -48,6 +48,11 @@ class _JobSet:
         self.table = None
         self.group = None
         self.done = None        # event: the grouped launch has finished reading the set
+        self.xs = []            # deferred mode: input tensor of job i (None for an alias)
+        self.versions = []      # ... and its version counter when the hook saw it
+        self.stage_sig = None   # (unique job indices, B) the staging table was built for
+        self.stage_table = None
+        self.stage_group = None
 
 
 class CovarianceHooks:
@@ -62,9 +67,17 @@ class CovarianceHooks:
     DEFAULT_IGNORE = ["roi_head.bbox_head.fc_cls", "roi_head.bbox_head.fc_reg", "teacher"]
 
     def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
-                 mode="grouped", ring=3):
+                 mode="deferred", ring=3):
         """``mode``
-        * ``"grouped"`` (default): every hook call only STAGES its layer (HBM-bound) into
+        * ``"deferred"`` (default): a hook call only records its layer input; at the end of
+          the forward (``flush``) ONE grouped staging launch (two when a gather layout needs
+          the batch mean first) stages all recorded inputs on a staging stream and ONE
+          persistent tcgen05 launch contracts them on a side stream - ~3 launches per
+          forward instead of ~90 short ones.  The recorded inputs are kept alive until the
+          set is reused and must not be modified in place between the hook and the end of
+          the forward (checked through the tensors' version counters; mmdet's R50-FPN,
+          RPN and RoI heads satisfy this - use ``"grouped"`` for models that do not).
+        * ``"grouped"``: every hook call only STAGES its layer (HBM-bound) into
           that layer's own workspace on the caller's stream; at the end of the forward
           (``flush``) the Gram updates of all staged layers run as ONE persistent
           tcgen05 launch on a side stream, overlapping the next forward.  Two workspace
@@ -74,8 +87,8 @@ class CovarianceHooks:
         * ``"immediate"``: stage + contract back to back on the caller's stream.
         Every result access joins the side stream first."""
         self.model = model
-        if mode not in ("grouped", "overlap", "immediate"):
-            raise ValueError("mode must be 'grouped', 'overlap' or 'immediate'")
+        if mode not in ("deferred", "grouped", "overlap", "immediate"):
+            raise ValueError("mode must be 'deferred', 'grouped', 'overlap' or 'immediate'")
         self.mode = mode
         self._sets = [_JobSet(), _JobSet()]
         self._cur = 0
@@ -142,8 +155,13 @@ class CovarianceHooks:
         js = self._sets[self._cur]
         dev = x.device
         main = torch.cuda.current_stream(dev)
-        if js.pos == 0 and js.done is not None:
-            main.wait_event(js.done)          # the set's previous launch must be finished
+        deferred = self.mode == "deferred"
+        if js.pos == 0:
+            if js.done is not None:
+                main.wait_event(js.done)      # the set's previous launch must be finished
+            js.keep.clear()                   # ... and only then may its inputs be recycled
+            js.xs = []
+            js.versions = []
         # the same tensor with the same geometry earlier in this forward (e.g. the stage
         # output that feeds both layerN.0.conv1 and the FPN lateral conv): stage it once
         ident = (x.data_ptr(), x._version, tuple(x.shape), geom, B)
@@ -160,10 +178,13 @@ class CovarianceHooks:
             js.jobs.append([key, geom, ws, la, src])
             js.sig = None
         if src is None:
-            check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(),
-                                            main.cuda_stream), "nsgp_cov_conv2d_stage")
+            if not deferred:
+                check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(),
+                                                main.cuda_stream), "nsgp_cov_conv2d_stage")
             js.seen[ident] = pos
             js.keep.append(x)                 # keeps the storage (and its address) alive
+        js.xs.append(x if src is None else None)
+        js.versions.append((x._version, B))
         js.pos += 1
         la.calls += 1
 
@@ -175,13 +196,21 @@ class CovarianceHooks:
             return
         del js.jobs[js.pos:]
         js.seen.clear()
-        js.keep.clear()
         dev = js.jobs[0][2].device
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev)
         staged = torch.cuda.Event()
         staged.record(main)
-        side.wait_event(staged)
+        side.wait_event(staged)               # the inputs exist / are staged
+        if self.mode == "deferred":
+            # staging and contraction back to back on the side stream: measured
+            # (scripts/bench_cov.py, NSGP_TIMELINE=1) the two do not gain from running
+            # concurrently - next to the HBM-bound staging kernel the operand-delivery-bound
+            # contraction kernels run 1.5-3x slower - so they are serialised and the
+            # caller's stream stays free for the rest of the step
+            self._stage_deferred(js, side)
+        else:
+            js.keep.clear()
         if js.sig is None:
             n = len(js.jobs)
             arr = (CovJob * n)()
@@ -209,6 +238,56 @@ class CovarianceHooks:
         js.pos = 0
         self._cur ^= 1
         self._pending = True
+
+    def _stage_deferred(self, js, stream):
+        """Stage every recorded input of the set: one grouped launch (per-layer launches when
+        the inputs are not uniformly batched / 16-byte aligned)."""
+        import ctypes
+        uniq = [i for i, x in enumerate(js.xs) if x is not None]
+        for i in uniq:
+            if js.xs[i]._version != js.versions[i][0]:
+                raise _lib.NsgpError(
+                    "input of %s was modified in place after its forward hook ran; "
+                    "CovarianceHooks(mode='deferred') stages at the end of the forward - "
+                    "use mode='grouped' for this model" % js.jobs[i][0])
+        Bs = {js.versions[i][1] for i in uniq}
+        ok = len(Bs) == 1 and all(js.xs[i].data_ptr() % 16 == 0 for i in uniq)
+        if not ok:
+            for i in uniq:
+                key, geom, ws, la, _ = js.jobs[i]
+                check(lib.nsgp_cov_conv2d_stage(ptr(js.xs[i]), js.versions[i][1], *geom, ptr(ws),
+                                                ws.numel(), stream.cuda_stream),
+                      "nsgp_cov_conv2d_stage")
+            return
+        B = Bs.pop()
+        sig = (tuple(uniq), B, tuple((js.jobs[i][1], js.jobs[i][2].data_ptr()) for i in uniq))
+        if js.stage_sig != sig:
+            n = len(uniq)
+            arr = (CovJob * n)()
+            for k, i in enumerate(uniq):
+                key, geom, ws, la, _ = js.jobs[i]
+                j = arr[k]
+                (j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw) = geom
+                j.acc, j.workspace, j.workspace_bytes = la.acc.data_ptr(), ws.data_ptr(), ws.numel()
+            need = int(lib.nsgp_cov_stage_group_bytes(arr, n, B))
+            if need == 0:
+                raise _lib.NsgpError("nsgp_cov_stage_group_bytes failed: %s" %
+                                     lib.nsgp_last_error().decode("utf-8", "replace"))
+            dev = js.jobs[0][2].device
+            if js.stage_table is None or js.stage_table.numel() < need or \
+                    js.stage_table.device != dev:
+                js.stage_table = torch.empty(need, dtype=torch.uint8, device=dev)
+            js.stage_group = StageGroup()
+            check(lib.nsgp_cov_stage_group_build(arr, n, B, ptr(js.stage_table),
+                                                 js.stage_table.numel(),
+                                                 ctypes.byref(js.stage_group),
+                                                 stream.cuda_stream),
+                  "nsgp_cov_stage_group_build")
+            js.stage_sig = sig
+        xs = (ctypes.c_void_p * len(uniq))(*[js.xs[i].data_ptr() for i in uniq])
+        check(lib.nsgp_cov_stage_group_launch(ptr(js.stage_table), ctypes.byref(js.stage_group),
+                                              xs, stream.cuda_stream),
+              "nsgp_cov_stage_group_launch")
 
     def join(self):
         """Make the current stream wait for every contraction issued on the side stream."""
@@ -263,9 +342,9 @@ class CovarianceHooks:
               "nsgp_cov_conv2d_layout")
         la = self._layer(key, layout, x.device)
         mode = self.mode
-        if mode == "grouped" and lib.nsgp_get_engine() != 0:
+        if mode in ("grouped", "deferred") and lib.nsgp_get_engine() != 0:
             mode = "overlap"            # the bring-up engine has no grouped launch
-        if mode == "grouped":
+        if mode in ("grouped", "deferred"):
             self._stage_job(x, key, (Cin, H, W, kh, kw, sh, sw, ph, pw), B, layout, la)
             return
         if mode == "immediate":

@@ -21,6 +21,24 @@ struct ProfRec { cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof[kProfKinds];
 cudaEvent_t g_prof_open[kProfKinds];
 }
+namespace {
+constexpr int kTlSlots = 512;
+unsigned long long* g_tl_dev = nullptr;
+int g_tl_n = 0;
+int g_tl_kind[kTlSlots];
+}
+unsigned long long* timeline_slot(int kind) {
+  static const bool on = getenv("NSGP_TIMELINE") != nullptr;
+  if (!on || g_tl_n >= kTlSlots) return nullptr;
+  if (g_tl_dev == nullptr) {
+    if (cudaMalloc(&g_tl_dev, kTlSlots * 2 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    std::vector<unsigned long long> init(kTlSlots * 2);
+    for (int i = 0; i < kTlSlots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+    cudaMemcpy(g_tl_dev, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  }
+  g_tl_kind[g_tl_n] = kind;
+  return g_tl_dev + 2 * (g_tl_n++);
+}
 void profile_begin(int kind, cudaStream_t s) {
   cudaEvent_t e;
   cudaEventCreate(&e);
@@ -609,6 +627,56 @@ int nsgp_group_launch(const void* table_dev, const nsgp_group_t* group, void* st
   return group_launch(table_dev, group_from_abi(*group), (cudaStream_t)stream_);
 }
 
+// ---- grouped staging: all layer inputs of a forward in one (two) launches ----------
+static float* job_mean_scratch(const nsgp_cov_job_t& j, const ConvGeom& g, float* stage) {
+  if (mean_scratch_elems(g) == 0) return nullptr;
+  char* m = align_up((char*)stage + stage_bytes(g) + layer_table_bytes(g), 256);
+  if (m + mean_scratch_elems(g) * sizeof(float) <= (const char*)j.workspace + j.workspace_bytes)
+    return reinterpret_cast<float*>(m);
+  return nullptr;
+}
+
+size_t nsgp_cov_stage_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs, int B) {
+  if (!jobs || n_jobs <= 0 || B <= 0) return 1024;
+  std::vector<ConvGeom> geoms;
+  std::vector<float*> stages, accs;
+  if (cov_jobs_setup(jobs, n_jobs, &geoms, &stages, &accs)) return 0;
+  return stage_group_bytes(geoms.data(), n_jobs, B) + 256;
+}
+
+int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs, int n_jobs, int B, void* table_dev,
+                               size_t table_bytes, nsgp_stage_group_t* out, void* stream_) {
+  NSGP_REQUIRE(jobs && table_dev && out && n_jobs > 0 && B > 0,
+               "cov_stage_group_build: bad arguments");
+  std::vector<ConvGeom> geoms;
+  std::vector<float*> stages, accs, means;
+  int rc = cov_jobs_setup(jobs, n_jobs, &geoms, &stages, &accs);
+  if (rc) return rc;
+  for (int i = 0; i < n_jobs; ++i) means.push_back(job_mean_scratch(jobs[i], geoms[i], stages[i]));
+  StageGroupInfo gi{};
+  rc = stage_group_build(geoms.data(), stages.data(), means.data(), n_jobs, B, table_dev,
+                         table_bytes, &gi, (cudaStream_t)stream_);
+  if (rc) return rc;
+  out->n_jobs = gi.n_jobs; out->B = gi.B;
+  out->n_items[0] = gi.n_items[0]; out->n_items[1] = gi.n_items[1];
+  out->off_jobs = gi.off_jobs;
+  out->off_items[0] = gi.off_items[0]; out->off_items[1] = gi.off_items[1];
+  out->off_xs = gi.off_xs; out->bytes = gi.bytes;
+  return 0;
+}
+
+int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg,
+                                const void* const* xs, void* stream_) {
+  NSGP_REQUIRE(table_dev && sg && xs, "cov_stage_group_launch: null pointer");
+  StageGroupInfo gi{};
+  gi.n_jobs = sg->n_jobs; gi.B = sg->B;
+  gi.n_items[0] = sg->n_items[0]; gi.n_items[1] = sg->n_items[1];
+  gi.off_jobs = sg->off_jobs;
+  gi.off_items[0] = sg->off_items[0]; gi.off_items[1] = sg->off_items[1];
+  gi.off_xs = sg->off_xs; gi.bytes = sg->bytes;
+  return stage_group_launch(table_dev, gi, xs, (cudaStream_t)stream_);
+}
+
 // ---------------------------------------------------------------- RePRE
 int repre_class_index(const int64_t* labels, int M, int C, int32_t* counts, int32_t* offsets,
                       int32_t* rows, void* stream_) {
@@ -823,6 +891,22 @@ int nsgp_debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_
                         void* stream_) {
   NSGP_REQUIRE(out_dev && iters > 0 && n_ctas > 0, "debug_mma_rate: bad arguments");
   return debug_mma_rate(mode, iters, out_dev, n_ctas, (cudaStream_t)stream_);
+}
+
+int nsgp_debug_timeline_read(unsigned long long* out, int* kinds, int max_slots) {
+  NSGP_REQUIRE(out && kinds && max_slots > 0, "timeline_read: bad arguments");
+  NSGP_CHECK_CUDA(cudaDeviceSynchronize());
+  const int n = g_tl_n < max_slots ? g_tl_n : max_slots;
+  if (n > 0) {
+    NSGP_CHECK_CUDA(cudaMemcpy(out, g_tl_dev, (size_t)n * 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) kinds[i] = g_tl_kind[i];
+    std::vector<unsigned long long> init(kTlSlots * 2);
+    for (int i = 0; i < kTlSlots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+    cudaMemcpy(g_tl_dev, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  }
+  g_tl_n = 0;
+  return n;
 }
 
 int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, void* stream_) {

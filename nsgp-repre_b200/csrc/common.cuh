@@ -43,6 +43,22 @@ extern unsigned long long g_launches;   // kernels launched by this library
 enum ProfKind : int { kProfGram = 0, kProfGemm = 1, kProfStage = 2, kProfSgd = 3,
                       kProfRepre = 4, kProfKinds = 5 };
 extern int g_profile;
+// bring-up timeline (NSGP_TIMELINE=1): every launch of an instrumented kernel gets a slot
+// {first block start, last block end} in globaltimer ns, read by nsgp_debug_timeline_read
+unsigned long long* timeline_slot(int kind);       // nullptr when disabled
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* tl) {
+  if (tl != nullptr && threadIdx.x == 0) atomicMin(tl, tl_now());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl) {
+  if (tl != nullptr && threadIdx.x == 0) atomicMax(tl + 1, tl_now());
+}
+#endif
 void profile_begin(int kind, cudaStream_t s);
 void profile_end(int kind, cudaStream_t s);
 struct ProfScope {

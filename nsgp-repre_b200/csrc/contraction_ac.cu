@@ -80,7 +80,7 @@ __device__ unsigned long long g_ac_counters[160 * 8];
 
 __global__ void __launch_bounds__(kThreadsAc, 1)
 autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict__ items,
-                   int n_items, int dbg, int sa_n) {
+                   int n_items, int dbg, int sa_n, unsigned long long* tl) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,6 +98,7 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   const int lane = threadIdx.x & 31;
   const long long t_start = clock64();
   long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  tl_begin(tl);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -280,6 +281,7 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
 
   tc_fence_before();
   __syncthreads();
+  tl_end(tl);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -430,7 +432,7 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   const int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
   ProfScope prof(kProfGram, stream);
   static const int dbg = getenv("NSGP_DBG_COUNTERS") ? 1 : 0;
-  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n);
+  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10));
   NSGP_LAUNCHED();
   return 0;
 }

@@ -113,7 +113,8 @@ template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constant__ TcParams pp,
                       const TcProblem* __restrict__ gprobs, const TcItem* __restrict__ gitems,
-                      int n_items, int prefetch_dist, int dbg) {
+                      int n_items, int prefetch_dist, int dbg,
+                      unsigned long long* tl) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -131,6 +132,7 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const long long t_start = clock64();
+  tl_begin(tl);
   long long c_wait = 0, c_issue = 0, c_acc = 0, c_kb = 0;
 
   if (warp == 0 && lane == 0) {
@@ -396,6 +398,7 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  tl_end(tl);
   if (PAIR) cluster_sync();          // the peer may still be reading this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
@@ -522,13 +525,15 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<true>, maps, p, gprobs, gitems,
-                                       n_items, prefetch_distance(), dbg_counters()));
+                                       n_items, prefetch_distance(), dbg_counters(),
+                                       (unsigned long long*)nullptr));
   } else {
     int rc = configure_kernel<false>();
     if (rc) return rc;
     const int grid = n_items < sm_count() ? n_items : sm_count();
     contraction_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(
-        maps, p, gprobs, gitems, n_items, prefetch_distance(), dbg_counters());
+        maps, p, gprobs, gitems, n_items, prefetch_distance(), dbg_counters(),
+        kind == kProfGram ? timeline_slot(0) : nullptr);
   }
   NSGP_LAUNCHED();
   return 0;

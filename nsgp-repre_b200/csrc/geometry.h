@@ -273,6 +273,35 @@ static inline size_t mean_scratch_elems(const ConvGeom& g) {
   if (vec_flat || vec_ac) return 0;
   return (size_t)round_up((long long)g.C * g.H * g.W, 4);
 }
+// grouped staging (stage.cu): all layer inputs of a forward in one or two launches
+enum StageKind : int {
+  kStFlatVec = 0, kStAcVec, kStAcEdges, kStMean, kStConv, kStExplicit, kStAcScalar, kSt3x3Vec
+};
+struct alignas(16) StageJobDev {
+  ConvGeom g;
+  float* stage;
+  float* mean;                 // batch-mean scratch of the two-pass layouts (or null)
+  long long hl;
+  long long rowbuf_off, colbuf_off, cornerbuf_off;
+  int Hc, pad;
+};
+struct alignas(16) StageItem {
+  int job;
+  short kind, from_mean;
+  long long lo, hi;
+  long long pad;
+};
+struct StageGroupInfo {
+  int n_jobs, B;
+  int n_items[2];
+  size_t off_jobs, off_items[2], off_xs, bytes;
+};
+size_t stage_group_bytes(const ConvGeom* geoms, int n, int B);
+int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
+                      int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
+                      cudaStream_t stream);
+int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
+                       cudaStream_t stream);
 int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,
                                  cudaStream_t s);
 int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,

@@ -1,5 +1,7 @@
 // Staging kernels: batch-mean + tf32 hi/lo split + layout for the contraction
 // engines.  All are HBM-bound element-wise/reduction kernels.
+#include <vector>
+
 #include "common.cuh"
 #include "geometry.h"
 
@@ -29,9 +31,12 @@ __device__ __forceinline__ void split_store4(float* hi, float* lo, float a, floa
   *reinterpret_cast<float4*>(lo) = l;
 }
 
-__global__ void __launch_bounds__(256)
-stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
-                  int B, long long hl_stride) {
+// Every staging routine is a __device__ body over an index span (first, step, end) so that
+// the same code runs as a stand-alone grid-stride kernel (per-layer entry points) and as
+// one work item of the grouped staging kernel (stage_group_kernel, end of this file).
+__device__ __forceinline__ void
+stage_conv_body(const float* __restrict__ x, float* __restrict__ stage, const ConvGeom& g,
+                int B, long long hl_stride, long long first, long long step, long long end) {
   // one thread per aligned group of 4 staged columns (Ws % 4 == 0): the row decode is
   // paid once per float4 and both planes are written with 128-bit stores
   const int W4 = g.Ws >> 2;
@@ -39,8 +44,8 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
   const long long img = (long long)g.C * g.H * g.W;
   const float fb = (float)B;
   const int HWout = g.Hout * g.Wout;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  if (end > total) end = total;
+  for (long long idx = first; idx < end; idx += step) {
     const int x4 = (int)(idx % W4);
     long long rest = idx / W4;
     const int r = (int)(rest % g.Hs);
@@ -83,18 +88,25 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
   }
 }
 
+__global__ void __launch_bounds__(256)
+stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGeom g,
+                  int B, long long hl_stride) {
+  stage_conv_body(x, stage, g, B, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, 1LL << 62);
+}
+
 // ---------------------------------------------------------------------------
 // Fast paths (same staged layout as stage_conv_kernel, 128-bit loads and stores).
 // ---------------------------------------------------------------------------
 // 1x1 stride-1 conv input with H*W % 4 == 0: the staged plane is the batch mean of
 // x itself.  One thread per float4.
 template <int B_UNROLL>
-__global__ void __launch_bounds__(256)
-stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, long long n4,
-                      int B, long long img, long long hl_stride) {
+__device__ __forceinline__ void
+stage_flat_vec_body(const float* __restrict__ x, float* __restrict__ stage, long long n4,
+                    int B, long long img, long long hl_stride, long long first, long long step,
+                    long long end) {
   const float inv_div = (float)B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
+  if (end > n4) end = n4;
+  for (long long i = first; i < end; i += step) {
     const float* p = x + i * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int b = 0;
@@ -114,16 +126,23 @@ stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, lo
   }
 }
 
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, long long n4,
+                      int B, long long img, long long hl_stride) {
+  stage_flat_vec_body<B_UNROLL>(x, stage, n4, B, img, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, n4);
+}
+
 // Batch mean of x (B, n) -> out (n), n % 4 == 0, 16-byte aligned: first pass of the
 // two-pass staging used by the layouts whose second pass is a gather (stride-2 tap
 // copies, odd widths, the explicit stem): the gather then reads 1/B of the data.
 template <int B_UNROLL>
-__global__ void __launch_bounds__(256)
-batch_mean_vec_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int B,
-                      long long img) {
+__device__ __forceinline__ void
+batch_mean_vec_body(const float* __restrict__ x, float* __restrict__ out, long long n4, int B,
+                    long long img, long long first, long long step, long long end) {
   const float fb = (float)B;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
+  if (end > n4) end = n4;
+  for (long long i = first; i < end; i += step) {
     const float* p = x + i * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int b = 0;
@@ -143,14 +162,22 @@ batch_mean_vec_kernel(const float* __restrict__ x, float* __restrict__ out, long
   }
 }
 
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+batch_mean_vec_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int B,
+                      long long img) {
+  batch_mean_vec_body<B_UNROLL>(x, out, n4, B, img, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, n4);
+}
+
 // 3x3 stride-1 pad-1 conv input with W % 4 == 0: each thread averages one aligned
 // float4 of the input row and writes it to the three column-shifted copies; the
 // +-1 neighbours come from the adjacent lanes (or one extra scalar load at the
 // warp / row edges).  Halo rows (r = 0, Hs-1) are written as zeros.
 template <int B_UNROLL>
-__global__ void __launch_bounds__(256)
-stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                       int W, int B, long long hl_stride) {
+__device__ __forceinline__ void
+stage_3x3s1_vec_body(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                     int W, int B, long long hl_stride, long long first, long long step,
+                     long long end) {
   const int W4 = W >> 2, Hs = H + 2;
   const long long total = (long long)C * Hs * W4;
   const long long img = (long long)C * H * W;
@@ -159,8 +186,8 @@ stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, i
   const int lane = threadIdx.x & 31;
   // every lane of a warp runs the same number of iterations (shuffles below)
   const long long total_r = (total + 31) / 32 * 32;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_r;
-       idx += (long long)gridDim.x * blockDim.x) {
+  if (end > total_r) end = total_r;
+  for (long long idx = first; idx < end; idx += step) {
     const bool live = idx < total;
     int x4 = 0, r = 0, c = 0;
     if (live) {
@@ -216,6 +243,13 @@ stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, i
   }
 }
 
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_3x3s1_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                       int W, int B, long long hl_stride) {
+  stage_3x3s1_vec_body<B_UNROLL>(x, stage, C, H, W, B, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, 1LL << 62);
+}
+
 // ---------------------------------------------------------------------------
 // Autocorrelation layout (3x3 s1 p1, geometry.h): three column-shifted copies of the
 // zero-extended batch mean, copy_s[c][r][x] = m~[c][r][x+s], r < H+2, x < Ws, plus the
@@ -229,10 +263,11 @@ __device__ __forceinline__ long long ac_tiled_off(int s, int c, int r, int xs, i
   return tile * 4096 + (long long)(c & 127) * 32 + (xs & 31);
 }
 
-__global__ void __launch_bounds__(256)
-stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                      int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
-                      float* __restrict__ rowbuf) {
+__device__ __forceinline__ void
+stage_autocorr_body(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                    int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
+                    float* __restrict__ rowbuf, long long first, long long step,
+                    long long end) {
   // plane layout: [3][C][Hs][Ws];  tiled layout: [3][CB*128][Hs][NS*32] tile-major, plus the
   // two edge rows of every copy in plain layout rowbuf[e][s][c][Wr]
   const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Wr = (W + 3) & ~3;
@@ -240,8 +275,8 @@ stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, in
   const long long total = 3LL * Cc * Hs * Wc;
   const long long img = (long long)C * H * W;
   const float fb = (float)B;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  if (end > total) end = total;
+  for (long long idx = first; idx < end; idx += step) {
     int xs = (int)(idx % Wc);
     long long rest = idx / Wc;
     int r = (int)(rest % Hs);
@@ -275,12 +310,20 @@ stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, in
   }
 }
 
+__global__ void __launch_bounds__(256)
+stage_autocorr_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                      int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
+                      float* __restrict__ rowbuf) {
+  stage_autocorr_body(x, stage, C, H, W, Hs, Ws, B, hl_stride, tiled, rowbuf, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, 1LL << 62);
+}
+
 // W % 4 == 0, 16-byte aligned input: one thread per aligned float4 of a staged row.
 template <int B_UNROLL>
-__global__ void __launch_bounds__(256)
-stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                          int W, int B, long long hl_stride, int tiled,
-                          float* __restrict__ rowbuf) {
+__device__ __forceinline__ void
+stage_autocorr_vec_body(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                        int W, int B, long long hl_stride, int tiled,
+                        float* __restrict__ rowbuf, long long first, long long step,
+                        long long end) {
   const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Wr = W;      // W % 4 == 0 here
   const int Hs = H + 2, Ws = tiled ? NS * 32 : W + 4, W4 = Ws >> 2;
   const int Cc = tiled ? CB * 128 : C;
@@ -290,8 +333,8 @@ stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage
   const float fb = (float)B;
   const int lane = threadIdx.x & 31;
   const long long total_r = (total + 31) / 32 * 32;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_r;
-       idx += (long long)gridDim.x * blockDim.x) {
+  if (end > total_r) end = total_r;
+  for (long long idx = first; idx < end; idx += step) {
     const bool live = idx < total;
     int x4 = 0, r = 0, c = 0;
     if (live) {
@@ -360,17 +403,26 @@ stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage
   }
 }
 
+template <int B_UNROLL>
+__global__ void __launch_bounds__(256)
+stage_autocorr_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                          int W, int B, long long hl_stride, int tiled,
+                          float* __restrict__ rowbuf) {
+  stage_autocorr_vec_body<B_UNROLL>(x, stage, C, H, W, B, hl_stride, tiled, rowbuf, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x,
+                                    1LL << 62);
+}
+
 // edge columns colbuf[side][shift][c][u] = m~[c][u+shift][side ? 0 : W-1] (pitch Hc) and
 // corner pixels cornerbuf[q][c][0] (pitch 4): q = 0 (H-1,W-1), 1 (H-1,0), 2 (0,W-1), 3 (0,0)
-__global__ void __launch_bounds__(256)
-stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ colbuf,
-                            float* __restrict__ cornerbuf, int C, int H, int W, int Hc, int B,
-                            long long hl_stride) {
+__device__ __forceinline__ void
+stage_autocorr_edges_body(const float* __restrict__ x, float* __restrict__ colbuf,
+                          float* __restrict__ cornerbuf, int C, int H, int W, int Hc, int B,
+                          long long hl_stride, long long first, long long step, long long end) {
   const long long n_col = 6LL * C * Hc, n_cor = 16LL * C;
   const long long img = (long long)C * H * W;
   const float fb = (float)B;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_col + n_cor;
-       idx += (long long)gridDim.x * blockDim.x) {
+  if (end > n_col + n_cor) end = n_col + n_cor;
+  for (long long idx = first; idx < end; idx += step) {
     int c, y, xx;
     bool valid;
     float* dst;
@@ -408,27 +460,38 @@ stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ col
   }
 }
 
+__global__ void __launch_bounds__(256)
+stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ colbuf,
+                            float* __restrict__ cornerbuf, int C, int H, int W, int Hc, int B,
+                            long long hl_stride) {
+  stage_autocorr_edges_body(x, colbuf, cornerbuf, C, H, W, Hc, B, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, 1LL << 62);
+}
+
 // ---------------------------------------------------------------------------
 // Explicit im2col fallback (any kernel size / dilation-free conv whose channel
 // count does not fit the implicit path, e.g. the 7x7 stem with Cin = 3).
 // Rows are written directly in the reference's (Cin, kh, kw) order.
 // stage[hl][row][k],  row < d, k < Hout*Wout, pitch Ws.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stage,
-                           ConvGeom g, int B, long long hl_stride) {
-  // blockIdx.y = im2col row (c, i, j) - uniform per block; threads over groups of 4 K columns
+__device__ __forceinline__ void
+stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
+                         const ConvGeom& g, int B, long long hl_stride, long long first,
+                         long long step, long long end) {
+  // index = (im2col row (c, i, j), group of 4 K columns)
   const long long img = (long long)g.C * g.H * g.W;
   const int taps = g.kh * g.kw;
   const int d = g.C * taps;
   const int K = g.Hout * g.Wout;
-  const int row = blockIdx.y;
-  const int c = row / taps, t = row - c * taps;
-  const int i = t / g.kw, j = t - i * g.kw;
-  const bool row_ok = row < d;
   const float fb = (float)B;
   const int W4 = g.Ws >> 2;
-  for (int k4 = blockIdx.x * blockDim.x + threadIdx.x; k4 < W4; k4 += gridDim.x * blockDim.x) {
+  const long long total = (long long)g.Cs * W4;
+  if (end > total) end = total;
+  for (long long idx = first; idx < end; idx += step) {
+    const int row = (int)(idx / W4);
+    const int k4 = (int)(idx - (long long)row * W4);
+    const int c = row / taps, t = row - c * taps;
+    const int i = t / g.kw, j = t - i * g.kw;
+    const bool row_ok = row < d;
     float v[4];
     int k = k4 * 4;
     int oy = k / g.Wout, ox = k - oy * g.Wout;
@@ -449,6 +512,14 @@ stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stag
     float* o = stage + (long long)row * g.Ws + k;
     split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
+}
+
+__global__ void __launch_bounds__(256)
+stage_conv_explicit_kernel(const float* __restrict__ x, float* __restrict__ stage,
+                           ConvGeom g, int B, long long hl_stride) {
+  stage_conv_explicit_body(x, stage, g, B, hl_stride,
+                           blockIdx.x * (long long)blockDim.x + threadIdx.x,
+                           (long long)gridDim.x * blockDim.x, 1LL << 62);
 }
 
 // The staging kernels use no shared memory, but the persistent contraction kernels they
@@ -553,9 +624,9 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
       Bg = 1;
     }
     if (g.mode == kModeExplicit) {
-      int bx = ceil_div(g.Ws / 4, 256);
-      if (bx > 64) bx = 64;
-      dim3 grid(bx, g.Cs);
+      long long ne = (long long)g.Cs * (g.Ws / 4);
+      int grid = (int)((ne + 255) / 256);
+      if (grid > 148 * 32) grid = 148 * 32;
       stage_conv_explicit_kernel<<<grid, 256, 0, stream>>>(src, stage, g, Bg, hl);
     } else {
       int blocks = (int)((total / 4 + 255) / 256);
@@ -565,6 +636,213 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
     }
   }
   NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Grouped staging: the layer inputs of a whole forward staged by ONE launch (two when a
+// gather layout reads the batch mean written by the first).  A layer's staging kernels
+// are short (34 MB of input takes ~10 us, of which half is launch ramp and tail) and
+// there are ~90 of them per forward; as work items of one persistent launch they stream
+// back to back.  Item = (job, routine, index range); phase 0 reads the layer inputs,
+// phase 1 reads the batch means phase 0 wrote.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restrict__ items,
+                   int n_items, const float* const* __restrict__ xs, int B,
+                   unsigned long long* tl) {
+  tl_begin(tl);
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const StageItem it = items[w];
+    const StageJobDev& j = jobs[it.job];
+    const ConvGeom& g = j.g;
+    const float* x = it.from_mean ? j.mean : xs[it.job];
+    const int Bx = it.from_mean ? 1 : B;
+    const long long first = it.lo + threadIdx.x, step = blockDim.x, end = it.hi;
+    const long long img = (long long)g.C * g.H * g.W;
+    switch (it.kind) {
+      case kStFlatVec:
+        stage_flat_vec_body<8>(x, j.stage, img / 4, Bx, img, j.hl, first, step, end);
+        break;
+      case kStAcVec:
+        stage_autocorr_vec_body<8>(x, j.stage, g.C, g.H, g.W, Bx, j.hl, g.tiled,
+                                   j.stage + j.rowbuf_off, first, step, end);
+        break;
+      case kStAcEdges:
+        stage_autocorr_edges_body(x, j.stage + j.colbuf_off, j.stage + j.cornerbuf_off, g.C,
+                                  g.H, g.W, j.Hc, Bx, j.hl, first, step, end);
+        break;
+      case kStMean:
+        batch_mean_vec_body<8>(x, j.mean, img / 4, Bx, img, first, step, end);
+        break;
+      case kStConv:
+        stage_conv_body(x, j.stage, g, Bx, j.hl, first, step, end);
+        break;
+      case kStExplicit:
+        stage_conv_explicit_body(x, j.stage, g, Bx, j.hl, first, step, end);
+        break;
+      case kStAcScalar:
+        stage_autocorr_body(x, j.stage, g.C, g.H, g.W, g.Hs, g.Ws, Bx, j.hl, g.tiled,
+                            j.stage + j.rowbuf_off, first, step, end);
+        break;
+      case kSt3x3Vec:
+        stage_3x3s1_vec_body<8>(x, j.stage, g.C, g.H, g.W, Bx, j.hl, first, step, end);
+        break;
+      default:
+        break;
+    }
+  }
+  tl_end(tl);
+}
+
+// Plans one layer: the same routine choice as launch_stage_conv (x assumed 16-byte aligned;
+// the caller checks).  Appends to items[phase] when items != nullptr, always counts.
+static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
+                           std::vector<StageItem>* items /* [2] or null */, size_t* counts) {
+  const long long img = (long long)g.C * g.H * g.W;
+  const bool aligned = img % 4 == 0;
+  auto add = [&](int phase, int kind, int from_mean, long long total, long long chunk) {
+    for (long long lo = 0; lo < total; lo += chunk) {
+      ++counts[phase];
+      if (items) {
+        StageItem it{};
+        it.job = job; it.kind = (short)kind; it.from_mean = (short)from_mean;
+        it.lo = lo; it.hi = lo + chunk < total ? lo + chunk : total;
+        items[phase].push_back(it);
+      }
+    }
+  };
+  const long long kVec = 2048, kScalar = 8192;
+  const bool two_pass_ok = B > 1 && aligned && have_mean;
+  if (g.mode == kModeAutocorr) {
+    if (aligned && g.W % 4 == 0 && (g.tiled || g.Ws == g.W + 4)) {
+      const long long n = g.tiled ? (long long)ac_cblocks(g) * 128 * g.Hs * (ac_strips(g) * 8)
+                                  : (long long)g.C * g.Hs * (g.Ws / 4);
+      add(0, kStAcVec, 0, round_up(n, 32), kVec);
+    } else {
+      const long long n = g.tiled ? 3LL * ac_cblocks(g) * 128 * g.Hs * ac_strips(g) * 32
+                                  : (long long)g.C * g.Hs * g.Ws * 3;
+      if (two_pass_ok) {
+        add(0, kStMean, 0, img / 4, kVec);
+        add(1, kStAcScalar, 1, n, kScalar);
+      } else {
+        add(0, kStAcScalar, 0, n, kScalar);
+      }
+    }
+    add(0, kStAcEdges, 0, 6LL * g.C * ac_col_pitch(g) + 16LL * g.C, kVec);
+    return;
+  }
+  if (g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && aligned && (g.H * g.W) % 4 == 0) {
+    add(0, kStFlatVec, 0, img / 4, kVec);
+    return;
+  }
+  if (g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 &&
+      g.pw == 1 && aligned && g.W % 4 == 0) {
+    add(0, kSt3x3Vec, 0, round_up((long long)g.C * g.Hs * (g.W / 4), 32), kVec);
+    return;
+  }
+  const bool sparse = g.mode == kModeFlat && g.sh * g.sw > 1;
+  const bool two = two_pass_ok && !sparse;
+  if (two) add(0, kStMean, 0, img / 4, kVec);
+  if (g.mode == kModeExplicit)
+    add(two ? 1 : 0, kStExplicit, two ? 1 : 0, (long long)g.Cs * (g.Ws / 4), kVec);
+  else
+    add(two ? 1 : 0, kStConv, two ? 1 : 0, (long long)g.Cs * g.Hs * g.ncopy * (g.Ws / 4), kVec);
+}
+
+namespace tc { int sm_count(); }
+using tc::sm_count;
+
+size_t stage_group_bytes(const ConvGeom* geoms, int n, int B) {
+  size_t counts[2] = {0, 0};
+  for (int i = 0; i < n; ++i) plan_stage_job(geoms[i], i, B, true, nullptr, counts);
+  return (size_t)n * sizeof(StageJobDev) + (counts[0] + counts[1]) * sizeof(StageItem) +
+         (size_t)n * sizeof(void*) + 1024;
+}
+
+int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
+                      int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
+                      cudaStream_t stream) {
+  NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
+               "stage group table must be 64-byte aligned");
+  std::vector<StageJobDev> jobs(n);
+  std::vector<StageItem> items[2];
+  size_t counts[2] = {0, 0};
+  for (int i = 0; i < n; ++i) {
+    const ConvGeom& g = geoms[i];
+    StageJobDev& j = jobs[i];
+    memset(&j, 0, sizeof(j));
+    j.g = g;
+    j.stage = stages[i];
+    j.mean = means[i];
+    j.hl = stage_hl_stride(g);
+    if (g.mode == kModeAutocorr) {
+      j.rowbuf_off = ac_rowbuf_off(g);
+      j.colbuf_off = ac_colbuf_off(g);
+      j.cornerbuf_off = ac_cornerbuf_off(g);
+      j.Hc = ac_col_pitch(g);
+    }
+    plan_stage_job(g, i, B, means[i] != nullptr, items, counts);
+  }
+  info->n_jobs = n;
+  info->B = B;
+  info->off_jobs = 0;
+  size_t off = round_up((long long)((size_t)n * sizeof(StageJobDev)), 64);
+  for (int ph = 0; ph < 2; ++ph) {
+    info->n_items[ph] = (int)items[ph].size();
+    info->off_items[ph] = off;
+    off = round_up((long long)(off + items[ph].size() * sizeof(StageItem)), 64);
+  }
+  info->off_xs = off;
+  off += (size_t)n * sizeof(void*);
+  info->bytes = off;
+  NSGP_REQUIRE(off <= table_bytes, "stage group table too small (%zu < %zu)", table_bytes, off);
+  char* t = (char*)table_dev;
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(t, jobs.data(), (size_t)n * sizeof(StageJobDev),
+                                  cudaMemcpyHostToDevice, stream));
+  for (int ph = 0; ph < 2; ++ph)
+    if (!items[ph].empty())
+      NSGP_CHECK_CUDA(cudaMemcpyAsync(t + info->off_items[ph], items[ph].data(),
+                                      items[ph].size() * sizeof(StageItem),
+                                      cudaMemcpyHostToDevice, stream));
+  return 0;
+}
+
+int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
+                       cudaStream_t stream) {
+  if (info.n_jobs == 0) return 0;
+  static const bool carve_once = [] {
+    const char* e = getenv("NSGP_STAGE_GROUP_CARVEOUT");
+    const int co = e ? atoi(e) : -1;
+    if (co >= 0)
+      cudaFuncSetAttribute(stage_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    return true;
+  }();
+  (void)carve_once;
+  const char* t = (const char*)table_dev;
+  for (int i = 0; i < info.n_jobs; ++i)
+    NSGP_REQUIRE(xs[i] && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0,
+                 "stage group: input %d must be a 16-byte aligned device pointer", i);
+  NSGP_CHECK_CUDA(cudaMemcpyAsync((void*)(t + info.off_xs), xs,
+                                  (size_t)info.n_jobs * sizeof(void*), cudaMemcpyHostToDevice,
+                                  stream));
+  ProfScope prof(kProfStage, stream);
+  for (int ph = 0; ph < 2; ++ph) {
+    if (info.n_items[ph] == 0) continue;
+    // blocks per SM: few enough that the persistent contraction CTA (224 threads, ~16 K
+    // registers) of the previous forward always finds room next to them
+    static const int per_sm = [] {
+      const char* e = getenv("NSGP_STAGE_BLOCKS_PER_SM");
+      const int v = e ? atoi(e) : 3;
+      return v > 0 && v <= 8 ? v : 3;
+    }();
+    int grid = info.n_items[ph] < sm_count() * per_sm ? info.n_items[ph] : sm_count() * per_sm;
+    stage_group_kernel<<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
+        reinterpret_cast<const StageItem*>(t + info.off_items[ph]), info.n_items[ph],
+        reinterpret_cast<const float* const*>(t + info.off_xs), info.B, timeline_slot(2));
+    NSGP_LAUNCHED();
+  }
   return 0;
 }
 

@@ -43,6 +43,38 @@ def run(mode, join_each):
            prof["stage"][0] / reps))
 
 modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ("immediate", "overlap", "grouped")
+def timeline():
+    if not os.environ.get("NSGP_TIMELINE"):
+        return
+    import ctypes
+    n = 512
+    buf = (ctypes.c_ulonglong * (2 * n))()
+    kinds = (ctypes.c_int * n)()
+    m = _lib.lib.nsgp_debug_timeline_read(buf, kinds, n)
+    ev = [(buf[2 * i], buf[2 * i + 1], kinds[i]) for i in range(m)]
+    ev = ev[-15:]
+    t0 = min(e[0] for e in ev)
+    names = {2: "stage", 0: "gram-generic", 10: "gram-autocorr"}
+    for a, b, k in sorted(ev):
+        print("   %-14s %8.3f -> %8.3f ms  (%.3f)" % (names.get(k, k), (a - t0) / 1e6, (b - t0) / 1e6, (b - a) / 1e6))
+
+def counters():
+    if not os.environ.get("NSGP_DBG_COUNTERS"):
+        return
+    import ctypes
+    import numpy as np
+    n = 148 * 8
+    buf = (ctypes.c_ulonglong * n)()
+    _lib.check(_lib.lib.nsgp_debug_read_counters(buf, -n), "counters")
+    c = np.array(list(buf), dtype=np.float64).reshape(148, 8)
+    tot = c[:, 7].mean()
+    st = max(1.0, c[:, 4].mean())
+    print("   AC kernel per-CTA cycles: mean %.0f max %.0f min %.0f (%.2f ms at 1.965 GHz), %.0f cycles/row step | MMA warp: wait-A %.0f%% wait-B %.0f%% wait-epi %.0f%% issue %.0f%%" %
+          (tot, c[:, 7].max(), c[:, 7].min(), tot / 1.965e6, tot / st, 100 * c[:, 0].mean() / tot, 100 * c[:, 1].mean() / tot,
+           100 * c[:, 2].mean() / tot, 100 * c[:, 3].mean() / tot))
+
 for mode in modes:
     for je in (1, 0):
         run(mode, je)
+        counters()
+        timeline()

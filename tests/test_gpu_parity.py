@@ -70,7 +70,8 @@ def test_contraction_gemm_3xtf32(pkg, engine, M, N, K):
 
 
 # ----------------------------------------------------------------------- covariance
-def test_covariance_toy_model_matches_reference_fixture(pkg, engine, golden_dir):
+@pytest.mark.parametrize("mode", ["deferred", "grouped", "immediate"])
+def test_covariance_toy_model_matches_reference_fixture(pkg, engine, golden_dir, mode):
     """Every conv geometry of R50-FPN at toy size, 3 batches, through the forward
     hooks, against the fixture produced by the reference's compute_cov/update_cov."""
     g = _load(golden_dir, "cov_toy.pt")
@@ -78,7 +79,9 @@ def test_covariance_toy_model_matches_reference_fixture(pkg, engine, golden_dir)
     net.load_state_dict(g["state_dict"])
     batches = synth.toy_batches(seed=g["seed"])
     net = net.cuda()
-    hooks = pkg.CovarianceHooks(net, add_default_ignores=False)
+    if engine != 0 and mode != "deferred":
+        pytest.skip("the bring-up engine has one host mode")
+    hooks = pkg.CovarianceHooks(net, add_default_ignores=False, mode=mode)
     fea = hooks.cal_fea_in([b.cuda() for b in batches])
     assert set(fea) == set(g["fea_in"])
     for k, ref in g["fea_in"].items():
@@ -104,12 +107,15 @@ GEOMS = [
 ]
 
 
+@pytest.mark.parametrize("mode", ["deferred", "grouped"])
 @pytest.mark.parametrize("Cin,H,W,k,s,p,B", GEOMS)
-def test_covariance_layer_geometries(pkg, engine, Cin, H, W, k, s, p, B):
+def test_covariance_layer_geometries(pkg, engine, Cin, H, W, k, s, p, B, mode):
+    if engine != 0 and mode != "deferred":
+        pytest.skip("the bring-up engine has one host mode")
     g = torch.Generator().manual_seed(Cin * 131 + H)
     conv = torch.nn.Conv2d(Cin, 4, k, stride=s, padding=p, bias=False).cuda()
     model = torch.nn.Sequential(conv)
-    hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+    hooks = pkg.CovarianceHooks(model, add_default_ignores=False, mode=mode).register()
     want = None
     for _ in range(2):
         x = torch.relu(torch.randn(B, Cin, H, W, generator=g))
@@ -121,6 +127,37 @@ def test_covariance_layer_geometries(pkg, engine, Cin, H, W, k, s, p, B):
     got = hooks.fea_in["0.weight"]
     assert got.shape == (Cin * k * k, Cin * k * k)
     assert rel_fro(got, want) < 2e-5
+
+
+def test_covariance_deferred_rejects_inplace_modification(pkg, engine):
+    """Deferred staging reads the layer input at the end of the forward: an in-place
+    write between the hook and the flush must be an error, never a wrong covariance."""
+    if engine != 0:
+        pytest.skip("grouped launches need the tcgen05 engine")
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(8, 4, 1, bias=False)
+
+        def forward(self, x):
+            y = self.conv(x)
+            x.mul_(2.0)
+            return y
+
+    net = Net().cuda()
+    x = torch.relu(torch.randn(2, 8, 6, 8)).cuda()
+    hooks = pkg.CovarianceHooks(net, add_default_ignores=False, mode="deferred").register()
+    with pytest.raises(pkg._lib.NsgpError, match="modified in place"):
+        with torch.no_grad():
+            net(x.clone())
+    hooks.remove()
+    hooks2 = pkg.CovarianceHooks(net, add_default_ignores=False, mode="grouped").register()
+    with torch.no_grad():
+        net(x.clone())
+    hooks2.remove()
+    want = O.cov_conv2d(x.cpu().double(), (1, 1), (1, 1), (0, 0))
+    assert rel_fro(hooks2.fea_in["conv.weight"], want) < 2e-5
 
 
 def test_covariance_long_k_chain(pkg, engine):
