@@ -288,6 +288,26 @@ int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int 
                         int64_t* labels, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Density ordering + greedy cover of every class (:421-448) and the table of prototype
+ * segments, all on the device.  Inputs as produced by repre_cosine_count_batched (masks and
+ * counts concatenated per class, rows_sel = the classes' rows); `saved`/`n_saved` replay the
+ * masks of mask.pth (:425-433; device bytes, n_saved[c] masks of sizes[c] bytes per class).
+ * Outputs (device): seg_off[n_classes*(max_picks+1)+1], seg_rows[sum sizes*(max_picks+1)],
+ * seg_label[n_classes*(max_picks+1)], info = [n_segments | picks per class | picks
+ * (row within the class, -2 = replayed mask)], n_classes*(max_picks+1)+1 ints. */
+size_t repre_greedy_segments_workspace_bytes(const int32_t* sizes /* host */, int n_classes,
+                                             int max_picks);
+int repre_greedy_segments(const uint8_t* masks, const int32_t* counts, const int32_t* rows_sel,
+                          const int32_t* sizes /* host */, const int32_t* class_ids /* host */,
+                          int n_classes, int max_picks, const uint8_t* saved,
+                          const int32_t* n_saved /* host */, int32_t* seg_off, int32_t* seg_rows,
+                          int32_t* seg_label, int32_t* info, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* repre_segment_mean over at most max_segments segments, the live count read on the device */
+int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
+                           int max_segments, const int32_t* n_segments_dev, int max_seg_rows,
+                           float* out, void* stream);
+
 /* bring-up: per-CTA wait/issue cycle counters of the last tcgen05 contraction launched
  * with NSGP_DBG_COUNTERS=1 in the environment (8 counters per CTA, host buffer) */
 int nsgp_debug_read_counters(unsigned long long* out /* host */, int n);

@@ -112,6 +112,13 @@ SIGNATURES = {
     "repre_cosine_count_batched": (c_int, [c_void_p, c_int, c_void_p, C.POINTER(C.c_int32), c_int,
                                            c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "repre_greedy_segments_workspace_bytes": (c_size_t, [C.POINTER(C.c_int32), c_int, c_int]),
+    "repre_greedy_segments": (c_int, [c_void_p, c_void_p, c_void_p, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), c_int, c_int, c_void_p,
+                                      C.POINTER(C.c_int32), c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "repre_segment_mean_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_int, c_void_p, c_void_p]),
     "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     C.c_uint64, c_void_p, c_void_p]),
     "repre_kmeans_assign_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

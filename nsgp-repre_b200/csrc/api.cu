@@ -739,23 +739,89 @@ int repre_cosine_count(const float* F, int D, const int32_t* rows, int n, float 
   return launch_threshold_count(S, n, ld, thresh, mask, counts, sim_out, stream);
 }
 
+// ---- density ordering + greedy cover + segment table on the device (:421-448) -------
+size_t repre_greedy_segments_workspace_bytes(const int32_t* sizes, int n_classes, int max_picks) {
+  if (!sizes || n_classes <= 0 || max_picks < 0) return 1024;
+  size_t n = 0;
+  for (int c = 0; c < n_classes; ++c) n += (size_t)sizes[c];
+  return (size_t)n_classes * sizeof(GreedyClass) + n * 4 + n + 64 +
+         (size_t)n_classes * (max_picks + 2) * 4 + 2048;
+}
+
+int repre_greedy_segments(const uint8_t* masks, const int32_t* counts, const int32_t* rows_sel,
+                          const int32_t* sizes, const int32_t* class_ids, int n_classes,
+                          int max_picks, const uint8_t* saved, const int32_t* n_saved,
+                          int32_t* seg_off, int32_t* seg_rows, int32_t* seg_label,
+                          int32_t* info, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(masks && counts && rows_sel && sizes && class_ids && seg_off && seg_rows &&
+                   seg_label && info && workspace,
+               "greedy_segments: null pointer");
+  NSGP_REQUIRE(n_classes > 0 && max_picks >= 0, "greedy_segments: bad sizes");
+  NSGP_REQUIRE(workspace_bytes >= repre_greedy_segments_workspace_bytes(sizes, n_classes, max_picks),
+               "greedy_segments: workspace too small");
+  std::vector<GreedyClass> h(n_classes);
+  long long moff = 0, soff = 0;
+  int roff = 0, max_n = 0;
+  for (int c = 0; c < n_classes; ++c) {
+    NSGP_REQUIRE(sizes[c] > 0, "greedy_segments: class %d has no rows", class_ids[c]);
+    GreedyClass& g = h[c];
+    g.mask_off = moff; g.saved_off = soff; g.row_off = roff; g.n = sizes[c];
+    g.n_saved = (saved && n_saved) ? n_saved[c] : 0;
+    NSGP_REQUIRE(g.n_saved >= 0 && g.n_saved <= max_picks, "greedy_segments: bad n_saved");
+    g.class_id = class_ids[c];
+    moff += (long long)sizes[c] * sizes[c];
+    soff += (long long)g.n_saved * sizes[c];
+    roff += sizes[c];
+    if (sizes[c] > max_n) max_n = sizes[c];
+  }
+  char* ws = align_up((char*)workspace, 256);
+  GreedyClass* cls_dev = reinterpret_cast<GreedyClass*>(ws);
+  int* order_ws = reinterpret_cast<int*>(align_up(ws + (size_t)n_classes * sizeof(GreedyClass), 16));
+  int* seg_sizes = order_ws + roff;
+  int* seg_base = seg_sizes + (size_t)n_classes * (max_picks + 1);
+  unsigned char* covered_ws = reinterpret_cast<unsigned char*>(seg_base + n_classes);
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(cls_dev, h.data(), (size_t)n_classes * sizeof(GreedyClass),
+                                  cudaMemcpyHostToDevice, stream));
+  // info: [0] = number of segments, [1 .. n_classes] = picks per class, then the picks
+  int* nseg = info;
+  int* npicks = info + 1;
+  int* picks = info + 1 + n_classes;
+  return launch_greedy_segments(cls_dev, n_classes, max_n, masks, counts, saved, rows_sel,
+                                max_picks, order_ws, covered_ws, seg_sizes, seg_base, picks,
+                                npicks, seg_off, seg_rows, seg_label, nseg, stream);
+}
+
+int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
+                           int max_segments, const int32_t* n_segments_dev, int max_seg_rows,
+                           float* out, void* stream_) {
+  NSGP_REQUIRE(F && seg_offsets && rows && out && n_segments_dev, "segment_mean_dev: null pointer");
+  return launch_segment_mean(F, D, seg_offsets, rows, max_segments, max_seg_rows, nullptr, 0, out,
+                             (cudaStream_t)stream_, n_segments_dev);
+}
+
 // ---- all classes at once: 1 normalise launch, 1 memset, 1 grouped Gram, 1 threshold launch
 static void batched_layout(const int32_t* sizes, int n_classes, int D, size_t* n_total,
                            size_t* s_elems, size_t* table_bytes) {
   size_t n = 0, s = 0;
+  // the tcgen05 engine wants >= 8 operand rows: a smaller class is contracted as 8 rows
+  // (the extra rows are the next class's or padding; only its own n x n block is read back)
   for (int c = 0; c < n_classes; ++c) {
+    const size_t ne = sizes[c] > 0 && sizes[c] < 8 ? 8 : (size_t)sizes[c];
     n += (size_t)sizes[c];
-    s += (size_t)sizes[c] * (size_t)round_up(sizes[c], 4);
+    s += ne * (size_t)round_up((long long)ne, 4);
   }
   *n_total = n;
   *s_elems = s;
   std::vector<ContractionArgs> probs;
   for (int c = 0; c < n_classes; ++c) {
     if (sizes[c] <= 0) continue;
+    const int ne = sizes[c] < 8 ? 8 : sizes[c];
     ContractionArgs a{};
-    a.A = matrix_operand(nullptr, nullptr, sizes[c], D, D);
+    a.A = matrix_operand(nullptr, nullptr, ne, D, D);
     a.B = a.A;
-    a.n_cols = sizes[c];
+    a.n_cols = ne;
     a.epi = kEpiGramAtomic;
     probs.push_back(a);
   }
@@ -766,7 +832,7 @@ size_t repre_cosine_count_batched_workspace_bytes(const int32_t* sizes, int n_cl
   if (!sizes || n_classes <= 0) return 1024;
   size_t n, s, tb;
   batched_layout(sizes, n_classes, D, &n, &s, &tb);
-  return 2 * (size_t)round_up((long long)n, 8) * D * 4 + s * 4 + tb +
+  return 2 * ((size_t)round_up((long long)n, 8) + 8) * D * 4 + s * 4 + tb +
          (size_t)n_classes * sizeof(ClassExtent) + 4096;
 }
 
@@ -785,29 +851,33 @@ int repre_cosine_count_batched(const float* F, int D, const int32_t* rows, const
   if (n_total == 0) return 0;
   char* ws = align_up((char*)workspace, 1024);
   float* hi = reinterpret_cast<float*>(ws);
-  float* lo = hi + (size_t)round_up((long long)n_total, 8) * D;
-  float* S = lo + (size_t)round_up((long long)n_total, 8) * D;
+  const size_t rows_alloc = (size_t)round_up((long long)n_total, 8) + 8;
+  float* lo = hi + rows_alloc * D;
+  float* S = lo + rows_alloc * D;
   char* table = align_up(reinterpret_cast<char*>(S + s_elems), 256);
   ClassExtent* ext_dev = reinterpret_cast<ClassExtent*>(align_up(table + table_bytes, 256));
   NSGP_REQUIRE((char*)(ext_dev + n_classes) <= (char*)workspace + workspace_bytes,
                "cosine_count_batched: workspace layout overflow");
   int rc = launch_normalize_split(F, D, rows, (int)n_total, hi, lo, stream);
   if (rc) return rc;
+  // rows past the last class that an 8-row operand may touch
+  NSGP_CHECK_CUDA(cudaMemsetAsync(hi + n_total * D, 0, (rows_alloc - n_total) * D * 4, stream));
+  NSGP_CHECK_CUDA(cudaMemsetAsync(lo + n_total * D, 0, (rows_alloc - n_total) * D * 4, stream));
   NSGP_CHECK_CUDA(cudaMemsetAsync(S, 0, s_elems * 4, stream));
   std::vector<ContractionArgs> probs;
   std::vector<ClassExtent> ext(n_classes);
   size_t row_off = 0, s_off = 0, mask_off = 0;
   int max_n = 0;
   for (int c = 0; c < n_classes; ++c) {
-    const int n = sizes[c], ld = (int)round_up(n, 4);
+    const int n = sizes[c], ne = (n > 0 && n < 8) ? 8 : n, ld = (int)round_up(ne, 4);
     ext[c] = ClassExtent{(long long)s_off, (long long)mask_off, (int)row_off, n, ld, 0};
     if (n > 0) {
       ContractionArgs a{};
-      a.A = matrix_operand(hi + row_off * D, lo + row_off * D, n, D, D);
+      a.A = matrix_operand(hi + row_off * D, lo + row_off * D, ne, D, D);
       a.B = a.A;
       a.out = S + s_off;
       a.ld = ld;
-      a.n_cols = n;
+      a.n_cols = ne;
       a.alpha = 1.f;
       a.epi = kEpiGramAtomic;
       a.splits = 1;
@@ -815,7 +885,7 @@ int repre_cosine_count_batched(const float* F, int D, const int32_t* rows, const
     }
     if (n > max_n) max_n = n;
     row_off += n;
-    s_off += (size_t)n * ld;
+    s_off += (size_t)ne * ld;
     mask_off += (size_t)n * n;
   }
   GroupInfo gi{};

@@ -84,8 +84,9 @@ template <int MODE>
 __global__ void __launch_bounds__(kSegThreads)
 segment_mean_kernel(const float* __restrict__ F, int D, const int* __restrict__ seg_off,
                     const int* __restrict__ rows, const float* __restrict__ mu,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, const int* __restrict__ nseg_dev) {
   const int s = blockIdx.y;
+  if (nseg_dev != nullptr && s >= *nseg_dev) return;   // grid sized for the maximum
   const int col = (blockIdx.x * kSegThreads + threadIdx.x) * 4;
   if (col >= D) return;
   const int beg = seg_off[s], end = seg_off[s + 1];
@@ -136,7 +137,7 @@ segment_mean_kernel(const float* __restrict__ F, int D, const int* __restrict__ 
 
 int launch_segment_mean(const float* F, int D, const int* seg_off, const int* rows, int nseg,
                         int max_seg_rows, const float* mu, int mode, float* out,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const int* nseg_dev) {
   NSGP_REQUIRE(D % 4 == 0, "segment_mean: D must be a multiple of 4");
   if (nseg == 0) return 0;
   int chunks = ceil_div(D, kSegThreads * 4);
@@ -150,9 +151,11 @@ int launch_segment_mean(const float* F, int D, const int* seg_off, const int* ro
   dim3 grid(chunks, nseg, splits);
   ProfScope prof(kProfRepre, stream);
   if (mode == 1)
-    segment_mean_kernel<1><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out);
+    segment_mean_kernel<1><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out,
+                                                             nseg_dev);
   else
-    segment_mean_kernel<0><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out);
+    segment_mean_kernel<0><<<grid, kSegThreads, 0, stream>>>(F, D, seg_off, rows, mu, out,
+                                                             nseg_dev);
   NSGP_LAUNCHED();
   return 0;
 }
@@ -269,6 +272,182 @@ int launch_threshold_count(const float* S, int n, int ld, float thresh, unsigned
   threshold_count_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(S, n, ld, thresh, mask, counts,
                                                              sim_out);
   NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Density ordering + greedy cover (:421-448) on the device: one CTA per class.
+//   order  = stable descending sort of the neighbour counts (torch's CPU sort is stable:
+//            equal counts keep ascending row order), rank by counting - n is hundreds
+//   thr    = sorted[-n // 3]  (python floor division: index n - ceil(n/3))
+//   covered= count <= thr;  then up to max_picks times: the first not-covered row in
+//            density order becomes a prototype seed, its neighbour mask is OR-ed into
+//            covered (:430-448).  Masks replayed from mask.pth come first (:425-433).
+// Outputs per class: picks (row within the class, -2 = replayed mask), npicks, and the
+// segment sizes [n, popcount(mask_0), ...] that the segment table is built from.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+greedy_cover_kernel(const GreedyClass* __restrict__ cls, const unsigned char* __restrict__ masks,
+                    const int* __restrict__ counts, const unsigned char* __restrict__ saved,
+                    int max_picks, int* __restrict__ order_ws,
+                    unsigned char* __restrict__ covered_ws, int* __restrict__ picks,
+                    int* __restrict__ npicks, int* __restrict__ seg_sizes) {
+  const int ci = blockIdx.x;
+  const GreedyClass e = cls[ci];
+  const int n = e.n, tid = threadIdx.x;
+  const int* cnt = counts + e.row_off;
+  const unsigned char* mask = masks + e.mask_off;
+  int* order = order_ws + e.row_off;
+  unsigned char* cov = covered_ws + e.row_off;
+  __shared__ int s_best, s_red[8];
+  for (int i = tid; i < n; i += 256) {
+    const int ci_cnt = cnt[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const int cj = cnt[j];
+      r += (cj > ci_cnt) || (cj == ci_cnt && j < i);
+    }
+    order[r] = i;
+  }
+  __syncthreads();
+  const int thr = cnt[order[n - (n + 2) / 3]];
+  for (int i = tid; i < n; i += 256) cov[i] = cnt[i] <= thr ? 1 : 0;
+  if (tid == 0) seg_sizes[ci * (max_picks + 1)] = n;
+  __syncthreads();
+  int np = 0;
+  for (int p = 0; p < max_picks; ++p) {
+    const unsigned char* m;
+    int pick;
+    if (p < e.n_saved) {
+      m = saved + e.saved_off + (long long)p * n;
+      pick = -2;
+    } else {
+      if (tid == 0) s_best = 0x7fffffff;
+      __syncthreads();
+      for (int r = tid; r < n; r += 256)
+        if (!cov[order[r]]) { atomicMin(&s_best, r); break; }
+      __syncthreads();
+      const int best = s_best;
+      __syncthreads();
+      if (best == 0x7fffffff) break;              // nothing left to cover (uniform)
+      pick = order[best];
+      m = mask + (long long)pick * n;
+    }
+    int local = 0;
+    for (int i = tid; i < n; i += 256)
+      if (m[i]) { cov[i] = 1; ++local; }
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = local;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_red[w];
+      picks[ci * max_picks + np] = pick;
+      seg_sizes[ci * (max_picks + 1) + 1 + np] = t;
+    }
+    ++np;
+    __syncthreads();
+  }
+  if (tid == 0) npicks[ci] = np;
+}
+
+// segment numbering and row offsets over all classes (one block; classes are few)
+__global__ void __launch_bounds__(256)
+segment_table_kernel(const GreedyClass* __restrict__ cls, int n_classes, int max_picks,
+                     const int* __restrict__ npicks, const int* __restrict__ seg_sizes,
+                     int* __restrict__ seg_base, int* __restrict__ seg_off,
+                     int* __restrict__ seg_label, int* __restrict__ nseg_out) {
+  __shared__ int s_nseg;
+  if (threadIdx.x == 0) {
+    int sb = 0;
+    for (int ci = 0; ci < n_classes; ++ci) { seg_base[ci] = sb; sb += 1 + npicks[ci]; }
+    s_nseg = sb;
+    *nseg_out = sb;
+  }
+  __syncthreads();
+  // row offset of a class = rows of all earlier classes' segments
+  for (int ci = threadIdx.x; ci < n_classes; ci += blockDim.x) {
+    int off = 0;
+    for (int cj = 0; cj < ci; ++cj) {
+      const int k = 1 + npicks[cj];
+      for (int q = 0; q < k; ++q) off += seg_sizes[cj * (max_picks + 1) + q];
+    }
+    const int k = 1 + npicks[ci], b = seg_base[ci];
+    for (int q = 0; q < k; ++q) {
+      seg_off[b + q] = off;
+      seg_label[b + q] = cls[ci].class_id;
+      off += seg_sizes[ci * (max_picks + 1) + q];
+    }
+    if (ci == n_classes - 1) seg_off[s_nseg] = off;
+  }
+}
+
+// rows of segment (class, slot): slot 0 = every row of the class, slot q > 0 = the rows
+// under the q-th mask, ascending (the boolean-mask gather of :443)
+__global__ void __launch_bounds__(256)
+segment_rows_kernel(const GreedyClass* __restrict__ cls, const unsigned char* __restrict__ masks,
+                    const unsigned char* __restrict__ saved, const int* __restrict__ rows_sel,
+                    int max_picks, const int* __restrict__ picks, const int* __restrict__ npicks,
+                    const int* __restrict__ seg_base, const int* __restrict__ seg_off,
+                    int* __restrict__ seg_rows) {
+  const int q = blockIdx.x, ci = blockIdx.y;
+  if (q > npicks[ci]) return;
+  const GreedyClass e = cls[ci];
+  const int n = e.n;
+  const int* src = rows_sel + e.row_off;
+  int* dst = seg_rows + seg_off[seg_base[ci] + q];
+  if (q == 0) {
+    for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+    return;
+  }
+  const int pick = picks[ci * max_picks + q - 1];
+  const unsigned char* m = pick == -2 ? saved + e.saved_off + (long long)(q - 1) * n
+                                      : masks + e.mask_off + (long long)pick * n;
+  __shared__ int warp_sums[8];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int start = 0; start < n; start += 256) {
+    const int i = start + threadIdx.x;
+    const bool hit = (i < n) && m[i];
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    const int in_warp = __popc(ballot & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      const int sw = warp_sums[w];
+      if (w < warp) before += sw;
+      total += sw;
+    }
+    if (hit) dst[base + before + in_warp] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) base += total;
+    __syncthreads();
+  }
+}
+
+int launch_greedy_segments(const GreedyClass* cls_dev, int n_classes, int max_n,
+                           const unsigned char* masks, const int* counts,
+                           const unsigned char* saved, const int* rows_sel, int max_picks,
+                           int* order_ws, unsigned char* covered_ws, int* seg_sizes,
+                           int* seg_base, int* picks, int* npicks, int* seg_off, int* seg_rows,
+                           int* seg_label, int* nseg_out, cudaStream_t stream) {
+  if (n_classes == 0) return 0;
+  ProfScope prof(kProfRepre, stream);
+  greedy_cover_kernel<<<n_classes, 256, 0, stream>>>(cls_dev, masks, counts, saved, max_picks,
+                                                     order_ws, covered_ws, picks, npicks,
+                                                     seg_sizes);
+  NSGP_LAUNCHED();
+  segment_table_kernel<<<1, 256, 0, stream>>>(cls_dev, n_classes, max_picks, npicks, seg_sizes,
+                                              seg_base, seg_off, seg_label, nseg_out);
+  NSGP_LAUNCHED();
+  dim3 grid(max_picks + 1, n_classes);
+  segment_rows_kernel<<<grid, 256, 0, stream>>>(cls_dev, masks, saved, rows_sel, max_picks, picks,
+                                                npicks, seg_base, seg_off, seg_rows);
+  NSGP_LAUNCHED();
+  (void)max_n;
   return 0;
 }
 

@@ -5,8 +5,23 @@
 namespace nsgp {
 int launch_class_index(const long long* labels, int M, int C, int* counts, int* offsets,
                        int* rows, cudaStream_t s);
+// nseg_dev != null: the grid covers `nseg` segments at most, the live count is read on
+// the device (segments built by launch_greedy_segments)
 int launch_segment_mean(const float* F, int D, const int* seg_off, const int* rows, int nseg,
-                        int max_seg_rows, const float* mu, int mode, float* out, cudaStream_t s);
+                        int max_seg_rows, const float* mu, int mode, float* out, cudaStream_t s,
+                        const int* nseg_dev = nullptr);
+struct GreedyClass {          // one class of a greedy-cover call
+  long long mask_off;         // byte offset of its (n x n) neighbour mask
+  long long saved_off;        // byte offset of its replayed masks (n_saved x n)
+  int row_off;                // first row in the concatenated row / count arrays
+  int n, n_saved, class_id;
+};
+int launch_greedy_segments(const GreedyClass* cls_dev, int n_classes, int max_n,
+                           const unsigned char* masks, const int* counts,
+                           const unsigned char* saved, const int* rows_sel, int max_picks,
+                           int* order_ws, unsigned char* covered_ws, int* seg_sizes,
+                           int* seg_base, int* picks, int* npicks, int* seg_off, int* seg_rows,
+                           int* seg_label, int* nseg_out, cudaStream_t s);
 int launch_normalize_split(const float* F, int D, const int* rows, int n, float* hi, float* lo,
                            cudaStream_t s);
 int launch_threshold_count(const float* S, int n, int ld, float thresh, unsigned char* mask,

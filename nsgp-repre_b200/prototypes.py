@@ -2,12 +2,14 @@
 ``StandardMultiPrototypeReplayHead`` (mmdet/models/roi_heads/
 standard_roi_replay_head.py:375-501).
 
-GPU kernels do the bandwidth/compute work - per-class segmented means (:412-414),
-L2-normalise + cosine Gram + ``>= 0.6`` + neighbour counts (:417-421), masked
-means (:443), the device-resident replay gather (:458-463).  The tiny
-sequential part - density ordering and the greedy cover (:421-448, at most nine
-picks per class) - stays on the host and calls ``torch.sort`` on the CPU counts
-exactly like the reference does, so equal-count ties resolve identically.
+Everything runs on the device - per-class segmented means (:412-414), L2-normalise +
+cosine Gram + ``>= 0.6`` + neighbour counts (:417-421), the density ordering and the
+greedy cover (:421-448: one CTA per class; a stable descending rank reproduces the tie
+order of torch's CPU sort), masked means (:443), the device-resident replay gather
+(:458-463).  The host only learns the class sizes (to size buffers and the grouped
+Gram) and, at the end, the number of prototypes; ``save_idx`` (the ``mask.pth``
+payload) is fetched when it is asked for.  With the SIMT bring-up engine the ordering
+and the cover run on the host with ``torch.sort`` like the reference.
 """
 from __future__ import annotations
 
@@ -45,7 +47,8 @@ class MultiPrototypeReplay:
         self.thresh = thresh
         self.bbox_featss = None
         self.tmp_label = None
-        self.save_idx = None
+        self._save_idx = None
+        self._lazy_masks = None
         self.sigma = None
         self._out = None
         self._ws = None
@@ -80,8 +83,6 @@ class MultiPrototypeReplay:
                                     stream), "repre_class_index")
         h_off = offsets.cpu().tolist()
 
-        # neighbour masks / counts of every class, launched back to back into ONE
-        # device buffer [masks | counts | rows] that comes back in a single D2H copy
         sizes = []
         for c in previous_cls:
             n = h_off[c + 1] - h_off[c]
@@ -90,6 +91,11 @@ class MultiPrototypeReplay:
                 raise IndexError("class %d has no stored RoI feature "
                                  "(index 0 is out of bounds for dimension 0 with size 0)" % c)
             sizes.append(n)
+        if lib.nsgp_get_engine() == 0:
+            return self._build_device(feats, rows, h_off, previous_cls, sizes, save_idx, stream)
+
+        # neighbour masks / counts of every class, launched back to back into ONE
+        # device buffer [masks | counts | rows] that comes back in a single D2H copy
         mask_bytes = sum(n * n for n in sizes)
         mask_pad = (mask_bytes + 15) // 16 * 16
         cnt_elems = sum(sizes)
@@ -145,8 +151,10 @@ class MultiPrototypeReplay:
             seg_rows.append(cls_rows)
             seg_off.append(seg_off[-1] + n)
             seg_label.append(c)
-            # torch's CPU sort, the call the reference makes, so ties order identically
-            sim_sum, idx = torch.from_numpy(cnt_np.astype(np.int64)).sort(dim=-1, descending=True)  # :421
+            # stable, like the reference's sort under its pinned torch 1.12 (equal counts keep
+            # ascending row order; the device path ranks the same way)
+            sim_sum, idx = torch.from_numpy(cnt_np.astype(np.int64)).sort(
+                dim=-1, descending=True, stable=True)                    # :421
             thr = int(sim_sum[-n // 3])                                  # :422
             covered = cnt_np <= thr                                      # :423
             idx_np = idx.numpy()
@@ -186,6 +194,110 @@ class MultiPrototypeReplay:
         self._segments = (off_t, all_rows, max_rows)
         self._feats = feats
         return self
+
+    def _build_device(self, feats, rows, h_off, previous_cls, sizes, saved_masks, stream):
+        """tcgen05 engine: Gram, ordering, cover, segment table and means without leaving
+        the device; one small D2H at the end for the number of prototypes."""
+        import ctypes
+        dev = feats.device
+        M, D = feats.shape
+        ncls = len(sizes)
+        mp = self.max_proto - 1
+        sizes_arr = (ctypes.c_int32 * ncls)(*sizes)
+        ids_arr = (ctypes.c_int32 * ncls)(*previous_cls)
+        n_tot = sum(sizes)
+        mask_bytes = sum(n * n for n in sizes)
+        need = int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D)) + \
+            int(lib.repre_greedy_segments_workspace_bytes(sizes_arr, ncls, mp)) + 512
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws = self._ws
+        ws2_off = (int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D)) + 255) \
+            // 256 * 256
+        consecutive = all(b == a + 1 for a, b in zip(previous_cls, previous_cls[1:]))
+        if consecutive:
+            rows_sel = rows[h_off[previous_cls[0]]:h_off[previous_cls[-1] + 1]]
+        else:
+            rows_sel = torch.cat([rows[h_off[c]:h_off[c + 1]] for c in previous_cls])
+        masks = torch.empty(max(mask_bytes, 1), dtype=torch.uint8, device=dev)
+        counts = torch.empty(n_tot, dtype=torch.int32, device=dev)
+        check(lib.repre_cosine_count_batched(
+            ptr(feats), D, ptr(rows_sel), sizes_arr, ncls, float(self.thresh), ptr(masks),
+            ptr(counts), ptr(ws), ws2_off, stream), "repre_cosine_count_batched")
+        # masks replayed from mask.pth (:425-433): one H2D of the packed bytes
+        saved_dev, n_saved_arr = None, None
+        saved_lists = []
+        for ci, c in enumerate(previous_cls):
+            lst = list(saved_masks[c]) if c < len(saved_masks) else []
+            saved_lists.append(lst)
+        if any(saved_lists):
+            n_saved = [min(len(l), mp) for l in saved_lists]
+            chunks = []
+            for l, k, n in zip(saved_lists, n_saved, sizes):
+                for m in l[:k]:
+                    m = m.cpu().to(torch.uint8)
+                    if m.numel() != n:
+                        raise IndexError("replayed mask has %d entries, the class has %d rows "
+                                         "(The shape of the mask does not match the tensor)" %
+                                         (m.numel(), n))
+                    chunks.append(m)
+            if chunks:
+                saved_dev = torch.cat(chunks).to(dev)
+                n_saved_arr = (ctypes.c_int32 * ncls)(*n_saved)
+        nseg_max = ncls * (mp + 1)
+        seg = torch.empty(2 * nseg_max + 1 + n_tot * (mp + 1) + 1 + ncls + ncls * mp,
+                          dtype=torch.int32, device=dev)
+        seg_off = seg[:nseg_max + 1]
+        seg_label = seg[nseg_max + 1:2 * nseg_max + 1]
+        seg_rows = seg[2 * nseg_max + 1:2 * nseg_max + 1 + n_tot * (mp + 1)]
+        info = seg[2 * nseg_max + 1 + n_tot * (mp + 1):]
+        check(lib.repre_greedy_segments(
+            ptr(masks), ptr(counts), ptr(rows_sel), sizes_arr, ids_arr, ncls, mp,
+            ptr(saved_dev), n_saved_arr, ptr(seg_off), ptr(seg_rows), ptr(seg_label), ptr(info),
+            ws.data_ptr() + ws2_off, ws.numel() - ws2_off, stream), "repre_greedy_segments")
+        out = torch.empty(nseg_max, D, dtype=torch.float32, device=dev)
+        max_rows = max(sizes)
+        check(lib.repre_segment_mean_dev(ptr(feats), D, ptr(seg_off), ptr(seg_rows), nseg_max,
+                                         ptr(info), int(max_rows), ptr(out), stream),
+              "repre_segment_mean_dev")
+        h_info = info.cpu().tolist()                                 # the one late sync
+        nseg = h_info[0]
+        self.bbox_featss = out[:nseg]
+        self.tmp_label = seg_label[:nseg].to(torch.int64)
+        self._segments = (seg_off, seg_rows, max_rows)
+        self._feats = feats
+        self._lazy_masks = (masks, sizes, list(previous_cls), h_info[1:1 + ncls],
+                            h_info[1 + ncls:], saved_lists, list(saved_masks), mp)
+        self._save_idx = None
+        return self
+
+    @property
+    def save_idx(self):
+        """``mask.pth`` payload (:450-452): list[class] of list of bool masks over the
+        class's rows; built from the device picks on first access."""
+        if self._save_idx is None and self._lazy_masks is not None:
+            masks, sizes, classes, npicks, picks, saved_lists, save_idx, mp = self._lazy_masks
+            moff = 0
+            for ci, (c, n) in enumerate(zip(classes, sizes)):
+                tmp = list(saved_lists[ci])
+                mine = [p for p in picks[ci * mp:ci * mp + npicks[ci]] if p >= 0]
+                if mine:
+                    idx = torch.tensor(mine, dtype=torch.int64, device=masks.device)
+                    sel = masks[moff:moff + n * n].view(n, n)[idx].cpu().bool()
+                    tmp.extend(sel[k].clone() for k in range(len(mine)))
+                moff += n * n
+                if c < len(save_idx):
+                    save_idx[c] = tmp
+                else:
+                    save_idx.append(tmp)
+            self._save_idx = save_idx
+            self._lazy_masks = None
+        return self._save_idx
+
+    @save_idx.setter
+    def save_idx(self, value):
+        self._save_idx = value
+        self._lazy_masks = None
 
     @torch.no_grad()
     def build_sigma(self):

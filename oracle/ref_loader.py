@@ -210,14 +210,49 @@ def ref_optimizer(named_params, **kw):
     return opt
 
 
+class stable_sort_ties:
+    """The reference orders neighbour counts with ``sim_mask.sum(-1).sort(dim=-1,
+    descending=True)`` (standard_roi_replay_head.py:421) and the counts are small
+    integers, so ties are the rule.  Under the reference's pinned torch 1.12
+    (README.md:20-22) the CPU sort is a stable sort: equal counts keep ascending row
+    order.  torch >= 2.x in this container dispatches the non-stable call to a
+    vectorised sort whose tie order is unspecified (and differs between CPUs), which
+    would make the greedy picks irreproducible.  This context manager runs the
+    reference with its original tie order by making ``Tensor.sort`` stable - nothing
+    else about the call changes."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.Tensor.sort
+        orig = self._orig
+
+        def sort(t, *args, **kwargs):
+            if "stable" in kwargs or (args and isinstance(args[0], bool)):
+                return orig(t, *args, **kwargs)
+            return orig(t, *args, stable=True, **kwargs)
+
+        torch.Tensor.sort = sort
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.sort = self._orig
+        return False
+
+
 def ref_prototypes(feats, cls_targets, task_split, task_id, max_prototype, tmpdir,
-                   saved_masks=None):
+                   saved_masks=None, stable_ties=True):
     """Run the reference StandardMultiPrototypeReplayHead.__init__ prototype build
     (standard_roi_replay_head.py:397-452) on a synthetic rois_etc.pth.
 
     Returns (bbox_featss (P,D), tmp_label (P,), mask list as saved to mask.pth).
+    ``stable_ties``: see ``stable_sort_ties``.
     """
     import torch
+    if stable_ties:
+        with stable_sort_ties():
+            return ref_prototypes(feats, cls_targets, task_split, task_id, max_prototype,
+                                  tmpdir, saved_masks, stable_ties=False)
     Head = load_multi_prototype_head()
     prev = os.path.join(tmpdir, "x_%d" % (task_id - 1))
     cur = os.path.join(tmpdir, "x_%d" % task_id)

@@ -242,13 +242,15 @@ def greedy_masks(mask: torch.Tensor, counts: torch.Tensor, max_proto: int,
                  saved=None):
     """standard_roi_replay_head.py:421-448 - density-ordered greedy cover.
 
-    ``order`` is torch's (non-stable) descending sort of the counts, exactly the
-    call the reference makes, so ties resolve identically.  The lowest-density
+    ``order`` is the STABLE descending sort of the counts: the reference's call
+    (``.sort(dim=-1, descending=True)``) is a stable sort under its pinned torch 1.12;
+    torch >= 2.x leaves the tie order of the non-stable call unspecified
+    (oracle/ref_loader.py::stable_sort_ties).  The lowest-density
     third (counts <= sorted[(-n)//3]) starts out as already covered.  Up to
     ``max_proto-1`` picks; a saved mask list (mask.pth from the previous task)
     is replayed first (:432-433)."""
     n = counts.shape[0]
-    ordered, order = counts.sort(dim=-1, descending=True)
+    ordered, order = counts.sort(dim=-1, descending=True, stable=True)
     thr = ordered[-n // 3]
     covered = counts <= thr
     picked = saved if saved is not None else []      # mutated in place, as :426,440

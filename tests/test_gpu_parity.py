@@ -366,6 +366,43 @@ def test_prototypes_match_reference_fixture(pkg, engine, golden_dir):
     assert rel_fro(mp2.bbox_featss, g["protos2"]) < 1e-5
 
 
+@pytest.mark.parametrize("seed,classes,per_class,sub,noise,max_proto,D", [
+    (3, 4, 150, 12, 0.35, 10, 1024),     # more sub-clusters than picks: the cover stops at 9
+    (4, 2, 333, 3, 0.60, 10, 512),       # noisy: similarities straddle 0.6, many equal counts
+    (5, 5, 41, 2, 0.35, 4, 2048),        # max_prototype = 4
+    (6, 3, 700, 20, 0.45, 10, 256),      # n > 2 x 256 rows per class (multi-pass compaction)
+    (7, 1, 1, 1, 0.35, 10, 64),          # a class with a single row
+])
+def test_prototypes_device_cover_matches_oracle(pkg, seed, classes, per_class, sub, noise,
+                                                max_proto, D):
+    """Density ordering, greedy cover and segment table on the device against the CPU
+    restatement: same labels, same picked masks, prototypes within 1e-5; then the next
+    task replays a truncated mask list (mask.pth) and continues the cover."""
+    feats, lab = synth.proto_features(seed=seed, classes=classes, per_class=per_class, D=D,
+                                      sub=sub, noise=noise, bg=17)
+    want_p, want_l, want_m = O.build_prototypes(feats, lab, range(classes), max_proto)
+    mp = pkg.MultiPrototypeReplay(max_prototype=max_proto).build(feats.cuda(), lab.cuda(),
+                                                                 range(classes))
+    assert torch.equal(mp.tmp_label.cpu(), want_l)
+    assert [len(m) for m in mp.save_idx] == [len(m) for m in want_m]
+    for mine, ref in zip(mp.save_idx, want_m):
+        for a, b in zip(mine, ref):
+            assert torch.equal(a.cpu().bool(), b.bool())
+    assert rel_fro(mp.bbox_featss, want_p) < 1e-5
+    # replay: keep only the first pick of every class, the cover continues after it
+    saved = [[m.clone() for m in ms[:1]] for ms in want_m]
+    want_p2, want_l2, want_m2 = O.build_prototypes(feats, lab, range(classes), max_proto,
+                                                   saved_masks=[list(m) for m in saved])
+    mp2 = pkg.MultiPrototypeReplay(max_prototype=max_proto).build(
+        feats.cuda(), lab.cuda(), range(classes), saved_masks=[list(m) for m in saved])
+    assert torch.equal(mp2.tmp_label.cpu(), want_l2)
+    for mine, ref in zip(mp2.save_idx, want_m2):
+        assert len(mine) == len(ref)
+        for a, b in zip(mine, ref):
+            assert torch.equal(a.cpu().bool(), b.bool())
+    assert rel_fro(mp2.bbox_featss, want_p2) < 1e-5
+
+
 def test_cosine_count_mask_vs_oracle(pkg, engine):
     """Neighbour mask / counts (:417-421): identical to the oracle except where the
     similarity is within 1e-5 of the threshold (documented near-tie rule)."""
