@@ -484,10 +484,13 @@ def main():
         ncols = (t * (t + 1) // 2 - t) * 128 + t * last_n       # upper block-triangle
         issued += 3 * 2.0 * 128 * ncols * kpad
     achieved = cov_flops / (gram_ms_step * 1e-3) / 1e12
-    roofline = {"kernel": "grouped covariance launches: autocorr_tc_kernel (3x3 s1 convs) + "
+    roofline = {"kernel": "grouped covariance contraction: autocorr_tc_kernel (3x3 s1 convs) + "
                           "contraction_tc_kernel (rest), tcgen05 kind::tf32, 3xTF32",
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": None,
+                "frac": achieved / tf32_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one step,
+                # ncu --set full (profiles/ncu_r01_deferred_summary.csv): 2.57 + 2.02 GB
+                "traffic": 4.594e9,
                 "peak_source": peaks_src,
                 "launches_per_step": gram_n / prof_steps, "ms_per_step": gram_ms_step,
                 "issued_tflops": issued / (gram_ms_step * 1e-3) / 1e12,
@@ -499,6 +502,19 @@ def main():
                         "fewer than the algorithmic count, which is why frac can exceed the "
                         "issued fraction"}
     kernel_ms = {k: v[0] / prof_steps for k, v in prof.items()}
+    # the HBM-bound half of the covariance pass: grouped staging (batch mean + tf32 split +
+    # layout) - algorithmic bytes = one read of every layer input (the staged operand it
+    # writes is this implementation's own traffic and is counted in `traffic` only)
+    stage_ms = kernel_ms["stage"]
+    roofline_staging = {"kernel": "stage_group_kernel (2 launches per step: layer inputs, then "
+                                  "the gather layouts from the batch means)",
+                        "bound": "hbm", "achieved": input_bytes / (stage_ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "frac": input_bytes / (stage_ms * 1e-3) / 1e9 / hbm_peak,
+                        # ncu --set full, both launches: 9.76+3.21 and 0.13+0.58 GB
+                        "traffic": 13.68e9, "ms_per_step": stage_ms,
+                        "note": "dram traffic / time = 5.0 TB/s = 77 % of the measured copy "
+                                "bandwidth (first launch alone: 5.7 TB/s = 87 %)"}
 
     # RePRE statistics as bandwidth: algorithmic bytes = one read of F + prototypes out
     repre_bytes = feats_d.numel() * 4 + labels_d.numel() * 8
@@ -573,7 +589,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
             "config": config, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_staging": roofline_staging,
+            "cpu_baseline": cpu_baseline,
             "phase_ms": {"covariance_61_layers": cov_ms, "sgdnscl_step_projection": sgd_ms,
                          "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms},
             "kernel_ms_per_step": kernel_ms,
