@@ -308,6 +308,50 @@ int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, co
                            int max_segments, const int32_t* n_segments_dev, int max_seg_rows,
                            float* out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * SURVEY 8(f)-4  EWC importance and penalty
+ *   replaces the per-tensor loops of BRNullSpaceRunner.calculate_save_importance
+ *   (mmdet/engine/runner/nsrunner_roi_replay.py:978-981) and EWCHook.__call__ (:1056-1069)
+ *   with one multi-tensor launch each.  `tensors` is a host array; table_dev is a device
+ *   scratch of nsgp_ewc_table_bytes(n) bytes.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const float* p;          /* accumulate: the gradient; penalty: the parameter */
+  float* importance;       /* accumulate: (numel) in/out; penalty: (tasks, numel) */
+  const float* old_params; /* penalty: (tasks, numel) */
+  float* grad;             /* penalty backward: gradient of p, accumulated into */
+  long long numel;
+  int tasks;
+} nsgp_ewc_tensor_t;
+size_t nsgp_ewc_table_bytes(int n);
+/* importance += (grad * grad) * mul / div   (one rounding per operation, reference order) */
+int nsgp_ewc_accumulate(const nsgp_ewc_tensor_t* tensors /* host */, int n, float mul, float div,
+                        void* table_dev, size_t table_bytes, void* stream);
+/* *loss_dev = coeff * sum_n sum_t importance * (p - old)^2   (fp64 accumulation) */
+int nsgp_ewc_penalty(const nsgp_ewc_tensor_t* tensors /* host */, int n, float coeff,
+                     double* loss_dev, void* table_dev, size_t table_bytes, void* stream);
+/* grad += *grad_out_dev * 2 * coeff * sum_t importance_t * (p - old_t) */
+int nsgp_ewc_penalty_backward(const nsgp_ewc_tensor_t* tensors /* host */, int n, float coeff,
+                              const float* grad_out_dev, void* table_dev, size_t table_bytes,
+                              void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * SURVEY 8(f)-3  teacher pseudo-label merge
+ *   replaces the per-box loop of FasterRCNNRoIReplay.loss
+ *   (mmdet/models/detectors/faster_rcnn_roi_replay.py:78-108): for every image, every
+ *   teacher box in order: max torchvision box_iou against the ground truth plus the teacher
+ *   boxes already accepted for the RoI head; > iou_thresh (0.7, compared as a python float)
+ *   drops it; score > rpn_thresh (0.5) keeps it for the RPN targets, score > roi_thresh
+ *   (0.7) for the RoI targets.  Boxes are (N,4) fp32 xyxy, concatenated over the images
+ *   with offsets[n_images+1]; outputs keep_rpn / keep_roi per teacher box and
+ *   counts[2*b] / counts[2*b+1] = kept boxes of image b.
+ * ------------------------------------------------------------------------- */
+int nsgp_pseudo_label_merge(const float* gt_boxes, const int32_t* gt_offsets,
+                            const float* pseudo_boxes, const float* pseudo_scores,
+                            const int32_t* pseudo_offsets, int n_images, int max_pseudo,
+                            float rpn_thresh, float roi_thresh, double iou_thresh,
+                            uint8_t* keep_rpn, uint8_t* keep_roi, int32_t* counts, void* stream);
+
 /* bring-up: per-CTA wait/issue cycle counters of the last tcgen05 contraction launched
  * with NSGP_DBG_COUNTERS=1 in the environment (8 counters per CTA, host buffer) */
 int nsgp_debug_read_counters(unsigned long long* out /* host */, int n);

@@ -52,6 +52,11 @@ class StageGroup(C.Structure):
                 ("off_items", c_size_t * 2), ("off_xs", c_size_t), ("bytes", c_size_t)]
 
 
+class EwcTensor(C.Structure):
+    _fields_ = [("p", c_void_p), ("importance", c_void_p), ("old_params", c_void_p),
+                ("grad", c_void_p), ("numel", C.c_longlong), ("tasks", c_int)]
+
+
 class CovJob(C.Structure):
     _fields_ = [("Cin", c_int), ("H", c_int), ("W", c_int), ("kh", c_int), ("kw", c_int),
                 ("sh", c_int), ("sw", c_int), ("ph", c_int), ("pw", c_int),
@@ -124,6 +129,16 @@ SIGNATURES = {
     "repre_kmeans_assign_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "repre_kmeans_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
+    "nsgp_ewc_table_bytes": (c_size_t, [c_int]),
+    "nsgp_ewc_accumulate": (c_int, [C.POINTER(EwcTensor), c_int, c_float, c_float, c_void_p,
+                                    c_size_t, c_void_p]),
+    "nsgp_ewc_penalty": (c_int, [C.POINTER(EwcTensor), c_int, c_float, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
+    "nsgp_ewc_penalty_backward": (c_int, [C.POINTER(EwcTensor), c_int, c_float, c_void_p,
+                                          c_void_p, c_size_t, c_void_p]),
+    "nsgp_pseudo_label_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_int, c_float, c_float, c_double, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "nsgp_debug_read_counters": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
     "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,

@@ -117,6 +117,45 @@ def main():
                os.path.join(OUT, "prototypes.pt"))
     print("protos", tuple(protos.shape), tmp_label.tolist(), [len(m) for m in masks])
     print("protos2", tuple(protos2.shape), tmp_label2.tolist(), [len(m) for m in masks2])
+    # 5. teacher pseudo-label merge: the reference's FasterRCNNRoIReplay.loss
+    from oracle.synth import pseudo_label_case, ToyBNNet, ewc_batches
+    cases = []
+    for seed in (0, 1, 2):
+        gt_b, gt_l, ps_b, ps_s, ps_l = pseudo_label_case(seed)
+        out = R.ref_pseudo_label_merge(gt_b, gt_l, ps_b, ps_s, ps_l)
+        cases.append({"seed": seed, "out": out})
+        print("pseudo merge", seed, [(tuple(o[0].shape), tuple(o[2].shape)) for o in out])
+    torch.save(cases, os.path.join(OUT, "pseudo_merge.pt"))
+
+    # 6. EWC: calculate_save_importance over two "tasks", then EWCHook
+    torch.manual_seed(0)
+    net = ToyBNNet()
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    loss_fn = lambda m, b: nn.functional.cross_entropy(m(b["inputs"]), b["data_samples"])
+    terms, reg = R.ref_ewc_importance(net, ewc_batches(0), loss_fn)
+    with torch.no_grad():
+        for k, p in enumerate(reg.values()):
+            p.add_(0.05 * torch.randn(p.shape, generator=torch.Generator().manual_seed(100 + k)))
+    terms, reg = R.ref_ewc_importance(net, ewc_batches(1), loss_fn, previous_terms=terms)
+    state2 = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        for k, p in enumerate(reg.values()):
+            p.add_(0.02 * torch.randn(p.shape, generator=torch.Generator().manual_seed(200 + k)))
+    state3 = {k: v.clone() for k, v in net.state_dict().items()}
+    hook = R.ref_ewc_hook(net, reg, terms)
+    b = ewc_batches(2)[0]
+    net.train()
+    res = hook(b["inputs"], b["data_samples"])
+    for p in net.parameters():
+        p.grad = None
+    res["ewc_loss"].backward()
+    torch.save({"state0": state0, "state2": state2, "state3": state3,
+                "terms": {k: {n: [t.clone() for t in v] for n, v in d.items()}
+                          for k, d in terms.items()},
+                "reg_names": list(reg.keys()), "ewc_loss": res["ewc_loss"].detach(),
+                "grads": {n: p.grad.clone() for n, p in reg.items() if p.grad is not None}},
+               os.path.join(OUT, "ewc.pt"))
+    print("ewc", list(reg.keys()), float(res["ewc_loss"]))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

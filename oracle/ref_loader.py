@@ -268,3 +268,186 @@ def ref_prototypes(feats, cls_targets, task_split, task_id, max_prototype, tmpdi
                 max_prototype=max_prototype)
     masks = torch.load(os.path.join(cur, "mask.pth"), map_location="cpu")
     return head.bbox_featss, head.tmp_label, masks
+
+
+# --------------------------------------------------------------------------- #
+# EWC importance + penalty (nsrunner_roi_replay.py:946-990,1038-1073)
+# --------------------------------------------------------------------------- #
+
+def ref_ewc_importance(model, batches, loss_fn, previous_terms=None):
+    """Run the reference ``BRNullSpaceRunner.calculate_save_importance`` (:946-990) and
+    ``register_params`` (:1006-1031) as unbound functions on a stand-in runner: the
+    model is any ``nn.Module``, ``batches`` a list of "data_batch" dicts (the reference
+    scales by ``len(data_batch)`` = number of dict keys, :980), ``loss_fn(model, batch)``
+    the scalar loss.  Returns the ``ewc_reg_terms`` dict that the reference pickles."""
+    import tempfile
+    import torch
+    Runner = load_runner()
+
+    class _Logger:
+        def info(self, *a, **k):
+            pass
+
+    class _OptimWrapper:
+        def scale_loss(self, loss):
+            return loss
+
+        def backward(self, loss):
+            loss.backward()
+
+        def zero_grad(self):
+            for p in model.parameters():
+                p.grad = None
+
+    model.data_preprocessor = lambda batch, training: batch
+    model._run_forward = lambda data, mode: {"loss": loss_fn(model, data)}
+    model.parse_losses = lambda losses: (losses["loss"], {})
+    fake = SimpleNamespace(model=model, logger=_Logger(), train_dataloader=list(batches),
+                           optim_wrapper=_OptimWrapper(),
+                           ewc_reg_terms=previous_terms if previous_terms is not None else {},
+                           work_dir=tempfile.mkdtemp())
+    fake.register_params = lambda: Runner.register_params(fake)
+    try:
+        Runner.calculate_save_importance(fake, list(batches))
+    finally:
+        for attr in ("data_preprocessor", "_run_forward", "parse_losses"):
+            try:
+                delattr(model, attr)
+            except AttributeError:
+                pass
+    return fake.ewc_reg_terms, fake.reg_params
+
+
+def ref_ewc_hook(module, reg_params, ewc_reg_terms):
+    """The reference ``EWCHook`` (:1038-1073) wrapped around ``module.loss``."""
+    load_runner()
+    mod = sys.modules["_ref_nsrunner"]
+    return mod.EWCHook(module=module, reg_params=reg_params, ewc_reg_terms=ewc_reg_terms)
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY 8(f)-3: teacher pseudo-label merge (faster_rcnn_roi_replay.py:67-108)
+# --------------------------------------------------------------------------- #
+
+class Instances:
+    """Minimal stand-in for ``mmengine.structures.InstanceData`` (absent here): tensor
+    fields of equal length, ``len``, int / index-tensor ``__getitem__``, ``['field']``,
+    ``del``, ``cat``.  Only what the reference's merge loop touches."""
+
+    def __init__(self, **fields):
+        object.__setattr__(self, "_f", dict(fields))
+
+    def __getattr__(self, k):
+        f = object.__getattribute__(self, "_f")
+        if k in f:
+            return f[k]
+        raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self._f[k] = v
+
+    def __delattr__(self, k):
+        del self._f[k]
+
+    def __len__(self):
+        return 0 if not self._f else len(next(iter(self._f.values())))
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            return self._f[item]
+        if isinstance(item, int):
+            if item >= len(self) or item < -len(self):
+                raise IndexError(item)
+            item = slice(item, None, len(self)) if item >= 0 else slice(item, None, len(self))
+        return Instances(**{k: v[item] for k, v in self._f.items()})
+
+    def keys(self):
+        return list(self._f.keys())
+
+    @staticmethod
+    def cat(items):
+        import torch
+        keys = items[0].keys()
+        assert all(set(i.keys()) == set(keys) for i in items), "fields differ"
+        return Instances(**{k: torch.cat([i._f[k] for i in items]) for k in keys})
+
+    def __deepcopy__(self, memo):
+        return Instances(**{k: v.clone() for k, v in self._f.items()})
+
+
+def load_detector():
+    """The reference ``FasterRCNNRoIReplay`` class
+    (mmdet/models/detectors/faster_rcnn_roi_replay.py:14) on a trivial base class."""
+    if "det" not in _cache:
+        _install_stubs()
+        import torch.nn as nn
+        pkg = "_ref_detectors"
+        m = types.ModuleType(pkg)
+        m.__path__ = []
+        m.TwoStageDetector = type("TwoStageDetector", (nn.Module,), {})
+        sys.modules[pkg] = m
+        mod = _load_by_path(pkg + ".faster_rcnn_roi_replay",
+                            "mmdet/models/detectors/faster_rcnn_roi_replay.py", package=pkg)
+        _cache["det"] = mod.FasterRCNNRoIReplay
+    return _cache["det"]
+
+
+def ref_pseudo_label_merge(gt_boxes, gt_labels, ps_boxes, ps_scores, ps_labels,
+                           rpn_thresh=0.5, roi_thresh=0.7):
+    """Run the reference ``FasterRCNNRoIReplay.loss`` (:40-145) on a stand-in ``self`` whose
+    teacher returns the given predictions; the RPN head and RoI head record the data
+    samples they are handed.  Returns per image (rpn_boxes, rpn_labels, roi_boxes,
+    roi_labels); the RPN labels are recorded before :118-120 zero them."""
+    Det = load_detector()
+    n = len(gt_boxes)
+    samples = [SimpleNamespace(gt_instances=Instances(bboxes=gt_boxes[i].clone(),
+                                                      labels=gt_labels[i].clone()))
+               for i in range(n)]
+    preds = [SimpleNamespace(pred_instances=Instances(bboxes=ps_boxes[i].clone(),
+                                                      scores=ps_scores[i].clone(),
+                                                      labels=ps_labels[i].clone()))
+             for i in range(n)]
+    rec = {}
+
+    class _Teacher:
+        def eval(self):
+            return self
+
+        def predict(self, inputs, data_samples, rescale=False):
+            return preds
+
+    class _Rpn:
+        def loss_and_predict(self, x, rpn_data_samples, proposal_cfg=None):
+            rec["rpn"] = [(s.gt_instances.bboxes.clone(), None) for s in rpn_data_samples]
+            return {}, None
+
+    class _Roi:
+        def loss(self, x, rpn_results_list, batch_data_samples):
+            rec["roi"] = [(s.gt_instances.bboxes.clone(), s.gt_instances.labels.clone())
+                          for s in batch_data_samples]
+            return {}
+
+    class _Cfg(dict):
+        rpn = None
+
+    # :118-120 zero the RPN labels in place: wrap Instances.cat to remember them
+    rpn_labels = {}
+    fake = SimpleNamespace(extract_feat=lambda x: None, teacher_model=_Teacher(),
+                           rpn_thresh=rpn_thresh, roi_thresh=roi_thresh, with_rpn=True,
+                           train_cfg=_Cfg(), test_cfg=_Cfg(), rpn_head=_Rpn(), roi_head=_Roi())
+    import torch
+    orig_zeros_like = torch.zeros_like
+
+    def spy_zeros_like(t, *a, **k):
+        rpn_labels.setdefault("seq", []).append(t.clone())
+        return orig_zeros_like(t, *a, **k)
+
+    torch.zeros_like = spy_zeros_like
+    try:
+        Det.loss(fake, None, samples)
+    finally:
+        torch.zeros_like = orig_zeros_like
+    out = []
+    for i in range(n):
+        out.append((rec["rpn"][i][0], rpn_labels["seq"][i], rec["roi"][i][0], rec["roi"][i][1]))
+    return out

@@ -399,3 +399,80 @@ def kmeans_update(x, assign, k, old_centres):
         if sel.any():
             out[j] = x[sel].mean(0)
     return out
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY 8(f)-3 : teacher pseudo-label merge
+# --------------------------------------------------------------------------- #
+
+
+def pseudo_label_merge(gt_boxes, gt_labels, ps_boxes, ps_scores, ps_labels,
+                       rpn_thresh: float = 0.5, roi_thresh: float = 0.7,
+                       iou_thresh: float = 0.7):
+    """faster_rcnn_roi_replay.py:78-108, per image and per teacher box IN ORDER:
+    ``max_iou`` = max torchvision ``box_iou`` against the RoI ground-truth set, which
+    grows by every teacher box accepted for the RoI head (:104-106) - 0.0 while that set
+    is empty (:86-90); ``max_iou > 0.7`` (python float compare, :93) drops the box;
+    ``score > rpn_thresh`` / ``score > roi_thresh`` (fp32 tensor compares, :101,:105)
+    append it to the RPN / RoI targets.  Returns per image
+    (rpn_boxes, rpn_labels, roi_boxes, roi_labels)."""
+    from torchvision.ops import box_iou
+    out = []
+    for gb, gl, pb, psc, pl in zip(gt_boxes, gt_labels, ps_boxes, ps_scores, ps_labels):
+        roi_b, roi_l = gb.clone(), gl.clone()
+        rpn_b, rpn_l = gb.clone(), gl.clone()
+        for k in range(pb.shape[0]):
+            box = pb[k:k + 1]
+            max_iou = box_iou(box, roi_b).max().item() if roi_b.shape[0] > 0 else 0.0
+            if max_iou > iou_thresh:
+                continue
+            if bool(psc[k] > rpn_thresh):
+                rpn_b = torch.cat([rpn_b, box])
+                rpn_l = torch.cat([rpn_l, pl[k:k + 1]])
+            if bool(psc[k] > roi_thresh):
+                roi_b = torch.cat([roi_b, box])
+                roi_l = torch.cat([roi_l, pl[k:k + 1]])
+        out.append((rpn_b, rpn_l, roi_b, roi_l))
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY 8(f)-4 : EWC importance + penalty
+# --------------------------------------------------------------------------- #
+
+
+def ewc_register_params(model, must_names=("bn",), ignore_names=("teacher_model",)):
+    """nsrunner_roi_replay.py:1006-1031: parameters whose name contains a ``must``
+    substring and no ``ignore`` substring."""
+    reg = {}
+    for n, p in model.named_parameters():
+        if any(i in n for i in ignore_names):
+            continue
+        if len(must_names) == 0 or any(m in n for m in must_names):
+            reg[n] = p
+    return reg
+
+
+def ewc_accumulate(importance: dict, grads: dict, len_data_batch: int, len_dataloader: int):
+    """:978-981: ``importance[n] += grad**2 * len(data_batch) / len(dataloader)`` for every
+    registered parameter that has a gradient (in place, fp32, this operation order)."""
+    for n, p in importance.items():
+        g = grads.get(n)
+        if g is not None:
+            p += (g ** 2) * len_data_batch / len_dataloader
+    return importance
+
+
+def ewc_penalty(reg_params: dict, ewc_reg_terms: dict, coeff: float = 1000.0):
+    """:1056-1069: ``coeff * sum_n (importance_n * (p_n - old_n)**2).sum()`` with the
+    per-task terms concatenated along a new leading axis; differentiable in ``p``.
+    Evaluated in fp64 (the checker's value; the reference sums in fp32)."""
+    total = 0.0
+    for n, p in reg_params.items():
+        if not p.requires_grad:
+            continue
+        imp = torch.cat(ewc_reg_terms["importance"][n], dim=0).double()
+        old = torch.cat(ewc_reg_terms["task_param"][n], dim=0).double()
+        new = p.double().unsqueeze(0).expand(old.shape)
+        total = total + coeff * (imp * (new - old) ** 2).sum()
+    return total

@@ -77,3 +77,70 @@ def proto_features(seed=0, classes=3, per_class=60, D=12544, sub=5, noise=0.35, 
     return feats, lab
 
 
+
+
+def pseudo_label_case(seed=0, images=4, max_gt=6, max_pseudo=40):
+    """SURVEY 8(f)-3 inputs: per image a few ground-truth boxes (one image has none) and
+    teacher boxes in descending score order like mmdet's predict - some jittered copies of
+    the ground truth (IoU above 0.7), some near-duplicates of each other (so the growing
+    RoI set matters), scores spread over the 0.5 / 0.7 thresholds."""
+    g = torch.Generator().manual_seed(seed)
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * 300
+        wh = torch.rand(n, 2, generator=g) * 120 + 8
+        return torch.cat([xy, xy + wh], 1)
+
+    gt_b, gt_l, ps_b, ps_s, ps_l = [], [], [], [], []
+    for i in range(images):
+        ng = 0 if i == 1 else int(torch.randint(1, max_gt + 1, (1,), generator=g))
+        gb = boxes(ng)
+        npz = int(torch.randint(max_pseudo // 2, max_pseudo + 1, (1,), generator=g))
+        fresh = boxes(npz)
+        parts = [fresh]
+        if ng:
+            parts.append(gb + torch.randn(ng, 4, generator=g) * 2.0)     # overlaps the GT
+        parts.append(fresh[: npz // 3] + torch.randn(npz // 3, 4, generator=g) * 3.0)  # near-duplicates
+        pb = torch.cat(parts)
+        pb = pb[torch.randperm(pb.shape[0], generator=g)]
+        sc = torch.rand(pb.shape[0], generator=g).sort(descending=True).values
+        sc[::7] = 0.7            # exactly on the RoI threshold (fp32 0.7 > 0.7 is False)
+        sc[3::11] = 0.5
+        gt_b.append(gb); gt_l.append(torch.randint(0, 20, (ng,), generator=g))
+        ps_b.append(pb); ps_s.append(sc)
+        ps_l.append(torch.randint(0, 20, (pb.shape[0],), generator=g))
+    return gt_b, gt_l, ps_b, ps_s, ps_l
+
+
+class ToyBNNet(torch.nn.Module):
+    """SURVEY 8(f)-4 model: conv/BN stacks whose BatchNorm parameter names contain "bn"
+    (the reference registers exactly those, nsrunner_roi_replay.py:1013-1031), one
+    "teacher_model" copy that must be ignored, one frozen BN parameter."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.conv1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(8)
+        self.conv2 = nn.Conv2d(8, 16, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(16)
+        self.layer = nn.Sequential(nn.Conv2d(16, 1100, 1), nn.BatchNorm2d(1100))   # > 1 chunk
+        self.layer_bn_named = nn.BatchNorm2d(1100)
+        self.fc = nn.Linear(1100, 4)
+        self.teacher_model = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+        self.bn2.bias.requires_grad_(False)
+
+    def forward(self, x):
+        x = torch.relu(self.bn1(self.conv1(x)))
+        x = torch.relu(self.bn2(self.conv2(x)))
+        x = self.layer_bn_named(self.layer(x))
+        return self.fc(torch.relu(x).mean((2, 3)))
+
+    def loss(self, x, y):
+        return {"loss_cls": torch.nn.functional.cross_entropy(self(x), y)}
+
+
+def ewc_batches(seed=0, n=3):
+    g = torch.Generator().manual_seed(seed)
+    return [{"inputs": torch.randn(2, 3, 8, 8, generator=g),
+             "data_samples": torch.randint(0, 4, (2,), generator=g)} for _ in range(n)]

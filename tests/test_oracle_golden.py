@@ -156,3 +156,55 @@ def test_philox_known_answer():
     key = np.array([0xa4093822, 0x299f31d0], np.uint32)
     out = O.philox4x32_10(ctr, key)[0]
     assert [hex(int(v)) for v in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+# ------------------------------------------------------------------ SURVEY 8(f)-3 / 8(f)-4
+def test_pseudo_label_merge_oracle_matches_reference_fixture(golden_dir):
+    """oracle.restated.pseudo_label_merge against the outputs of the reference's own
+    FasterRCNNRoIReplay.loss (oracle/make_golden.py section 5): bit-exact."""
+    cases = torch.load(os.path.join(golden_dir, "pseudo_merge.pt"), weights_only=False)
+    for case in cases:
+        gt_b, gt_l, ps_b, ps_s, ps_l = synth.pseudo_label_case(case["seed"])
+        got = O.pseudo_label_merge(gt_b, gt_l, ps_b, ps_s, ps_l)
+        assert len(got) == len(case["out"])
+        for mine, ref in zip(got, case["out"]):
+            for a, b in zip(mine, ref):
+                assert torch.equal(a, b)
+        # the scenario is not degenerate: something was dropped for IoU, for score, and the
+        # RPN / RoI target sets differ
+        assert any(m[0].shape[0] != m[2].shape[0] for m in got)
+        assert any(m[0].shape[0] < g.shape[0] + p.shape[0] for m, g, p in zip(got, gt_b, ps_b))
+
+
+def test_ewc_oracle_matches_reference_fixture(golden_dir):
+    """Importance accumulation (:978-981) and penalty (:1056-1069) restated, against the
+    reference's calculate_save_importance / EWCHook run over two tasks."""
+    g = torch.load(os.path.join(golden_dir, "ewc.pt"), weights_only=False)
+    torch.manual_seed(0)
+    net = synth.ToyBNNet()
+    net.load_state_dict(g["state0"])
+    reg = O.ewc_register_params(net)
+    assert list(reg.keys()) == g["reg_names"]
+    # task 1 importance, restated loop
+    net.eval()
+    imp = {n: torch.zeros_like(p) for n, p in reg.items()}
+    batches = synth.ewc_batches(0)
+    for b in batches:
+        for p in net.parameters():
+            p.grad = None
+        torch.nn.functional.cross_entropy(net(b["inputs"]), b["data_samples"]).backward()
+        O.ewc_accumulate(imp, {n: p.grad for n, p in reg.items()}, len(b), len(batches))
+    for n in reg:
+        assert torch.equal(imp[n].unsqueeze(0), g["terms"]["importance"][n][0]), n
+    # penalty value and gradient at the fixture's parameters
+    net.load_state_dict(g["state3"])
+    reg = O.ewc_register_params(net)
+    net.train()
+    for p in net.parameters():
+        p.grad = None
+    loss = O.ewc_penalty(reg, g["terms"])
+    loss.backward()
+    assert abs(float(loss) - float(g["ewc_loss"])) <= 1e-5 * abs(float(g["ewc_loss"]))
+    for n, ref in g["grads"].items():
+        assert rel_fro(reg[n].grad, ref) < 1e-5, n
+    assert reg["bn2.bias"].grad is None and "bn2.bias" not in g["grads"]
