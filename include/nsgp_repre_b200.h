@@ -309,6 +309,25 @@ int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, co
                            float* out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * SURVEY 8(f)-2  RoIAlign over the FPN levels, optionally fused with the per-class sums
+ *   replaces SingleRoIExtractor.forward
+ *   (mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:45-118, pooling =
+ *   mmcv.ops.RoIAlign: average pooling, adaptive grid when sampling_ratio = 0, `aligned`)
+ *   feats[l]: (batch, channels, heights[l], widths[l]) fp32 NCHW device tensors (host array
+ *   of pointers), rois (n_rois,5) = [batch index, x1, y1, x2, y2] in image coordinates.
+ *   Level of a RoI: floor(log2(sqrt(w*h)/finest_scale + 1e-6)) clamped to the levels.
+ *   roi_feats (n_rois, channels*pooled*pooled) and/or class_sums (n_classes, same) +
+ *   class_counts (n_classes; labels outside [0,n_classes) are skipped); either output
+ *   may be NULL.  class_sums / class_counts are cleared by the call.
+ * ------------------------------------------------------------------------- */
+int repre_roi_align(const float* const* feats /* host */, const int32_t* heights /* host */,
+                    const int32_t* widths /* host */, const float* spatial_scales /* host */,
+                    int n_levels, int batch, int channels, const float* rois, int n_rois,
+                    int pooled, int sampling_ratio, int aligned, float finest_scale,
+                    const int64_t* labels, int n_classes, float* roi_feats, float* class_sums,
+                    int32_t* class_counts, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * SURVEY 8(f)-4  EWC importance and penalty
  *   replaces the per-tensor loops of BRNullSpaceRunner.calculate_save_importance
  *   (mmdet/engine/runner/nsrunner_roi_replay.py:978-981) and EWCHook.__call__ (:1056-1069)

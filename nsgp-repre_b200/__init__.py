@@ -11,6 +11,8 @@ sm_100a kernels reached through the C ABI of ``include/nsgp_repre_b200.h``:
   - mmdet/models/roi_heads/standard_roi_replay_head.py:375
 * ``rois``                         - all_gather_different_shape + the cal_rois tail
   (mmdet/engine/runner/nsrunner_roi_replay.py:73-105, 815-865)
+* ``roi_extract.SingleRoIExtractor`` - multi-level RoIAlign, optionally fused with the
+  per-class sums (mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:45-118)
 * ``ewc``                          - EWC importance accumulation and penalty
   (mmdet/engine/runner/nsrunner_roi_replay.py:946-1073)
 * ``pseudo_labels``                - teacher pseudo-label merge
@@ -28,6 +30,7 @@ from .covariance import CovarianceHooks, BRNullSpaceCovariance  # noqa: F401
 from .optim import SGDNSCL  # noqa: F401
 from .prototypes import MultiPrototypeReplay, StandardMultiPrototypeReplayHead  # noqa: F401
 from .rois import all_gather_different_shape, RoIHarvest  # noqa: F401
+from .roi_extract import SingleRoIExtractor  # noqa: F401
 from .ewc import EWCHook, EWCImportance, register_params  # noqa: F401
 from .pseudo_labels import merge_pseudo_labels, merge_into_samples  # noqa: F401
 from . import registry  # noqa: F401

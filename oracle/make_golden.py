@@ -156,6 +156,12 @@ def main():
                 "grads": {n: p.grad.clone() for n, p in reg.items() if p.grad is not None}},
                os.path.join(OUT, "ewc.pt"))
     print("ewc", list(reg.keys()), float(res["ewc_loss"]))
+    # 7. RoI extraction: the reference's SingleRoIExtractor.forward / map_roi_levels
+    from oracle.synth import roi_case
+    feats, rois, labels = roi_case(0)
+    out, lv = R.ref_roi_extract(feats, rois, out_channels=feats[0].shape[1])
+    torch.save({"seed": 0, "out": out, "levels": lv}, os.path.join(OUT, "roi_extract.pt"))
+    print("roi extract", tuple(out.shape), torch.bincount(lv, minlength=4).tolist())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -451,3 +451,57 @@ def ref_pseudo_label_merge(gt_boxes, gt_labels, ps_boxes, ps_scores, ps_labels,
     for i in range(n):
         out.append((rec["rpn"][i][0], rpn_labels["seq"][i], rec["roi"][i][0], rec["roi"][i][1]))
     return out
+
+
+# --------------------------------------------------------------------------- #
+# SingleRoIExtractor (single_level_roi_extractor.py:45-118)
+# --------------------------------------------------------------------------- #
+
+def load_roi_extractor():
+    """The reference ``SingleRoIExtractor`` class on a trivial ``BaseRoIExtractor``."""
+    if "roi_ext" not in _cache:
+        _install_stubs()
+        import torch.nn as nn
+        pkg = "_ref_roi_extractors"
+        m = types.ModuleType(pkg)
+        m.__path__ = []
+        sys.modules[pkg] = m
+        base = types.ModuleType(pkg + ".base_roi_extractor")
+        base.BaseRoIExtractor = type("BaseRoIExtractor", (nn.Module,), {})
+        sys.modules[pkg + ".base_roi_extractor"] = base
+        mod = _load_by_path(pkg + ".single_level_roi_extractor",
+                            "mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py",
+                            package=pkg)
+        _cache["roi_ext"] = mod.SingleRoIExtractor
+    return _cache["roi_ext"]
+
+
+def ref_roi_extract(feats, rois, featmap_strides=(4, 8, 16, 32), out_channels=256,
+                    output_size=7, sampling_ratio=0, finest_scale=56):
+    """Run the reference ``SingleRoIExtractor.forward`` and ``map_roi_levels`` (its own level
+    mapping, per-level gather and scatter).  ``mmcv.ops.RoIAlign`` is an un-vendored
+    dependency that is absent here; its place is taken by ``torchvision.ops.roi_align``
+    (same algorithm: aligned=True, average pooling, adaptive sampling grid)."""
+    import torch
+    import torch.nn as nn
+    from torchvision.ops import roi_align
+    Ext = load_roi_extractor()
+
+    class _Layer(nn.Module):
+        def __init__(self, scale):
+            super().__init__()
+            self.output_size = (output_size, output_size)
+            self.scale = scale
+
+        def forward(self, f, r):
+            return roi_align(f, r, self.output_size, self.scale, sampling_ratio, True)
+
+    fake = nn.Module()
+    fake.roi_layers = nn.ModuleList([_Layer(1.0 / s) for s in featmap_strides])
+    fake.out_channels = out_channels
+    fake.finest_scale = finest_scale
+    fake.map_roi_levels = lambda r, n: Ext.map_roi_levels(fake, r, n)
+    with torch.no_grad():
+        out = Ext.forward(fake, tuple(feats), rois)
+        lv = Ext.map_roi_levels(fake, rois, len(feats))
+    return out, lv

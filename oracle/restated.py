@@ -476,3 +476,46 @@ def ewc_penalty(reg_params: dict, ewc_reg_terms: dict, coeff: float = 1000.0):
         new = p.double().unsqueeze(0).expand(old.shape)
         total = total + coeff * (imp * (new - old) ** 2).sum()
     return total
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY 8(f)-2 : RoIAlign over the FPN levels (+ per-class sums)
+# --------------------------------------------------------------------------- #
+
+
+def map_roi_levels(rois: torch.Tensor, num_levels: int, finest_scale: float = 56):
+    """single_level_roi_extractor.py:45-63."""
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    lv = torch.floor(torch.log2(scale / finest_scale + 1e-6))
+    return lv.clamp(min=0, max=num_levels - 1).long()
+
+
+def roi_extract(feats, rois, featmap_strides=(4, 8, 16, 32), output_size=7, sampling_ratio=0,
+                finest_scale=56):
+    """:65-118 with mmcv.ops.RoIAlign (absent, un-vendored) restated by
+    torchvision.ops.roi_align - the same published algorithm (aligned=True, average
+    pooling, sampling grid ceil(roi/output) when sampling_ratio = 0)."""
+    from torchvision.ops import roi_align
+    C = feats[0].shape[1]
+    out = feats[0].new_zeros(rois.shape[0], C, output_size, output_size)
+    lv = map_roi_levels(rois, len(feats), finest_scale) if len(feats) > 1 else \
+        torch.zeros(rois.shape[0], dtype=torch.long)
+    for i, f in enumerate(feats):
+        inds = (lv == i).nonzero().squeeze(1)
+        if inds.numel():
+            out[inds] = roi_align(f, rois[inds], (output_size, output_size),
+                                  1.0 / featmap_strides[i], sampling_ratio, True)
+    return out, lv
+
+
+def roi_class_sums(roi_feats: torch.Tensor, labels: torch.Tensor, num_classes: int):
+    """Per-class sums and counts of flattened RoI features; ``sums / counts`` is the coarse
+    prototype of standard_roi_replay_head.py:411-415.  fp64 accumulation (checker)."""
+    F = roi_feats.reshape(roi_feats.shape[0], -1).double()
+    sums = torch.zeros(num_classes, F.shape[1], dtype=torch.float64)
+    counts = torch.zeros(num_classes, dtype=torch.int32)
+    for c in range(num_classes):
+        sel = labels == c
+        sums[c] = F[sel].sum(0)
+        counts[c] = int(sel.sum())
+    return sums, counts

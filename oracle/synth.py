@@ -144,3 +144,25 @@ def ewc_batches(seed=0, n=3):
     g = torch.Generator().manual_seed(seed)
     return [{"inputs": torch.randn(2, 3, 8, 8, generator=g),
              "data_samples": torch.randint(0, 4, (2,), generator=g)} for _ in range(n)]
+
+
+def roi_case(seed=0, batch=2, channels=16, img_h=256, img_w=320, n_rois=64, classes=5,
+             strides=(4, 8, 16, 32)):
+    """SURVEY 8(f)-2 inputs: FPN-shaped feature maps and proposals whose sizes span all four
+    levels (including boxes larger than the image, a degenerate zero-area box and boxes
+    sticking out of the image), labels with background = `classes`."""
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(batch, channels, -(-img_h // s), -(-img_w // s), generator=g) for s in strides]
+    side = torch.exp(torch.rand(n_rois, generator=g) * 5.2 + 2.3)        # ~10 .. 1800 px
+    ar = torch.exp((torch.rand(n_rois, generator=g) - 0.5) * 1.4)
+    w, h = side * ar.sqrt(), side / ar.sqrt()
+    cx = torch.rand(n_rois, generator=g) * img_w
+    cy = torch.rand(n_rois, generator=g) * img_h
+    rois = torch.stack([torch.randint(0, batch, (n_rois,), generator=g).float(),
+                        cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    rois[0, 1:] = torch.tensor([10.0, 20.0, 10.0, 20.0])                 # zero area
+    rois[1, 1:] = torch.tensor([-50.0, -40.0, 30.0, 60.0])               # sticks out
+    rois[2, 1:] = torch.tensor([0.0, 0.0, 112.0, 112.0])                 # scale == 2 * finest
+    rois[3, 1:] = torch.tensor([0.0, 0.0, 56.0, 56.0])
+    labels = torch.randint(0, classes + 1, (n_rois,), generator=g)
+    return feats, rois, labels

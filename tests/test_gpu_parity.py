@@ -645,3 +645,59 @@ def test_ewc_matches_reference_fixture(pkg, golden_dir, tmp_path):
     net.loss = hook.ori_loss
     hook2 = pkg.EWCHook(module=net, reg_params=reg, ewc_reg_terms=same)
     assert "ewc_loss" not in hook2(b["inputs"].cuda(), b["data_samples"].cuda())
+
+
+# ------------------------------------------------------------------------ SURVEY 8(f)-2
+def test_roi_extract_matches_reference_fixture(pkg, golden_dir):
+    g = _load(golden_dir, "roi_extract.pt")
+    feats, rois, labels = synth.roi_case(g["seed"])
+    ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                 out_channels=feats[0].shape[1], featmap_strides=[4, 8, 16, 32])
+    assert torch.equal(ext.map_roi_levels(rois.cuda(), 4).cpu(), g["levels"])
+    out = ext([f.cuda() for f in feats], rois.cuda())
+    assert out.shape == g["out"].shape
+    assert rel_fro(out, g["out"]) < 1e-5
+    assert float((out.cpu() - g["out"]).abs().max()) < 1e-4
+    # rows individually (a wrong level would be hidden in the global norm)
+    per = (out.cpu() - g["out"]).flatten(1).norm(dim=1) / g["out"].flatten(1).norm(dim=1).clamp(min=1e-6)
+    assert float(per.max()) < 1e-4
+
+
+@pytest.mark.parametrize("sampling_ratio,levels", [(0, 4), (2, 4), (0, 1)])
+def test_roi_extract_and_class_sums_r50_shape(pkg, sampling_ratio, levels):
+    """256 channels, 512 proposals, four levels; features and the fused per-class sums
+    against the CPU restatement."""
+    strides = (4, 8, 16, 32)[:levels]
+    feats, rois, labels = synth.roi_case(3, batch=2, channels=256, img_h=320, img_w=416,
+                                         n_rois=512, classes=19, strides=strides)
+    want, lv = O.roi_extract(feats, rois, featmap_strides=strides, sampling_ratio=sampling_ratio)
+    ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=sampling_ratio),
+                                 out_channels=256, featmap_strides=list(strides))
+    cf = [f.cuda() for f in feats]
+    out = ext(cf, rois.cuda())
+    assert rel_fro(out, want) < 1e-5
+    sums, counts, flat = ext.class_sums(cf, rois.cuda(), labels.cuda(), 19, return_feats=True)
+    assert torch.equal(flat, out.flatten(1))
+    want_s, want_c = O.roi_class_sums(want, labels, 19)
+    assert torch.equal(counts.cpu(), want_c)
+    assert rel_fro(sums, want_s) < 1e-5
+    sums2, counts2 = ext.class_sums(cf, rois.cuda(), labels.cuda(), 19)       # no feature matrix
+    assert torch.equal(counts2, counts) and rel_fro(sums2, want_s) < 1e-5
+    # coarse prototypes = sums / counts = the prototype build's class means
+    fg = counts.cpu() > 0
+    mp = pkg.MultiPrototypeReplay(max_prototype=1).build(flat, labels.cuda(),
+                                                         [c for c in range(19) if fg[c]])
+    means = (sums / counts.clamp(min=1).unsqueeze(1))[fg.to(sums.device)]
+    assert rel_fro(mp.bbox_featss, means) < 1e-5
+
+
+def test_roi_extract_empty_and_errors(pkg):
+    feats, rois, labels = synth.roi_case(1, channels=8, n_rois=4)
+    ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                 out_channels=8, featmap_strides=[4, 8, 16, 32])
+    out = ext([f.cuda() for f in feats], rois[:0].cuda())
+    assert out.shape == (0, 8, 7, 7)
+    with pytest.raises(pkg._lib.NsgpError):
+        ext(feats, rois)                                   # host tensors: no CPU fallback
+    with pytest.raises(pkg._lib.NsgpError):
+        pkg.SingleRoIExtractor(dict(type="RoIPool", output_size=7), 8, [4])

@@ -208,3 +208,14 @@ def test_ewc_oracle_matches_reference_fixture(golden_dir):
     for n, ref in g["grads"].items():
         assert rel_fro(reg[n].grad, ref) < 1e-5, n
     assert reg["bn2.bias"].grad is None and "bn2.bias" not in g["grads"]
+
+
+def test_roi_extract_oracle_matches_reference_fixture(golden_dir):
+    """oracle.restated.roi_extract against the reference's own SingleRoIExtractor.forward /
+    map_roi_levels (pooling by torchvision in both: mmcv is absent)."""
+    g = torch.load(os.path.join(golden_dir, "roi_extract.pt"), weights_only=False)
+    feats, rois, labels = synth.roi_case(g["seed"])
+    out, lv = O.roi_extract(feats, rois)
+    assert torch.equal(lv, g["levels"])
+    assert torch.equal(out, g["out"])
+    assert set(lv.tolist()) == {0, 1, 2, 3}
