@@ -49,6 +49,45 @@ __device__ __forceinline__ int roi_level(const float* __restrict__ roi, float fi
   return (int)l;
 }
 
+// Separable form of the bin average.  A sample at (y, x) contributes hy/ly (x) hx/lx to its
+// four pixels and the validity test is a test on y OR a test on x, so the sum over the
+// gh x gw samples of a bin factorises:
+//     out = 1/count * sum_Y sum_X  Wy[ph][Y] * Wx[pw][X] * f[Y][X]
+// with Wy[ph][Y] = sum over the bin's gh row samples of their weight on pixel row Y (and the
+// same for columns).  The tables depend on the RoI only - built once per block in shared
+// memory - and a bin touches ~(bin+2)^2 pixels instead of 4 * gh * gw (3-4x fewer loads).
+constexpr int kMaxSpan = 66;         // pixel rows / columns one bin can touch through the table
+constexpr int kMaxPooled = 14;
+
+struct AxisTable {
+  float w[kMaxPooled][kMaxSpan];
+  int first[kMaxPooled], n[kMaxPooled];
+};
+
+// one thread per bin index along the axis: accumulate the samples in order (deterministic)
+__device__ __forceinline__ bool build_axis(AxisTable& t, int p, float start, float bin, int g,
+                                           int size) {
+  int first = 0, n = 0;
+  bool ok = true;
+  for (int k = 0; k < kMaxSpan; ++k) t.w[p][k] = 0.f;
+  for (int i = 0; i < g; ++i) {
+    float v = start + (float)p * bin + ((float)i + .5f) * bin / (float)g;
+    if (v < -1.0f || v > (float)size) continue;            // sample contributes nothing
+    if (v <= 0.f) v = 0.f;
+    int lo = (int)v, hi;
+    if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else { hi = lo + 1; }
+    const float l = v - (float)lo, h = 1.f - l;
+    if (n == 0) first = lo;
+    if (hi - first >= kMaxSpan) { ok = false; break; }
+    t.w[p][lo - first] += h;
+    t.w[p][hi - first] += l;
+    n = hi - first + 1;
+  }
+  t.first[p] = first;
+  t.n[p] = n;
+  return ok;
+}
+
 // grid = (R, channel chunks); block = 256 threads over (channel within the chunk, bin)
 __global__ void __launch_bounds__(256)
 roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int pooled,
@@ -56,6 +95,8 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
                  const long long* __restrict__ labels, int n_classes,
                  float* __restrict__ roi_feats, float* __restrict__ class_sums,
                  int* __restrict__ class_counts, int ch_per_block) {
+  __shared__ AxisTable ty, tx;
+  __shared__ int s_fallback;
   const int r = blockIdx.x;
   const float* roi = rois + (long long)r * 5;
   const int b = (int)roi[0];
@@ -73,6 +114,17 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
   const int bins = pooled * pooled;
   const int c0 = blockIdx.y * ch_per_block;
   const int c1 = min(channels, c0 + ch_per_block);
+  if (threadIdx.x == 0) s_fallback = pooled > kMaxPooled ? 1 : 0;
+  __syncthreads();
+  if (pooled <= kMaxPooled) {
+    bool ok = true;
+    if (threadIdx.x < pooled) ok = build_axis(ty, threadIdx.x, sh, bin_h, gh, H);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + pooled)
+      ok = build_axis(tx, threadIdx.x - 32, sw, bin_w, gw, W);
+    if (!ok) s_fallback = 1;
+  }
+  __syncthreads();
+  const bool direct = s_fallback != 0;
   long long label = -1;
   if (class_sums != nullptr) {
     label = labels[r];
@@ -85,11 +137,22 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
     const int ph = bin / pooled, pw = bin - ph * pooled;
     const float* f = lv.feat[l] + ((long long)b * channels + c) * H * W;
     float acc = 0.f;
-    for (int iy = 0; iy < gh; ++iy) {
-      const float y = sh + (float)ph * bin_h + ((float)iy + .5f) * bin_h / (float)gh;
-      for (int ix = 0; ix < gw; ++ix) {
-        const float x = sw + (float)pw * bin_w + ((float)ix + .5f) * bin_w / (float)gw;
-        acc += bilinear(f, H, W, y, x);
+    if (!direct) {
+      const int ny = ty.n[ph], nx = tx.n[pw];
+      const float* f0 = f + (long long)ty.first[ph] * W + tx.first[pw];
+      for (int j = 0; j < ny; ++j) {
+        const float wy = ty.w[ph][j];
+        float row = 0.f;
+        for (int i = 0; i < nx; ++i) row += tx.w[pw][i] * __ldg(f0 + j * W + i);
+        acc += wy * row;
+      }
+    } else {
+      for (int iy = 0; iy < gh; ++iy) {
+        const float y = sh + (float)ph * bin_h + ((float)iy + .5f) * bin_h / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          const float x = sw + (float)pw * bin_w + ((float)ix + .5f) * bin_w / (float)gw;
+          acc += bilinear(f, H, W, y, x);
+        }
       }
     }
     const float v = acc / count;

@@ -109,10 +109,7 @@ class _EwcPenalty(torch.autograd.Function):
     def forward(ctx, hook, *params):
         dev = params[0].device
         n = len(params)
-        arr = (EwcTensor * n)()
-        for k, (p, (imp, old, tasks)) in enumerate(zip(params, hook._stacks)):
-            arr[k].p, arr[k].importance, arr[k].old_params = p.data_ptr(), imp.data_ptr(), old.data_ptr()
-            arr[k].numel, arr[k].tasks = p.numel(), tasks
+        arr = hook._tensor_table(params)
         table = _table(n, dev, hook._cache)
         loss = torch.empty(1, dtype=torch.float64, device=dev)
         check(lib.nsgp_ewc_penalty(arr, n, float(hook.coeff), loss.data_ptr(), table.data_ptr(),
@@ -127,17 +124,21 @@ class _EwcPenalty(torch.autograd.Function):
         params = ctx.saved_tensors
         dev = params[0].device
         n = len(params)
-        grads = [torch.zeros_like(p) for p in params]
-        arr = (EwcTensor * n)()
-        for k, (p, g, (imp, old, tasks)) in enumerate(zip(params, grads, hook._stacks)):
-            arr[k].p, arr[k].importance, arr[k].old_params = p.data_ptr(), imp.data_ptr(), old.data_ptr()
-            arr[k].grad, arr[k].numel, arr[k].tasks = g.data_ptr(), p.numel(), tasks
+        # one zero-filled allocation for all gradients, handed back as views
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        arr = hook._tensor_table(params)
+        base, off = flat.data_ptr(), 0
+        for k in range(n):
+            arr[k].grad = base + 4 * off
+            off += sizes[k]
         go = gout.detach().to(torch.float32).reshape(1).contiguous()
         table = _table(n, dev, hook._cache)
         check(lib.nsgp_ewc_penalty_backward(arr, n, float(hook.coeff), go.data_ptr(),
                                             table.data_ptr(), table.numel(),
                                             _lib.current_stream(dev)),
               "nsgp_ewc_penalty_backward")
+        grads = [g.view(p.shape) for g, p in zip(flat.split(sizes), params)]
         return (None,) + tuple(grads)
 
 
@@ -175,6 +176,17 @@ class EWCHook:
                 stacks.append((imp, old, imp.shape[0]))
             self._stacks, self._stack_key = stacks, key
         return [self.reg_params[n] for n in names]
+
+    def _tensor_table(self, params):
+        """Host table of the registered tensors; rebuilt only when an address changes."""
+        key = tuple(p.data_ptr() for p in params)
+        if self._cache.get("arr_key") != key:
+            arr = (EwcTensor * len(params))()
+            for k, (p, (imp, old, tasks)) in enumerate(zip(params, self._stacks)):
+                arr[k].p, arr[k].importance, arr[k].old_params = p.data_ptr(), imp.data_ptr(), old.data_ptr()
+                arr[k].numel, arr[k].tasks = p.numel(), tasks
+            self._cache["arr"], self._cache["arr_key"] = arr, key
+        return self._cache["arr"]
 
     def penalty(self):
         params = self._prepare()
