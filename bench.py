@@ -20,7 +20,9 @@ One "step" = one pass of the hot path over one synthetic batch
 `e2e`     : same metric with HOST inputs: pinned image batch -> H2D -> stand-in
             detector forward with the covariance hooks registered -> SGDNSCL.step ->
             pinned RoI features -> H2D -> prototype build -> replay gather -> D2H of
-            the step's results.  (Includes the stand-in detector's torch/cuDNN
+            the step's results (replay input + weight checksums); the covariance
+            contraction of step i runs on the side stream under the forward of step
+            i+1 and is joined after the last step, inside the timed region.  (Includes the stand-in detector's torch/cuDNN
             forward, which is not part of the hot path - see e2e_breakdown_ms.)
 `--impl reference`: the oracle port of the reference's torch CPU path (the reference
             itself is pure Python and /root/reference does not exist on the GPU
@@ -548,15 +550,20 @@ def main():
             sgd_step()
             main.wait_stream(copy_stream)
             staged = repre_step(f_d, l_d)
-            hooks.join()             # the step's covariance update is complete before it is read
-            res = torch.stack([staged.sum(), staged[0, 0],
-                               hooks._layers[key0].acc[:16].sum(), named[-1][1].sum()])
+            # the step's results: the replay classifier input and the updated weights.  The
+            # covariance sums are an accumulation that nothing reads before the end of the
+            # pass (cal_fea_in, nsrunner_roi_replay.py:738-757): their contraction runs on the
+            # side stream under the next forward and is joined - inside the timed region -
+            # after the last step (timed() -> hooks.join()), where a checksum is read back.
+            res = torch.stack([staged.sum(), staged[0, 0], named[0][1].sum(), named[-1][1].sum()])
             res_h.copy_(res, non_blocking=True)
             n = proto.tmp_label.numel()
             lab_out_h[:n].copy_(proto.tmp_label, non_blocking=True)
             main.synchronize()
 
         e2e_ms, _ = timed(e2e_step, args.steps, max(1, args.warmup))
+        cov_check = float(hooks._layers[key0].acc[:16].sum())     # accumulated over all steps
+        assert cov_check == cov_check and cov_check != 0.0
         hooks.remove()
         e2e_ms_step = e2e_ms / args.steps
         # forward without hooks, for the breakdown

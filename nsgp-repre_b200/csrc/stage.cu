@@ -34,9 +34,12 @@ __device__ __forceinline__ void split_store4(float* hi, float* lo, float a, floa
 // Every staging routine is a __device__ body over an index span (first, step, end) so that
 // the same code runs as a stand-alone grid-stride kernel (per-layer entry points) and as
 // one work item of the grouped staging kernel (stage_group_kernel, end of this file).
+// I = index type: 32-bit arithmetic for the decode whenever the index space allows (a 64-bit
+// division is ~5x the instructions, and the gather routines are instruction-bound)
+template <typename I>
 __device__ __forceinline__ void
-stage_conv_body(const float* __restrict__ x, float* __restrict__ stage, const ConvGeom& g,
-                int B, long long hl_stride, long long first, long long step, long long end) {
+stage_conv_body_t(const float* __restrict__ x, float* __restrict__ stage, const ConvGeom& g,
+                  int B, long long hl_stride, long long first, long long step, long long end) {
   // one thread per aligned group of 4 staged columns (Ws % 4 == 0): the row decode is
   // paid once per float4 and both planes are written with 128-bit stores
   const int W4 = g.Ws >> 2;
@@ -45,9 +48,9 @@ stage_conv_body(const float* __restrict__ x, float* __restrict__ stage, const Co
   const float fb = (float)B;
   const int HWout = g.Hout * g.Wout;
   if (end > total) end = total;
-  for (long long idx = first; idx < end; idx += step) {
+  for (I idx = (I)first; idx < (I)end; idx += (I)step) {
     const int x4 = (int)(idx % W4);
-    long long rest = idx / W4;
+    I rest = idx / W4;
     const int r = (int)(rest % g.Hs);
     rest /= g.Hs;
     const int c = (int)(rest % g.Cs);
@@ -86,6 +89,17 @@ stage_conv_body(const float* __restrict__ x, float* __restrict__ stage, const Co
     float* o = stage + (((long long)copy * g.Cs + c) * g.Hs + r) * g.Ws + x4 * 4;
     split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
+}
+
+constexpr long long kIdx32Max = 0x7fffffffLL - (1LL << 24);   // room for one stride past the end
+__device__ __forceinline__ void
+stage_conv_body(const float* __restrict__ x, float* __restrict__ stage, const ConvGeom& g,
+                int B, long long hl_stride, long long first, long long step, long long end) {
+  const long long total = (long long)g.Cs * g.Hs * g.ncopy * (g.Ws >> 2);
+  if (total < kIdx32Max && step < (1LL << 24))
+    stage_conv_body_t<int>(x, stage, g, B, hl_stride, first, step, end);
+  else
+    stage_conv_body_t<long long>(x, stage, g, B, hl_stride, first, step, end);
 }
 
 __global__ void __launch_bounds__(256)
@@ -263,11 +277,12 @@ __device__ __forceinline__ long long ac_tiled_off(int s, int c, int r, int xs, i
   return tile * 4096 + (long long)(c & 127) * 32 + (xs & 31);
 }
 
+template <typename I>
 __device__ __forceinline__ void
-stage_autocorr_body(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
-                    int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
-                    float* __restrict__ rowbuf, long long first, long long step,
-                    long long end) {
+stage_autocorr_body_t(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                      int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
+                      float* __restrict__ rowbuf, long long first, long long step,
+                      long long end) {
   // plane layout: [3][C][Hs][Ws];  tiled layout: [3][CB*128][Hs][NS*32] tile-major, plus the
   // two edge rows of every copy in plain layout rowbuf[e][s][c][Wr]
   const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Wr = (W + 3) & ~3;
@@ -276,9 +291,9 @@ stage_autocorr_body(const float* __restrict__ x, float* __restrict__ stage, int 
   const long long img = (long long)C * H * W;
   const float fb = (float)B;
   if (end > total) end = total;
-  for (long long idx = first; idx < end; idx += step) {
+  for (I idx = (I)first; idx < (I)end; idx += (I)step) {
     int xs = (int)(idx % Wc);
-    long long rest = idx / Wc;
+    I rest = idx / Wc;
     int r = (int)(rest % Hs);
     rest /= Hs;
     int c = (int)(rest % Cc);
@@ -308,6 +323,19 @@ stage_autocorr_body(const float* __restrict__ x, float* __restrict__ stage, int 
       }
     }
   }
+}
+
+__device__ __forceinline__ void
+stage_autocorr_body(const float* __restrict__ x, float* __restrict__ stage, int C, int H,
+                    int W, int Hs, int Ws, int B, long long hl_stride, int tiled,
+                    float* __restrict__ rowbuf, long long first, long long step,
+                    long long end) {
+  const int CB = (C + 127) >> 7, NS = (W + 31) >> 5;
+  const long long total = 3LL * (tiled ? CB * 128 : C) * Hs * (tiled ? NS * 32 : Ws);
+  if (total < kIdx32Max && step < (1LL << 24))
+    stage_autocorr_body_t<int>(x, stage, C, H, W, Hs, Ws, B, hl_stride, tiled, rowbuf, first, step, end);
+  else
+    stage_autocorr_body_t<long long>(x, stage, C, H, W, Hs, Ws, B, hl_stride, tiled, rowbuf, first, step, end);
 }
 
 __global__ void __launch_bounds__(256)
@@ -473,10 +501,11 @@ stage_autocorr_edges_kernel(const float* __restrict__ x, float* __restrict__ col
 // Rows are written directly in the reference's (Cin, kh, kw) order.
 // stage[hl][row][k],  row < d, k < Hout*Wout, pitch Ws.
 // ---------------------------------------------------------------------------
+template <typename I>
 __device__ __forceinline__ void
-stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
-                         const ConvGeom& g, int B, long long hl_stride, long long first,
-                         long long step, long long end) {
+stage_conv_explicit_body_t(const float* __restrict__ x, float* __restrict__ stage,
+                           const ConvGeom& g, int B, long long hl_stride, long long first,
+                           long long step, long long end) {
   // index = (im2col row (c, i, j), group of 4 K columns)
   const long long img = (long long)g.C * g.H * g.W;
   const int taps = g.kh * g.kw;
@@ -486,9 +515,9 @@ stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
   const int W4 = g.Ws >> 2;
   const long long total = (long long)g.Cs * W4;
   if (end > total) end = total;
-  for (long long idx = first; idx < end; idx += step) {
+  for (I idx = (I)first; idx < (I)end; idx += (I)step) {
     const int row = (int)(idx / W4);
-    const int k4 = (int)(idx - (long long)row * W4);
+    const int k4 = (int)(idx - (I)row * W4);
     const int c = row / taps, t = row - c * taps;
     const int i = t / g.kw, j = t - i * g.kw;
     const bool row_ok = row < d;
@@ -512,6 +541,17 @@ stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
     float* o = stage + (long long)row * g.Ws + k;
     split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
+}
+
+__device__ __forceinline__ void
+stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
+                         const ConvGeom& g, int B, long long hl_stride, long long first,
+                         long long step, long long end) {
+  const long long total = (long long)g.Cs * (g.Ws >> 2);
+  if (total < kIdx32Max && step < (1LL << 24))
+    stage_conv_explicit_body_t<int>(x, stage, g, B, hl_stride, first, step, end);
+  else
+    stage_conv_explicit_body_t<long long>(x, stage, g, B, hl_stride, first, step, end);
 }
 
 __global__ void __launch_bounds__(256)
