@@ -28,7 +28,8 @@ __version__ = "0.1.0"
 from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
 from .covariance import CovarianceHooks, BRNullSpaceCovariance  # noqa: F401
 from .optim import SGDNSCL  # noqa: F401
-from .prototypes import MultiPrototypeReplay, StandardMultiPrototypeReplayHead  # noqa: F401
+from .prototypes import (MultiPrototypeReplay, StandardMultiPrototypeReplayHead,  # noqa: F401
+                         kmeans_prototypes)
 from .rois import all_gather_different_shape, RoIHarvest  # noqa: F401
 from .roi_extract import SingleRoIExtractor  # noqa: F401
 from .ewc import EWCHook, EWCImportance, register_params  # noqa: F401

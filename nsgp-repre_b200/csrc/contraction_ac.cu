@@ -37,7 +37,17 @@ constexpr int SA = 3;                       // A ring stages (upper bound; run-t
 constexpr int SB = 4;                       // B ring stages (3 in the window + 1 in flight)
 constexpr uint32_t kPlane = BM * BK * 4;    // 16 KB: one hi or lo plane of a tile
 constexpr uint32_t kTile = 2 * kPlane;      // hi | lo
-constexpr int kRowsPerItem = 48;
+// rows per work item = accumulation chain of 12 steps per row (bias of the truncating tensor-core
+// accumulate ~1.9e-8 per step); NSGP_AC_ROWS overrides for experiments
+static int rows_per_item() {
+  static const int v = [] {
+    const char* e = getenv("NSGP_AC_ROWS");
+    const int r = e ? atoi(e) : 48;
+    return r >= 4 && r <= 256 ? r : 48;
+  }();
+  return v;
+}
+#define kRowsPerItem rows_per_item()
 constexpr int kThreadsAc = 224;             // 7 warps: B producer, MMA, 4 epilogue, A producer
 constexpr size_t kSmemAc = (size_t)(SA + SB) * kTile + 1024 + 256;
 

@@ -333,6 +333,43 @@ class MultiPrototypeReplay:
         return out
 
 
+@torch.no_grad()
+def kmeans_prototypes(feats: torch.Tensor, init_centres: torch.Tensor, iters: int = 10):
+    """Extension (BASELINE north_star item 3; the reference imports sklearn's KMeans at
+    standard_roi_replay_head.py:18 and never calls it - parity unpinned, checked against
+    ``oracle.restated.kmeans_assign / kmeans_update``): Lloyd iterations from explicit
+    initial centres, entirely on the device.  Assignment = argmin_k |x - c_k|^2 (ties ->
+    lowest k) through the tcgen05 contraction X C^T, update = segmented mean of the rows of
+    every cluster (an empty cluster keeps its centre).  Returns (centres (k,D), labels (n,))."""
+    _lib.require_cuda(feats, "features")
+    dev = feats.device
+    x = feats.detach().reshape(feats.shape[0], -1)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    n, D = x.shape
+    centres = init_centres.detach().to(device=dev, dtype=torch.float32).reshape(-1, D).clone()
+    k = centres.shape[0]
+    stream = _lib.current_stream(dev)
+    ws = torch.empty(int(lib.repre_kmeans_assign_workspace_bytes(n, k, D)), dtype=torch.uint8,
+                     device=dev)
+    labels = torch.empty(n, dtype=torch.int64, device=dev)
+    counts = torch.empty(k, dtype=torch.int32, device=dev)
+    offsets = torch.empty(k + 1, dtype=torch.int32, device=dev)
+    rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    new = torch.empty_like(centres)
+    for _ in range(max(1, int(iters))):
+        check(lib.repre_kmeans_assign(ptr(x), n, D, ptr(centres), k, ptr(labels), ptr(ws),
+                                      ws.numel(), stream), "repre_kmeans_assign")
+        check(lib.repre_class_index(ptr(labels), n, k, ptr(counts), ptr(offsets), ptr(rows),
+                                    stream), "repre_class_index")
+        check(lib.repre_segment_mean(ptr(x), D, ptr(offsets), ptr(rows), k, n, ptr(new), stream),
+              "repre_segment_mean")
+        centres = torch.where((counts > 0).unsqueeze(1), new, centres)
+    check(lib.repre_kmeans_assign(ptr(x), n, D, ptr(centres), k, ptr(labels), ptr(ws),
+                                  ws.numel(), stream), "repre_kmeans_assign")
+    return centres, labels
+
+
 class StandardMultiPrototypeReplayHead(nn.Module):
     """Constructor keywords and attributes of the reference head (:377-390):
     ``previous_path, task_id, task_split, max_prototype, work_dir``; attributes

@@ -570,6 +570,25 @@ def test_kmeans_assign_extension(pkg, engine):
     assert torch.equal(lab.cpu(), want)
 
 
+def test_kmeans_prototypes_extension(pkg):
+    """Lloyd iterations on the device (assign + segmented-mean update, an empty cluster keeps
+    its centre) against the plain-torch definition; parity unpinned by the reference."""
+    g = torch.Generator().manual_seed(8)
+    n, k, D = 700, 9, 12544
+    true = torch.randn(k - 1, D, generator=g)
+    x = true[torch.randint(0, k - 1, (n,), generator=g)] + 0.6 * torch.randn(n, D, generator=g)
+    init = torch.cat([x[torch.randperm(n, generator=g)[:k - 1]], 50.0 + torch.randn(1, D, generator=g)])
+    cent = init.double()
+    for _ in range(4):
+        lab, _ = O.kmeans_assign(x.double(), cent)
+        cent = O.kmeans_update(x.double(), lab, k, cent)
+    want_lab, _ = O.kmeans_assign(x.double(), cent)
+    got_c, got_l = pkg.kmeans_prototypes(x.cuda(), init.cuda(), iters=4)
+    assert torch.equal(got_l.cpu(), want_lab)
+    assert rel_fro(got_c, cent) < 1e-5
+    assert torch.equal(got_c[k - 1].cpu(), init[k - 1])          # the far-away centre stayed empty
+
+
 def test_head_loss_adds_replay_loss(pkg, tmp_path):
     """StandardMultiPrototypeReplayHead drop-in: artifacts in, mask.pth out,
     replay_loss_cls equal to the oracle's double-softmax CE (:497-499)."""
