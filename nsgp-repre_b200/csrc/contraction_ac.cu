@@ -47,7 +47,6 @@ static int rows_per_item() {
   }();
   return v;
 }
-#define kRowsPerItem rows_per_item()
 constexpr int kThreadsAc = 224;             // 7 warps: B producer, MMA, 4 epilogue, A producer
 constexpr size_t kSmemAc = (size_t)(SA + SB) * kTile + 1024 + 256;
 
@@ -337,7 +336,7 @@ size_t autocorr_table_bytes(const ConvGeom* geoms, int n) {
   for (int i = 0; i < n; ++i) {
     const ConvGeom& g = geoms[i];
     const size_t t = (size_t)ceil_div(g.C, BM);
-    items += 5 * t * t * (size_t)ceil_div(g.W, BK) * (size_t)ceil_div(g.H, kRowsPerItem);
+    items += 5 * t * t * (size_t)ceil_div(g.W, BK) * (size_t)ceil_div(g.H, rows_per_item());
   }
   return (size_t)n * sizeof(AcProblem) + items * sizeof(AcItem) + 1024;
 }
@@ -377,8 +376,8 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
       NSGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (autocorr) failed (%d)", (int)r);
     }
     const int strips = ceil_div(g.W, BK);
-    for (int u0 = 0; u0 < g.H; u0 += kRowsPerItem) {
-      const int u1 = u0 + kRowsPerItem < g.H ? u0 + kRowsPerItem : g.H;
+    for (int u0 = 0; u0 < g.H; u0 += rows_per_item()) {
+      const int u1 = u0 + rows_per_item() < g.H ? u0 + rows_per_item() : g.H;
       for (int st = 0; st < strips; ++st)
         for (int pass = 0; pass < 5; ++pass)
           for (int rb = 0; rb < p.tiles; ++rb)

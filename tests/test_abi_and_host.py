@@ -131,3 +131,38 @@ def test_roi_harvest_single_process_merge_and_reserve(tmp_path):
         assert src.numel() == 1 and int(cls[src]) == int(out[1][i])
     again = torch.load(str(tmp_path / "rois_etc.pth"))
     assert isinstance(again, list) and len(again) == 6 and torch.equal(again[0], out[0])
+
+
+# ----------------------------------------------------------------- SURVEY 8(f) host logic
+def test_f_rows_host_logic_and_no_cpu_fallback(golden_dir):
+    """CPU-side pieces of the 8(f) drop-ins: parameter registration rule (:1006-1031), the
+    level-mapping rule against the reference's own map_roi_levels, and host tensors are
+    rejected by every compute entry point."""
+    import nsgp_repre_b200 as pkg
+    from oracle import synth
+    net = synth.ToyBNNet()
+    reg = pkg.register_params(net)
+    assert list(reg) == ["bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias",
+                         "layer_bn_named.weight", "layer_bn_named.bias"]
+    assert pkg.register_params(net, must_names=()) .keys() == \
+        {n for n, _ in net.named_parameters() if "teacher_model" not in n}
+    g = torch.load(os.path.join(golden_dir, "roi_extract.pt"), weights_only=False)
+    feats, rois, labels = synth.roi_case(g["seed"])
+    ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), 16,
+                                 [4, 8, 16, 32])
+    assert torch.equal(ext.map_roi_levels(rois, 4), g["levels"])
+    with pytest.raises(pkg._lib.NsgpError):
+        ext(feats, rois)
+    gt_b, gt_l, ps_b, ps_s, ps_l = synth.pseudo_label_case(0)
+    with pytest.raises(pkg._lib.NsgpError):
+        pkg.merge_pseudo_labels(gt_b, gt_l, ps_b, ps_s, ps_l)
+    acc = pkg.EWCImportance(reg)
+    for p in reg.values():
+        p.grad = torch.ones_like(p)
+    with pytest.raises(pkg._lib.NsgpError):
+        acc.accumulate(2, 3)
+    terms = acc.finish(None)
+    assert set(terms) == {"importance", "task_param"} and terms["importance"]["bn1.weight"][0].shape == (1, 8)
+    hook = pkg.EWCHook(net, reg, terms)
+    with pytest.raises(pkg._lib.NsgpError):
+        hook.penalty()
