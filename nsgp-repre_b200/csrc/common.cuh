@@ -101,6 +101,11 @@ struct Operand {
   int K;                   // valid columns
   int rows;                // valid virtual rows (<= T*Cs)
   long long tap_off[kMaxTaps];   // element offset of tap t (% 4 == 0)
+  int tile_nkb;            // > 0 (T == 1 only): tile-major storage - element (r, k) lives at
+                           // ((r/128) * tile_nkb + k/32) * 4096 + (r%128) * 32 + k%32, i.e. every
+                           // 128-row x 32-column TMA box is one contiguous 16 KB tile (TMA
+                           // sustains > 2x the bytes/cycle of 128 scattered 128-byte rows);
+                           // columns K .. 32*tile_nkb are stored as zeros
 };
 
 // Epilogue of the contraction engines.

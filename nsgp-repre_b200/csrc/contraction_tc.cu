@@ -191,16 +191,20 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
         const int r0 = pf_it.rb * TILE + rank * BM;
         for (int r = r0; r < r0 + BM && r < q.A.rows; r += q.A.br) {
           const int t = r / q.A.Cs, c = r - t * q.A.Cs;
-          tma_prefetch_2d_elect(&pf_it.maps->a[0][t], kx, c);
-          tma_prefetch_2d_elect(&pf_it.maps->a[1][t], kx, c);
+          const int px = q.A.tile_nkb ? 0 : kx;
+          const int py = q.A.tile_nkb ? (((c >> 7) * q.A.tile_nkb + pf_kb) << 7) + (c & 127) : c;
+          tma_prefetch_2d_elect(&pf_it.maps->a[0][t], px, py);
+          tma_prefetch_2d_elect(&pf_it.maps->a[1][t], px, py);
         }
       }
       if (pb) {
         const int c0 = pf_it.cb * TILE + rank * BM;
         for (int r = c0; r < c0 + BM && r < q.B.rows; r += q.B.br) {
           const int t = r / q.B.Cs, c = r - t * q.B.Cs;
-          tma_prefetch_2d_elect(&pf_it.maps->b[0][t], kx, c);
-          tma_prefetch_2d_elect(&pf_it.maps->b[1][t], kx, c);
+          const int px = q.B.tile_nkb ? 0 : kx;
+          const int py = q.B.tile_nkb ? (((c >> 7) * q.B.tile_nkb + pf_kb) << 7) + (c & 127) : c;
+          tma_prefetch_2d_elect(&pf_it.maps->b[0][t], px, py);
+          tma_prefetch_2d_elect(&pf_it.maps->b[1][t], px, py);
         }
       }
       if (++pf_kb >= pf_it.kb1) {
@@ -216,8 +220,8 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
       const int r0 = it.rb * TILE + rank * BM;    // this CTA's A rows
       const int c0 = it.cb * TILE + rank * BM;    // the B rows this CTA stages
       const bool share = p.gram && p.same_operand && it.rb == it.cb;
-      const int a_rows = p.A.rows, a_br = p.A.br, a_cs = p.A.Cs;
-      const int b_rows = p.B.rows, b_br = p.B.br, b_cs = p.B.Cs;
+      const int a_rows = p.A.rows, a_br = p.A.br, a_cs = p.A.Cs, a_tn = p.A.tile_nkb;
+      const int b_rows = p.B.rows, b_br = p.B.br, b_cs = p.B.Cs, b_tn = p.B.tile_nkb;
       const int segs_a = seg_count(r0, a_rows, a_br);
       const int segs_b = share ? 0 : seg_count(c0, b_rows, b_br);
       // bytes landing on this CTA's full barrier per stage; full boxes always count
@@ -237,15 +241,19 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
           const int r = r0 + s * a_br;
           const int t = r / a_cs, c = r - t * a_cs;
           const uint32_t off = (uint32_t)(s * a_br) * (BK * 4);
-          tma_load_2d_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], kx0, c);
-          if (!(dbg & 4)) tma_load_2d_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], kx0, c);
+          const int lx = a_tn ? 0 : kx0;
+          const int ly = a_tn ? (((c >> 7) * a_tn + kb) << 7) + (c & 127) : c;
+          tma_load_2d_elect(sbase + off, &it.maps->a[0][t], &full_bar[stage], lx, ly);
+          if (!(dbg & 4)) tma_load_2d_elect(sbase + kABytes + off, &it.maps->a[1][t], &full_bar[stage], lx, ly);
         }
         for (int s = 0; s < segs_b; ++s) {
           const int r = c0 + s * b_br;
           const int t = r / b_cs, c = r - t * b_cs;
           const uint32_t off = (uint32_t)(s * b_br) * (BK * 4);
-          tma_load_2d_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], kx0, c);
-          if (!(dbg & 4)) tma_load_2d_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], kx0, c);
+          const int lx = b_tn ? 0 : kx0;
+          const int ly = b_tn ? (((c >> 7) * b_tn + kb) << 7) + (c & 127) : c;
+          tma_load_2d_elect(sbase + 2 * kABytes + off, &it.maps->b[0][t], &full_bar[stage], lx, ly);
+          if (!(dbg & 4)) tma_load_2d_elect(sbase + 3 * kABytes + off, &it.maps->b[1][t], &full_bar[stage], lx, ly);
         }
         if (dbg & 1) c_issue += clock64() - t1;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -457,6 +465,11 @@ int encode_operand(const Operand& o, int br, CUtensorMap (*dst)[kMaxTaps]) {
                    "tcgen05 engine: operand base must be 16-byte aligned");
       cuuint64_t gdim[2] = {(cuuint64_t)o.K, (cuuint64_t)o.Cs};
       cuuint64_t gstr[1] = {(cuuint64_t)o.row_pitch * 4};
+      if (o.tile_nkb > 0) {            // tile-major: a (32, row blocks * K blocks * 128) matrix
+        gdim[0] = BK;
+        gdim[1] = (cuuint64_t)ceil_div(o.Cs, 128) * o.tile_nkb * 128;
+        gstr[0] = BK * 4;
+      }
       cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)br};
       cuuint32_t estr[2] = {1, 1};
       CUresult r = enc(&dst[hl][t], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr,
@@ -471,6 +484,7 @@ int encode_operand(const Operand& o, int br, CUtensorMap (*dst)[kMaxTaps]) {
 
 void fill_operand(const Operand& o, int br, TcOperand* d) {
   d->T = o.T; d->Cs = o.Cs; d->rows = o.rows; d->br = br;
+  d->tile_nkb = o.tile_nkb; d->pad0 = d->pad1 = d->pad2 = 0;
 }
 
 constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 + 256;
@@ -571,6 +585,9 @@ int build_problem(const ContractionArgs& a, bool pair, TcProblem* out) {
                "tcgen05 engine: row pitch must be 16-byte");
   NSGP_REQUIRE(ceil_div(a.A.K, BK) == ceil_div(a.B.K, BK),
                "contraction: operands disagree on K blocks");
+  NSGP_REQUIRE((a.A.tile_nkb == 0 || (a.A.T == 1 && a.A.tile_nkb == ceil_div(a.A.K, BK))) &&
+                   (a.B.tile_nkb == 0 || (a.B.T == 1 && a.B.tile_nkb == ceil_div(a.B.K, BK))),
+               "tcgen05 engine: tile-major operands are single-tap with tile_nkb = K blocks");
   const int br_a = pick_box_rows(a.A), br_b = pick_box_rows(a.B);
   NSGP_REQUIRE(br_a > 0 && br_b > 0, "tcgen05 engine: operand rows per tap must be >= 8 "
                "(multiple of 8 when taps > 1)");

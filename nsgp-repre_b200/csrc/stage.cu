@@ -86,6 +86,19 @@ stage_conv_body_t(const float* __restrict__ x, float* __restrict__ stage, const 
       }
       v[e] = acc;
     }
+    if (g.ftiled) {
+      // tile-major single-tap operand (flat mode: copy = r = 0): 4 columns of one tile row,
+      // and the zero K tail of the row's last K block from the thread that ends the row
+      const int nkb = (HWout + 31) >> 5;
+      float* o = stage + ft_off(c, x4 * 4, nkb);
+      split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
+      if (x4 == W4 - 1)
+        for (int k = (x4 + 1) * 4; k < nkb * 32; k += 4) {
+          float* z = stage + ft_off(c, k, nkb);
+          split_store4(z, z + hl_stride, 0.f, 0.f, 0.f, 0.f);
+        }
+      continue;
+    }
     float* o = stage + (((long long)copy * g.Cs + c) * g.Hs + r) * g.Ws + x4 * 4;
     split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
@@ -113,12 +126,14 @@ stage_conv_kernel(const float* __restrict__ x, float* __restrict__ stage, ConvGe
 // ---------------------------------------------------------------------------
 // 1x1 stride-1 conv input with H*W % 4 == 0: the staged plane is the batch mean of
 // x itself.  One thread per float4.
+// K4 > 0: tile-major destination (geometry.h ftiled), K4 = float4 groups per row (H*W/4)
 template <int B_UNROLL>
 __device__ __forceinline__ void
 stage_flat_vec_body(const float* __restrict__ x, float* __restrict__ stage, long long n4,
                     int B, long long img, long long hl_stride, long long first, long long step,
-                    long long end) {
+                    long long end, int K4 = 0) {
   const float inv_div = (float)B;
+  const int nkb = (K4 * 4 + 31) >> 5;
   if (end > n4) end = n4;
   for (long long i = first; i < end; i += step) {
     const float* p = x + i * 4;
@@ -135,6 +150,17 @@ stage_flat_vec_body(const float* __restrict__ x, float* __restrict__ stage, long
       float4 v = ldg_stream4(p + (long long)b * img);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    if (K4 > 0) {
+      const int c = (int)(i / K4), k4 = (int)(i - (long long)c * K4);
+      float* o = stage + ft_off(c, k4 * 4, nkb);
+      split_store4(o, o + hl_stride, s.x / inv_div, s.y / inv_div, s.z / inv_div, s.w / inv_div);
+      if (k4 == K4 - 1)
+        for (int k = K4 * 4; k < nkb * 32; k += 4) {
+          float* z = stage + ft_off(c, k, nkb);
+          split_store4(z, z + hl_stride, 0.f, 0.f, 0.f, 0.f);
+        }
+      continue;
+    }
     split_store4(stage + i * 4, stage + i * 4 + hl_stride, s.x / inv_div, s.y / inv_div,
                  s.z / inv_div, s.w / inv_div);
   }
@@ -143,8 +169,8 @@ stage_flat_vec_body(const float* __restrict__ x, float* __restrict__ stage, long
 template <int B_UNROLL>
 __global__ void __launch_bounds__(256)
 stage_flat_vec_kernel(const float* __restrict__ x, float* __restrict__ stage, long long n4,
-                      int B, long long img, long long hl_stride) {
-  stage_flat_vec_body<B_UNROLL>(x, stage, n4, B, img, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, n4);
+                      int B, long long img, long long hl_stride, int K4) {
+  stage_flat_vec_body<B_UNROLL>(x, stage, n4, B, img, hl_stride, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, n4, K4);
 }
 
 // Batch mean of x (B, n) -> out (n), n % 4 == 0, 16-byte aligned: first pass of the
@@ -538,6 +564,17 @@ stage_conv_explicit_body_t(const float* __restrict__ x, float* __restrict__ stag
       v[e] = acc;
       if (++ox == g.Wout) { ox = 0; ++oy; }
     }
+    if (g.ftiled) {
+      const int nkb = (K + 31) >> 5;
+      float* o = stage + ft_off(row, k, nkb);
+      split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
+      if (k4 == W4 - 1)
+        for (int kz = k + 4; kz < nkb * 32; kz += 4) {
+          float* z = stage + ft_off(row, kz, nkb);
+          split_store4(z, z + hl_stride, 0.f, 0.f, 0.f, 0.f);
+        }
+      continue;
+    }
     float* o = stage + (long long)row * g.Ws + k;
     split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
   }
@@ -641,7 +678,8 @@ int launch_stage_conv(const float* x, float* stage, const ConvGeom& g, int B,
     long long n4 = (long long)g.C * g.H * g.W / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    stage_flat_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, n4, B, img, hl);
+    stage_flat_vec_kernel<8><<<blocks, 256, 0, stream>>>(x, stage, n4, B, img, hl,
+                                                        g.ftiled ? g.H * g.W / 4 : 0);
   } else if (g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 &&
              g.ph == 1 && g.pw == 1 && aligned && g.W % 4 == 0) {
     long long n = (long long)g.C * g.Hs * (g.W / 4);
@@ -702,7 +740,8 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
     const long long img = (long long)g.C * g.H * g.W;
     switch (it.kind) {
       case kStFlatVec:
-        stage_flat_vec_body<8>(x, j.stage, img / 4, Bx, img, j.hl, first, step, end);
+        stage_flat_vec_body<8>(x, j.stage, img / 4, Bx, img, j.hl, first, step, end,
+                               g.ftiled ? g.H * g.W / 4 : 0);
         break;
       case kStAcVec:
         stage_autocorr_vec_body<8>(x, j.stage, g.C, g.H, g.W, Bx, j.hl, g.tiled,

@@ -18,6 +18,7 @@ struct alignas(64) TcMaps {
 
 struct TcOperand {
   int T, Cs, rows, br;            // taps, rows per tap, valid rows, rows per TMA box
+  int tile_nkb, pad0, pad1, pad2; // > 0: tile-major storage (common.cuh Operand::tile_nkb)
 };
 
 struct TcParams {

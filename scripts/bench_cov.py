@@ -69,6 +69,14 @@ def counters():
     c = np.array(list(buf), dtype=np.float64).reshape(148, 8)
     tot = c[:, 7].mean()
     st = max(1.0, c[:, 4].mean())
+    buf2 = (ctypes.c_ulonglong * n)()
+    _lib.check(_lib.lib.nsgp_debug_read_counters(buf2, n), "counters")
+    g = np.array(list(buf2), dtype=np.float64).reshape(148, 8)
+    gt = g[:, 5].mean()
+    if gt > 0:
+        print("   generic kernel per-CTA cycles: mean %.0f max %.0f min %.0f | MMA warp: wait-operands %.0f%% issue %.0f%% wait-accum %.0f%% | producer: wait-stage %.0f%% issue %.0f%% | %.0f K blocks -> %.0f cycles/K-block" %
+              (gt, g[:, 5].max(), g[:, 5].min(), 100 * g[:, 0].mean() / gt, 100 * g[:, 1].mean() / gt, 100 * g[:, 2].mean() / gt,
+               100 * g[:, 3].mean() / gt, 100 * g[:, 4].mean() / gt, g[:, 6].mean(), gt / max(1.0, g[:, 6].mean())))
     print("   AC kernel per-CTA cycles: mean %.0f max %.0f min %.0f (%.2f ms at 1.965 GHz), %.0f cycles/row step | MMA warp: wait-A %.0f%% wait-B %.0f%% wait-epi %.0f%% issue %.0f%%" %
           (tot, c[:, 7].max(), c[:, 7].min(), tot / 1.965e6, tot / st, 100 * c[:, 0].mean() / tot, 100 * c[:, 1].mean() / tot,
            100 * c[:, 2].mean() / tot, 100 * c[:, 3].mean() / tot))
