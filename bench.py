@@ -174,7 +174,10 @@ def cpu_reference_rate(layers, budget_s, feats=None, labels=None, threads=None):
     order = sorted(layers, key=lambda r: r["cov_flops"])
     assumed_rate = 0.35e12 * max(1, threads) / 8          # FLOP/s guess, only for sizing
     picked, est = [], 0.0
-    step = max(1, len(order) // 12)
+    total_est = sum(r["cov_flops"] + r["proj_flops"] for r in order) / assumed_rate
+    # the whole step when it fits the budget (it does on a 16-core host: ~3 s), else every
+    # k-th layer by cost
+    step = 1 if total_est <= budget_s else max(1, len(order) // 12)
     for r in order[::step]:
         cost = (r["cov_flops"] + r["proj_flops"]) / assumed_rate
         if est + cost > budget_s and picked:
@@ -205,9 +208,11 @@ def cpu_reference_rate(layers, budget_s, feats=None, labels=None, threads=None):
         t0 = time.perf_counter()
         O.build_prototypes(feats, labels, range(OLD_CLASSES), 10)
         proto_s = time.perf_counter() - t0
+    names = "all layers of the step" if len(picked) == len(layers) else \
+        ", ".join(r["name"] for r in picked)
     desc = ("oracle port (torch CPU fp32) of compute_cov/update_cov + projection on %d of %d "
             "layers [%s], B=1 (covariance FLOPs do not depend on B)" %
-            (len(picked), len(layers), ", ".join(r["name"] for r in picked)))
+            (len(picked), len(layers), names))
     return flops / secs / 1e12, threads, desc, secs, proto_s
 
 
