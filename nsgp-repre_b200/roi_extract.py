@@ -8,6 +8,11 @@ sync per level), calls mmcv's RoIAlign and scatters the result back.  Here ONE l
 handles all levels, and ``class_sums`` adds the features straight into the per-class sums
 of the coarse prototypes (standard_roi_replay_head.py:411-415) without writing the
 (R, 12544) feature matrix.
+
+Forward only: this is the extractor of the no-grad paths - ``get_bbox_stuff`` during the RoI
+harvest (``cal_rois``, nsrunner_roi_replay.py:776-868) and the teacher's ``predict`` - where
+the reference runs it under ``torch.no_grad()``.  The training forward/backward of the RoI
+head keeps mmcv's differentiable op.
 """
 from __future__ import annotations
 
