@@ -327,6 +327,14 @@ int repre_roi_align(const float* const* feats /* host */, const int32_t* heights
                     const int64_t* labels, int n_classes, float* roi_feats, float* class_sums,
                     int32_t* class_counts, void* stream);
 
+/* gradient of repre_roi_align w.r.t. the feature maps: grad_feats[l] (batch, channels, H_l, W_l),
+ * zero-filled (or holding a gradient to add to) by the caller, accumulated into with atomics */
+int repre_roi_align_backward(float* const* grad_feats /* host */, const int32_t* heights,
+                             const int32_t* widths, const float* spatial_scales, int n_levels,
+                             int batch, int channels, const float* rois, int n_rois, int pooled,
+                             int sampling_ratio, int aligned, float finest_scale,
+                             const float* grad_out, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * SURVEY 8(f)-4  EWC importance and penalty
  *   replaces the per-tensor loops of BRNullSpaceRunner.calculate_save_importance

@@ -162,6 +162,83 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
   }
 }
 
+// Backward of the same pooling: d feat[Y][X] += Wy[ph][Y] * Wx[pw][X] * d out[c][ph][pw] / count
+// (the transpose of the separable forward; atomics because RoIs and bins overlap).
+__global__ void __launch_bounds__(256)
+roi_align_backward_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int pooled,
+                          int sampling_ratio, int aligned, float finest_scale,
+                          const float* __restrict__ grad_out, int ch_per_block) {
+  __shared__ AxisTable ty, tx;
+  __shared__ int s_fallback;
+  const int r = blockIdx.x;
+  const float* roi = rois + (long long)r * 5;
+  const int b = (int)roi[0];
+  const int l = lv.n > 1 ? roi_level(roi, finest_scale, lv.n) : 0;
+  const int H = lv.H[l], W = lv.W[l];
+  const float sc = lv.scale[l], off = aligned ? 0.5f : 0.f;
+  const float sw = roi[1] * sc - off, sh = roi[2] * sc - off;
+  const float ew = roi[3] * sc - off, eh = roi[4] * sc - off;
+  float rw = ew - sw, rh = eh - sh;
+  if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+  const float bin_h = rh / (float)pooled, bin_w = rw / (float)pooled;
+  const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)pooled);
+  const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)pooled);
+  const float count = fmaxf((float)(gh * gw), 1.f);
+  const int bins = pooled * pooled;
+  const int c0 = blockIdx.y * ch_per_block;
+  const int c1 = min(channels, c0 + ch_per_block);
+  if (threadIdx.x == 0) s_fallback = pooled > kMaxPooled ? 1 : 0;
+  __syncthreads();
+  if (pooled <= kMaxPooled) {
+    bool ok = true;
+    if (threadIdx.x < pooled) ok = build_axis(ty, threadIdx.x, sh, bin_h, gh, H);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + pooled)
+      ok = build_axis(tx, threadIdx.x - 32, sw, bin_w, gw, W);
+    if (!ok) s_fallback = 1;
+  }
+  __syncthreads();
+  const bool direct = s_fallback != 0;
+  const long long D = (long long)channels * bins;
+  for (int e = threadIdx.x; e < (c1 - c0) * bins; e += 256) {
+    const int c = c0 + e / bins, bin = e - (e / bins) * bins;
+    const int ph = bin / pooled, pw = bin - ph * pooled;
+    float* f = const_cast<float*>(lv.feat[l]) + ((long long)b * channels + c) * H * W;
+    const float g = grad_out[(long long)r * D + (long long)c * bins + bin] / count;
+    if (g == 0.f) continue;
+    if (!direct) {
+      const int ny = ty.n[ph], nx = tx.n[pw];
+      float* f0 = f + (long long)ty.first[ph] * W + tx.first[pw];
+      for (int j = 0; j < ny; ++j) {
+        const float wy = ty.w[ph][j] * g;
+        if (wy == 0.f) continue;
+        for (int i = 0; i < nx; ++i) {
+          const float w = wy * tx.w[pw][i];
+          if (w != 0.f) atomicAdd(f0 + j * W + i, w);
+        }
+      }
+    } else {
+      for (int iy = 0; iy < gh; ++iy) {
+        float y = sh + (float)ph * bin_h + ((float)iy + .5f) * bin_h / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          float x = sw + (float)pw * bin_w + ((float)ix + .5f) * bin_w / (float)gw;
+          float yy = y;
+          if (yy < -1.0f || yy > (float)H || x < -1.0f || x > (float)W) continue;
+          if (yy <= 0.f) yy = 0.f;
+          if (x <= 0.f) x = 0.f;
+          int y_low = (int)yy, x_low = (int)x, y_high, x_high;
+          if (y_low >= H - 1) { y_high = y_low = H - 1; yy = (float)y_low; } else { y_high = y_low + 1; }
+          if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else { x_high = x_low + 1; }
+          const float ly = yy - (float)y_low, lx = x - (float)x_low, hy = 1.f - ly, hx = 1.f - lx;
+          atomicAdd(f + y_low * W + x_low, g * hy * hx);
+          atomicAdd(f + y_low * W + x_high, g * hy * lx);
+          atomicAdd(f + y_high * W + x_low, g * ly * hx);
+          atomicAdd(f + y_high * W + x_high, g * ly * lx);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace nsgp
 
 using namespace nsgp;
@@ -202,6 +279,37 @@ extern "C" int repre_roi_align(const float* const* feats, const int32_t* heights
   roi_align_kernel<<<grid, 256, 0, stream>>>(lv, channels, rois, pooled, sampling_ratio, aligned,
                                              finest_scale, (const long long*)labels, n_classes,
                                              roi_feats, class_sums, class_counts, ch_per_block);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+extern "C" int repre_roi_align_backward(float* const* grad_feats, const int32_t* heights,
+                                        const int32_t* widths, const float* spatial_scales,
+                                        int n_levels, int batch, int channels, const float* rois,
+                                        int n_rois, int pooled, int sampling_ratio, int aligned,
+                                        float finest_scale, const float* grad_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(grad_feats && heights && widths && spatial_scales, "roi_align_backward: null level tables");
+  NSGP_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "roi_align_backward: 1..%d levels", kMaxLevels);
+  NSGP_REQUIRE(batch > 0 && channels > 0 && pooled > 0 && n_rois >= 0, "roi_align_backward: bad sizes");
+  if (n_rois == 0) return 0;
+  NSGP_REQUIRE(rois && grad_out, "roi_align_backward: null pointer");
+  RoiLevels lv{};
+  lv.n = n_levels;
+  for (int i = 0; i < n_levels; ++i) {
+    NSGP_REQUIRE(grad_feats[i] && heights[i] > 0 && widths[i] > 0,
+                 "roi_align_backward: level %d is empty", i);
+    lv.feat[i] = grad_feats[i]; lv.H[i] = heights[i]; lv.W[i] = widths[i];
+    lv.scale[i] = spatial_scales[i];
+  }
+  int ch_per_block = 256 / (pooled * pooled);
+  if (ch_per_block < 1) ch_per_block = 1;
+  ch_per_block *= 4;
+  dim3 grid(n_rois, ceil_div(channels, ch_per_block));
+  ProfScope prof(kProfRepre, stream);
+  roi_align_backward_kernel<<<grid, 256, 0, stream>>>(lv, channels, rois, pooled, sampling_ratio,
+                                                      aligned, finest_scale, grad_out,
+                                                      ch_per_block);
   NSGP_LAUNCHED();
   return 0;
 }

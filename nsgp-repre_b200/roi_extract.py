@@ -9,10 +9,11 @@ handles all levels, and ``class_sums`` adds the features straight into the per-c
 of the coarse prototypes (standard_roi_replay_head.py:411-415) without writing the
 (R, 12544) feature matrix.
 
-Forward only: this is the extractor of the no-grad paths - ``get_bbox_stuff`` during the RoI
-harvest (``cal_rois``, nsrunner_roi_replay.py:776-868) and the teacher's ``predict`` - where
-the reference runs it under ``torch.no_grad()``.  The training forward/backward of the RoI
-head keeps mmcv's differentiable op.
+Differentiable w.r.t. the feature maps (``repre_roi_align_backward``: the transpose of the
+pooling, atomics into zero-filled gradient maps), so it serves the training forward of the
+RoI head as well as the no-grad paths (``get_bbox_stuff`` during ``cal_rois``,
+nsrunner_roi_replay.py:776-868, and the teacher's ``predict``).  Like mmcv's op it has no
+gradient w.r.t. the RoI coordinates.
 """
 from __future__ import annotations
 
@@ -23,6 +24,42 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    """forward = the multi-level launch; backward = its transpose into fresh gradient maps."""
+
+    @staticmethod
+    def forward(ctx, ext, rois, *feats):
+        with torch.no_grad():
+            out, _, _, (C, P) = ext._launch(feats, rois, None, None, 0, True)
+        ctx.ext = ext
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.save_for_backward(rois)
+        return out.view(-1, C, P, P)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ext = ctx.ext
+        (rois,) = ctx.saved_tensors
+        dev = grad_out.device
+        L = len(ctx.shapes)
+        grads = [torch.zeros(sh, dtype=torch.float32, device=dev) for sh in ctx.shapes]
+        R = rois.shape[0]
+        if R > 0:
+            B, C = ctx.shapes[0][0], ctx.shapes[0][1]
+            go = grad_out.detach().float().contiguous()
+            r = rois.detach().float().contiguous()
+            ptrs = (ctypes.c_void_p * L)(*[g.data_ptr() for g in grads])
+            hs = (ctypes.c_int32 * L)(*[sh[2] for sh in ctx.shapes])
+            ws = (ctypes.c_int32 * L)(*[sh[3] for sh in ctx.shapes])
+            sc = (ctypes.c_float * L)(*[1.0 / s for s in ext.featmap_strides[:L]])
+            check(lib.repre_roi_align_backward(ptrs, hs, ws, sc, L, B, C, ptr(r), R,
+                                               ext.output_size, ext.sampling_ratio,
+                                               1 if ext.aligned else 0, float(ext.finest_scale),
+                                               ptr(go), _lib.current_stream(dev)),
+                  "repre_roi_align_backward")
+        return (None, None) + tuple(grads)
 
 
 class SingleRoIExtractor(nn.Module):
@@ -117,10 +154,18 @@ class SingleRoIExtractor(nn.Module):
               "repre_roi_align")
         return out, sums, counts, (C, P)
 
-    @torch.no_grad()
     def forward(self, feats, rois, roi_scale_factor=None):
         """:65-118 - (R, out_channels, 7, 7) RoI features."""
-        out, _, _, (C, P) = self._launch(feats, rois, roi_scale_factor, None, 0, True)
+        feats = list(feats)[: self.num_inputs]
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            if roi_scale_factor is not None:
+                rois = self.roi_rescale(rois.type_as(feats[0]), roi_scale_factor)
+            fs = [f if f.dtype == torch.float32 and f.is_contiguous() else f.float().contiguous()
+                  for f in feats]
+            _lib.require_cuda(fs[0], "feature maps")
+            return _RoIAlignFn.apply(self, rois.type_as(fs[0]).detach(), *fs)
+        with torch.no_grad():
+            out, _, _, (C, P) = self._launch(feats, rois, roi_scale_factor, None, 0, True)
         return out.view(-1, C, P, P)
 
     @torch.no_grad()

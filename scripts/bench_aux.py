@@ -50,6 +50,24 @@ def tv_then_sum():
     f = tv().flatten(1)
     return torch.stack([f[clab == c].sum(0) for c in range(19)])
 t_tv_sum = gpu_ms(tv_then_sum)
+gf = [f.clone().requires_grad_(True) for f in cf]
+gout = torch.randn(R, C, 7, 7, device=dev)
+def ours_fb():
+    for f in gf:
+        f.grad = None
+    ext(gf, crois).backward(gout)
+def tv_fb():
+    for f in gf:
+        f.grad = None
+    lv = ext.map_roi_levels(crois, 4)
+    out = gf[0].new_zeros(R, C, 7, 7)
+    for i in range(4):
+        inds = (lv == i).nonzero().squeeze(1)
+        if inds.numel():
+            out[inds] = roi_align(gf[i], crois[inds], (7, 7), 1.0 / ext.featmap_strides[i], 0, True)
+    out.backward(gout)
+t_fb = gpu_ms(ours_fb)
+t_tv_fb = gpu_ms(tv_fb)
 feat_bytes = sum(f.numel() * 4 for f in cf)
 out_bytes = R * C * 49 * 4
 print("8f-2 RoIAlign   R=%d C=%d 7x7, 4 levels of a %dx%d batch %d:" % (R, C, H, W, B))
@@ -58,6 +76,7 @@ print("   ours features           %.3f ms  (%.0f GB/s of features-read-once + ou
 print("   ours fused class sums   %.3f ms  (no %.0f MB feature matrix)" % (t_sum, out_bytes / 1e6))
 print("   torchvision per level (reference structure, CUDA)        %.3f ms" % t_tv)
 print("   torchvision per level + per-class masked sums (CUDA)     %.3f ms" % t_tv_sum)
+print("   forward + backward: ours %.3f ms | torchvision per level (CUDA) %.3f ms" % (t_fb, t_tv_fb))
 
 # ---------------------------------------------------------------- 8f-3 pseudo-label merge
 gt_b, gt_l, ps_b, ps_s, ps_l = synth.pseudo_label_case(21, images=8, max_gt=8, max_pseudo=100)
