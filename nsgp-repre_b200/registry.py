@@ -26,6 +26,12 @@ def register_all(force=True):
     _register_local("SGDNSCL", SGDNSCL)
     _register_local("StandardMultiPrototypeReplayHead", StandardMultiPrototypeReplayHead)
     _register_local("BRNullSpaceCovariance", CovarianceHooks)
+    from .roi_extract import SingleRoIExtractor
+    from .ewc import EWCHook
+    # local names only: mmdet's own 'SingleRoIExtractor' is replaced explicitly by the
+    # integrator, not behind the user's back
+    _register_local("SingleRoIExtractor", SingleRoIExtractor)
+    _register_local("EWCHook", EWCHook)
     try:
         from mmengine.registry import OPTIMIZERS
         OPTIMIZERS.register_module(name="SGDNSCL", module=SGDNSCL, force=force)
