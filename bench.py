@@ -406,6 +406,7 @@ def main():
     # task, nsrunner_roi_replay.py:746-749) - timed separately, not per step
     allreduce_ms = None
     if world > 1:
+        hooks.all_reduce()           # untimed: NCCL sets up its channels on the first large call
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -604,7 +605,8 @@ def main():
             "roofline": roofline, "roofline_staging": roofline_staging,
             "cpu_baseline": cpu_baseline,
             "phase_ms": {"covariance_61_layers": cov_ms, "sgdnscl_step_projection": sgd_ms,
-                         "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms},
+                         "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms,
+                         "allreduce_bytes": sum(la.acc.numel() * 4 for la in hooks._layers.values())},
             "kernel_ms_per_step": kernel_ms,
             "tflops": {"covariance_algorithmic": cov_flops / (cov_ms * 1e-3) / 1e12,
                        "projection_algorithmic": proj_flops / (sgd_ms * 1e-3) / 1e12},

@@ -442,8 +442,20 @@ class CovarianceHooks:
         self.join()
         # in place, one collective per accumulator, all in flight together: no 0.6 GB
         # flatten-and-copy round trip; NCCL pipelines them back to back over NVLink
-        works = [dist.all_reduce(la.acc, op=dist.ReduceOp.SUM, group=group, async_op=True)
-                 for la in self._layers.values()]
+        accs = [la.acc for la in self._layers.values()]
+        if dist.get_backend(group) == "nccl":
+            # one NCCL group call for all accumulators: a single fused launch instead of 61
+            # latency-bound ones (5.6 MB each on average)
+            try:
+                from torch.distributed.distributed_c10d import _coalescing_manager
+                with _coalescing_manager(group=group, device=accs[0].device, async_ops=True) as cm:
+                    for a in accs:
+                        dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
+                cm.wait()
+                return
+            except (ImportError, TypeError):
+                pass
+        works = [dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group, async_op=True) for a in accs]
         for w in works:
             w.wait()
 
