@@ -5,8 +5,10 @@ and the gather / reserve / merge / save tail of ``BRNullSpaceRunner.cal_rois``
 (:815-865).  The reference emulates a variable-length all-gather with 2*W zero-padded
 all-reduces per tensor (one pair per rank); here it is one all-gather of the row counts
 and one all-gather of the padded tensor - same result list, rank order preserved.
-The per-batch harvest itself (detector forward in 'roi_replay' mode, RoIAlign, the
-5-RoIs-per-batch selection) is upstream of this module.
+``select_rois`` is the 5-RoIs-per-batch selection of ``get_bbox_stuff``
+(mmdet/models/roi_heads/standard_roi_replay_head.py:165-201) with the reference's exact
+consumption of torch's global CPU generator, so a seeded run keeps the same RoIs; the RoI
+features it selects from come from ``roi_extract.SingleRoIExtractor``.
 """
 from __future__ import annotations
 
@@ -33,6 +35,29 @@ def all_gather_different_shape(t: torch.Tensor, group=None):
     return [p[:c] for p, c in zip(parts, counts)]
 
 
+@torch.no_grad()
+def select_rois(cls_target: torch.Tensor, bg_class_id: int, target_count: int = 5) -> torch.Tensor:
+    """Boolean mask over the sampled RoIs of one batch (:165-196): all foreground RoIs
+    (label != ``bg_class_id`` = num_classes), topped up with random background RoIs or thinned
+    by random removal to exactly ``target_count`` (all RoIs when there are fewer).  The random
+    picks are ``torch.randperm(n)[:k]`` on the default CPU generator, as in the reference."""
+    mask = cls_target != bg_class_id
+    current_count = int(torch.sum(mask).item())
+    delta = target_count - current_count
+    if delta > 0:
+        false_indices = torch.where(mask == False)[0]      # noqa: E712  (reference spelling)
+        if len(false_indices) < delta:
+            mask[:] = True
+        else:
+            indices_to_add = torch.randperm(len(false_indices))[:delta]
+            mask[false_indices[indices_to_add.to(false_indices.device)]] = True
+    elif delta < 0:
+        true_indices = torch.where(mask == True)[0]        # noqa: E712
+        indices_to_remove = torch.randperm(len(true_indices))[:-delta]
+        mask[true_indices[indices_to_remove.to(true_indices.device)]] = False
+    return mask
+
+
 class RoIHarvest:
     """Accumulates the six per-batch tensors of ``mode='roi_replay'`` (:805-813) and
     produces ``rois_etc.pth`` = [feats (M,12544) f32, cls (M,) i64, cls_w (M,) f32,
@@ -47,6 +72,22 @@ class RoIHarvest:
         for lst, t in zip(self._parts, (bbox_feats, cls_target, cls_weight, bbox_target,
                                         bbox_weight, rois)):
             lst.append(t)
+
+    @torch.no_grad()
+    def add_selected(self, bbox_feats, cls_target, cls_weight, bbox_target, bbox_weight, rois,
+                     bg_class_id, target_count=5, counter=None):
+        """The tail of ``get_bbox_stuff`` (:165-201): select ``target_count`` RoIs of the batch,
+        count them per class (``self.counter[c] += 1``, :198-200) and keep the six selected
+        tensors.  Returns them like the reference method does."""
+        mask = select_rois(cls_target, bg_class_id, target_count)
+        idx = mask.nonzero().flatten()                       # one sync instead of six
+        picked = tuple(t.index_select(0, idx) for t in (bbox_feats, cls_target, cls_weight,
+                                                        bbox_target, bbox_weight, rois))
+        if counter is not None:
+            for c in picked[1].tolist():
+                counter[c] += 1
+        self.add(*picked)
+        return picked
 
     @torch.no_grad()
     def finish(self, work_dir=None, previous_dir=None, task_id=1, reserve_per_class=0,

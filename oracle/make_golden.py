@@ -162,6 +162,15 @@ def main():
     out, lv = R.ref_roi_extract(feats, rois, out_channels=feats[0].shape[1])
     torch.save({"seed": 0, "out": out, "levels": lv}, os.path.join(OUT, "roi_extract.pt"))
     print("roi extract", tuple(out.shape), torch.bincount(lv, minlength=4).tolist())
+    # 8. the 5-RoIs-per-batch selection: the reference's get_bbox_stuff
+    from oracle.synth import roi_select_case
+    sel = []
+    for kind, seed in (("few", 11), ("many", 12), ("none", 13), ("tiny", 14)):
+        out, counter = R.ref_get_bbox_stuff(*roi_select_case(kind, seed), 20, seed)
+        sel.append({"kind": kind, "seed": seed, "out": [o.clone() for o in out],
+                    "n_counted": sum(counter.values())})
+        print("roi select", kind, out[1].tolist())
+    torch.save(sel, os.path.join(OUT, "roi_select.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -505,3 +505,55 @@ def ref_roi_extract(feats, rois, featmap_strides=(4, 8, 16, 32), out_channels=25
         out = Ext.forward(fake, tuple(feats), rois)
         lv = Ext.map_roi_levels(fake, rois, len(feats))
     return out, lv
+
+
+# --------------------------------------------------------------------------- #
+# the 5-RoIs-per-batch selection of get_bbox_stuff
+# (standard_roi_replay_head.py:106-202)
+# --------------------------------------------------------------------------- #
+
+def ref_get_bbox_stuff(bbox_feats, cls_target, cls_weight, bbox_target, bbox_weight, rois,
+                       num_classes, seed):
+    """Run the reference ``StandardRoIReplayHead.get_bbox_stuff`` on a stand-in ``self`` whose
+    assigner / sampler / extractor / bbox head hand back the given tensors; what is
+    exercised is the reference's own selection (:165-196), counter (:198-200) and
+    gather (:202) under ``torch.manual_seed(seed)``."""
+    import torch
+    load_multi_prototype_head()
+    mod = _cache["head_mod"]
+    n_img = 2
+    mod.unpack_gt_instances = lambda samples: ([None] * n_img, [None] * n_img, None)
+    mod.bbox2roi = lambda priors: rois
+
+    class _RpnResults(dict):
+        def pop(self, k):
+            return dict.pop(self, k)
+
+    class _Ext:
+        num_inputs = 4
+
+        def __call__(self, x, r):
+            return bbox_feats
+
+    class _BBoxHead:
+        def __init__(self):
+            self.num_classes = num_classes
+
+        def get_mid_features(self, f):
+            return f
+
+        def get_roi_targets(self, sampling_results, rcnn_train_cfg):
+            return cls_target.clone(), cls_weight, bbox_target, bbox_weight
+
+    fake = SimpleNamespace(
+        bbox_assigner=SimpleNamespace(assign=lambda *a: None),
+        bbox_sampler=SimpleNamespace(sample=lambda *a, **k: SimpleNamespace(priors=None)),
+        bbox_roi_extractor=_Ext(), with_shared_head=False, bbox_head=_BBoxHead(),
+        train_cfg=None, counter=defaultdict(int))
+    x = [torch.zeros(n_img, 1, 1, 1)] * 4
+    rpn = [_RpnResults(bboxes=None) for _ in range(n_img)]
+    for r in rpn:
+        r.priors = None
+    torch.manual_seed(seed)
+    out = mod.StandardRoIReplayHead.get_bbox_stuff(fake, x, rpn, [None] * n_img)
+    return out, dict(fake.counter)

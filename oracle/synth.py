@@ -166,3 +166,19 @@ def roi_case(seed=0, batch=2, channels=16, img_h=256, img_w=320, n_rois=64, clas
     rois[3, 1:] = torch.tensor([0.0, 0.0, 56.0, 56.0])
     labels = torch.randint(0, classes + 1, (n_rois,), generator=g)
     return feats, rois, labels
+
+
+def roi_select_case(kind, seed=0, M=64, D=24, num_classes=20):
+    """SURVEY 8(f)-1 inputs of the 5-per-batch selection: sampled-RoI tensors of one batch
+    with few (``"few"``), many (``"many"``) or no (``"none"``) foreground RoIs, or fewer than
+    five RoIs in total (``"tiny"``)."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "tiny":
+        M = 3
+    cls = torch.full((M,), num_classes, dtype=torch.int64)
+    nfg = {"few": 2, "many": 17, "none": 0, "tiny": 1}[kind]
+    pos = torch.randperm(M, generator=g)[:nfg]
+    cls[pos] = torch.randint(0, num_classes, (nfg,), generator=g)
+    return (torch.randn(M, D, generator=g), cls, torch.ones(M), torch.randn(M, 4, generator=g),
+            torch.ones(M, 4), torch.cat([torch.randint(0, 2, (M, 1), generator=g).float(),
+                                         torch.rand(M, 4, generator=g) * 100], 1))

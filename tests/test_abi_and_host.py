@@ -166,3 +166,24 @@ def test_f_rows_host_logic_and_no_cpu_fallback(golden_dir):
     hook = pkg.EWCHook(net, reg, terms)
     with pytest.raises(pkg._lib.NsgpError):
         hook.penalty()
+
+
+def test_roi_selection_matches_reference_fixture(golden_dir):
+    """RoIHarvest.add_selected against the reference's own get_bbox_stuff (:165-202) under the
+    same global seed: same five RoIs, same order, all six tensors."""
+    import collections
+    import nsgp_repre_b200 as pkg
+    from oracle import synth
+    cases = torch.load(os.path.join(golden_dir, "roi_select.pt"), weights_only=False)
+    assert [c["kind"] for c in cases] == ["few", "many", "none", "tiny"]
+    for case in cases:
+        args = synth.roi_select_case(case["kind"], case["seed"])
+        h = pkg.RoIHarvest()
+        counter = collections.defaultdict(int)
+        torch.manual_seed(case["seed"])
+        got = h.add_selected(*args, bg_class_id=20, counter=counter)
+        assert len(got) == 6
+        for a, b in zip(got, case["out"]):
+            assert torch.equal(a, b), case["kind"]
+        assert got[1].shape[0] == (3 if case["kind"] == "tiny" else 5)
+        assert sum(counter.values()) == case["n_counted"]
