@@ -315,7 +315,8 @@ int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, co
  *   mmcv.ops.RoIAlign: average pooling, adaptive grid when sampling_ratio = 0, `aligned`)
  *   feats[l]: (batch, channels, heights[l], widths[l]) fp32 NCHW device tensors (host array
  *   of pointers), rois (n_rois,5) = [batch index, x1, y1, x2, y2] in image coordinates.
- *   Level of a RoI: floor(log2(sqrt(w*h)/finest_scale + 1e-6)) clamped to the levels.
+ *   Level of a RoI: levels[r] when `levels` (device int32, n_rois) is given, else
+ *   floor(log2(sqrt(w*h)/finest_scale + 1e-6)) clamped to the levels, evaluated in the kernel.
  *   roi_feats (n_rois, channels*pooled*pooled) and/or class_sums (n_classes, same) +
  *   class_counts (n_classes; labels outside [0,n_classes) are skipped); either output
  *   may be NULL.  class_sums / class_counts are cleared by the call.
@@ -324,8 +325,8 @@ int repre_roi_align(const float* const* feats /* host */, const int32_t* heights
                     const int32_t* widths /* host */, const float* spatial_scales /* host */,
                     int n_levels, int batch, int channels, const float* rois, int n_rois,
                     int pooled, int sampling_ratio, int aligned, float finest_scale,
-                    const int64_t* labels, int n_classes, float* roi_feats, float* class_sums,
-                    int32_t* class_counts, void* stream);
+                    const int32_t* levels, const int64_t* labels, int n_classes, float* roi_feats,
+                    float* class_sums, int32_t* class_counts, void* stream);
 
 /* gradient of repre_roi_align w.r.t. the feature maps: grad_feats[l] (batch, channels, H_l, W_l),
  * zero-filled (or holding a gradient to add to) by the caller, accumulated into with atomics */
@@ -333,7 +334,7 @@ int repre_roi_align_backward(float* const* grad_feats /* host */, const int32_t*
                              const int32_t* widths, const float* spatial_scales, int n_levels,
                              int batch, int channels, const float* rois, int n_rois, int pooled,
                              int sampling_ratio, int aligned, float finest_scale,
-                             const float* grad_out, void* stream);
+                             const int32_t* levels, const float* grad_out, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * SURVEY 8(f)-4  EWC importance and penalty

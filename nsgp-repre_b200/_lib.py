@@ -131,12 +131,12 @@ SIGNATURES = {
                                     c_void_p, c_size_t, c_void_p]),
     "repre_roi_align": (c_int, [C.POINTER(c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(c_float), c_int, c_int, c_int, c_void_p, c_int, c_int,
-                                c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "repre_roi_align_backward": (c_int, [C.POINTER(c_void_p), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), C.POINTER(c_float), c_int, c_int,
                                          c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_void_p, c_void_p]),
     "nsgp_ewc_table_bytes": (c_size_t, [c_int]),
     "nsgp_ewc_accumulate": (c_int, [C.POINTER(EwcTensor), c_int, c_float, c_float, c_void_p,
                                     c_size_t, c_void_p]),

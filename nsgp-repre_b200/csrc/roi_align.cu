@@ -94,13 +94,15 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
                  int sampling_ratio, int aligned, float finest_scale,
                  const long long* __restrict__ labels, int n_classes,
                  float* __restrict__ roi_feats, float* __restrict__ class_sums,
-                 int* __restrict__ class_counts, int ch_per_block) {
+                 int* __restrict__ class_counts, int ch_per_block,
+                 const int* __restrict__ levels) {
   __shared__ AxisTable ty, tx;
   __shared__ int s_fallback;
   const int r = blockIdx.x;
   const float* roi = rois + (long long)r * 5;
   const int b = (int)roi[0];
-  const int l = lv.n > 1 ? roi_level(roi, finest_scale, lv.n) : 0;
+  const int l = levels != nullptr ? min(max(levels[r], 0), lv.n - 1)
+                                  : (lv.n > 1 ? roi_level(roi, finest_scale, lv.n) : 0);
   const int H = lv.H[l], W = lv.W[l];
   const float sc = lv.scale[l], off = aligned ? 0.5f : 0.f;
   const float sw = roi[1] * sc - off, sh = roi[2] * sc - off;
@@ -167,13 +169,15 @@ roi_align_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int
 __global__ void __launch_bounds__(256)
 roi_align_backward_kernel(RoiLevels lv, int channels, const float* __restrict__ rois, int pooled,
                           int sampling_ratio, int aligned, float finest_scale,
-                          const float* __restrict__ grad_out, int ch_per_block) {
+                          const float* __restrict__ grad_out, int ch_per_block,
+                          const int* __restrict__ levels) {
   __shared__ AxisTable ty, tx;
   __shared__ int s_fallback;
   const int r = blockIdx.x;
   const float* roi = rois + (long long)r * 5;
   const int b = (int)roi[0];
-  const int l = lv.n > 1 ? roi_level(roi, finest_scale, lv.n) : 0;
+  const int l = levels != nullptr ? min(max(levels[r], 0), lv.n - 1)
+                                  : (lv.n > 1 ? roi_level(roi, finest_scale, lv.n) : 0);
   const int H = lv.H[l], W = lv.W[l];
   const float sc = lv.scale[l], off = aligned ? 0.5f : 0.f;
   const float sw = roi[1] * sc - off, sh = roi[2] * sc - off;
@@ -247,8 +251,9 @@ extern "C" int repre_roi_align(const float* const* feats, const int32_t* heights
                                const int32_t* widths, const float* spatial_scales, int n_levels,
                                int batch, int channels, const float* rois, int n_rois,
                                int pooled, int sampling_ratio, int aligned, float finest_scale,
-                               const int64_t* labels, int n_classes, float* roi_feats,
-                               float* class_sums, int32_t* class_counts, void* stream_) {
+                               const int32_t* levels, const int64_t* labels, int n_classes,
+                               float* roi_feats, float* class_sums, int32_t* class_counts,
+                               void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSGP_REQUIRE(feats && heights && widths && spatial_scales, "roi_align: null level tables");
   NSGP_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "roi_align: 1..%d levels", kMaxLevels);
@@ -278,7 +283,8 @@ extern "C" int repre_roi_align(const float* const* feats, const int32_t* heights
   ProfScope prof(kProfRepre, stream);
   roi_align_kernel<<<grid, 256, 0, stream>>>(lv, channels, rois, pooled, sampling_ratio, aligned,
                                              finest_scale, (const long long*)labels, n_classes,
-                                             roi_feats, class_sums, class_counts, ch_per_block);
+                                             roi_feats, class_sums, class_counts, ch_per_block,
+                                             levels);
   NSGP_LAUNCHED();
   return 0;
 }
@@ -287,7 +293,8 @@ extern "C" int repre_roi_align_backward(float* const* grad_feats, const int32_t*
                                         const int32_t* widths, const float* spatial_scales,
                                         int n_levels, int batch, int channels, const float* rois,
                                         int n_rois, int pooled, int sampling_ratio, int aligned,
-                                        float finest_scale, const float* grad_out, void* stream_) {
+                                        float finest_scale, const int32_t* levels,
+                                        const float* grad_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NSGP_REQUIRE(grad_feats && heights && widths && spatial_scales, "roi_align_backward: null level tables");
   NSGP_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "roi_align_backward: 1..%d levels", kMaxLevels);
@@ -309,7 +316,7 @@ extern "C" int repre_roi_align_backward(float* const* grad_feats, const int32_t*
   ProfScope prof(kProfRepre, stream);
   roi_align_backward_kernel<<<grid, 256, 0, stream>>>(lv, channels, rois, pooled, sampling_ratio,
                                                       aligned, finest_scale, grad_out,
-                                                      ch_per_block);
+                                                      ch_per_block, levels);
   NSGP_LAUNCHED();
   return 0;
 }

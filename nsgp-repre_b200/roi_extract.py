@@ -30,10 +30,11 @@ class _RoIAlignFn(torch.autograd.Function):
     """forward = the multi-level launch; backward = its transpose into fresh gradient maps."""
 
     @staticmethod
-    def forward(ctx, ext, rois, *feats):
+    def forward(ctx, ext, rois, levels, *feats):
         with torch.no_grad():
-            out, _, _, (C, P) = ext._launch(feats, rois, None, None, 0, True)
+            out, _, _, (C, P) = ext._launch(feats, rois, None, None, 0, True, levels)
         ctx.ext = ext
+        ctx.levels = levels
         ctx.shapes = [tuple(f.shape) for f in feats]
         ctx.save_for_backward(rois)
         return out.view(-1, C, P, P)
@@ -57,9 +58,9 @@ class _RoIAlignFn(torch.autograd.Function):
             check(lib.repre_roi_align_backward(ptrs, hs, ws, sc, L, B, C, ptr(r), R,
                                                ext.output_size, ext.sampling_ratio,
                                                1 if ext.aligned else 0, float(ext.finest_scale),
-                                               ptr(go), _lib.current_stream(dev)),
+                                               ptr(ctx.levels), ptr(go), _lib.current_stream(dev)),
                   "repre_roi_align_backward")
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class SingleRoIExtractor(nn.Module):
@@ -109,17 +110,16 @@ class SingleRoIExtractor(nn.Module):
         return torch.stack((rois[:, 0], cx - new_w * 0.5, cy - new_h * 0.5, cx + new_w * 0.5,
                             cy + new_h * 0.5), dim=-1)
 
-    def _launch(self, feats, rois, roi_scale_factor, labels, num_classes, want_feats):
+    def _launch(self, feats, rois, roi_scale_factor, labels, num_classes, want_feats,
+                levels=None):
         feats = list(feats)[: self.num_inputs]
         f0 = feats[0]
         _lib.require_cuda(f0, "feature maps")
         rois = rois.type_as(f0)                                                  # :81
-        if roi_scale_factor is not None and len(feats) > 1:
-            # :98-99 - the level is chosen from the unscaled RoI, then the RoI is rescaled;
-            # evaluate the level with the kernel's own rule on the scaled RoI only when no
-            # scale factor is given
-            raise _lib.NsgpError("roi_scale_factor with several levels is not implemented")
         if roi_scale_factor is not None:
+            # :96-99 - the level comes from the unscaled RoI, then the RoI is rescaled
+            if len(feats) > 1:
+                levels = self.map_roi_levels(rois, len(feats)).to(torch.int32).contiguous()
             rois = self.roi_rescale(rois, roi_scale_factor)
         L = len(feats)
         B, C = f0.shape[0], f0.shape[1]
@@ -149,7 +149,7 @@ class SingleRoIExtractor(nn.Module):
             return out, sums, counts, (C, P)
         check(lib.repre_roi_align(ptrs, hs, ws, sc, L, B, C, ptr(rois), R, P, self.sampling_ratio,
                                   1 if self.aligned else 0, float(self.finest_scale),
-                                  ptr(labels), int(num_classes or 0), ptr(out), ptr(sums),
+                                  ptr(levels), ptr(labels), int(num_classes or 0), ptr(out), ptr(sums),
                                   ptr(counts), _lib.current_stream(f0.device)),
               "repre_roi_align")
         return out, sums, counts, (C, P)
@@ -158,12 +158,16 @@ class SingleRoIExtractor(nn.Module):
         """:65-118 - (R, out_channels, 7, 7) RoI features."""
         feats = list(feats)[: self.num_inputs]
         if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            levels = None
+            rois = rois.type_as(feats[0]).detach()
             if roi_scale_factor is not None:
-                rois = self.roi_rescale(rois.type_as(feats[0]), roi_scale_factor)
+                if len(feats) > 1:
+                    levels = self.map_roi_levels(rois, len(feats)).to(torch.int32).contiguous()
+                rois = self.roi_rescale(rois, roi_scale_factor)
             fs = [f if f.dtype == torch.float32 and f.is_contiguous() else f.float().contiguous()
                   for f in feats]
             _lib.require_cuda(fs[0], "feature maps")
-            return _RoIAlignFn.apply(self, rois.type_as(fs[0]).detach(), *fs)
+            return _RoIAlignFn.apply(self, rois, levels, *fs)
         with torch.no_grad():
             out, _, _, (C, P) = self._launch(feats, rois, roi_scale_factor, None, 0, True)
         return out.view(-1, C, P, P)

@@ -815,6 +815,25 @@ def test_roi_extract_backward_matches_torchvision_autograd(pkg, sampling_ratio):
         assert not ext(cf, rois.cuda()).requires_grad
 
 
+def test_roi_extract_scale_factor_uses_unscaled_levels(pkg):
+    """roi_scale_factor (:96-99): the level is mapped from the unscaled RoI, the pooling uses
+    the rescaled one - against the restatement with the same order of operations."""
+    from torchvision.ops import roi_align
+    feats, rois, labels = synth.roi_case(9, channels=8, n_rois=48)
+    ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), 8,
+                                 [4, 8, 16, 32])
+    lv = O.map_roi_levels(rois, 4)
+    scaled = ext.roi_rescale(rois, 1.7)
+    want = feats[0].new_zeros(48, 8, 7, 7)
+    for i in range(4):
+        inds = (lv == i).nonzero().squeeze(1)
+        if inds.numel():
+            want[inds] = roi_align(feats[i], scaled[inds], (7, 7), 1.0 / ext.featmap_strides[i], 0, True)
+    got = ext([f.cuda() for f in feats], rois.cuda(), roi_scale_factor=1.7)
+    assert rel_fro(got, want) < 1e-5
+    assert not torch.equal(O.map_roi_levels(scaled, 4), lv)      # the distinction matters here
+
+
 def test_roi_extract_empty_and_errors(pkg):
     feats, rois, labels = synth.roi_case(1, channels=8, n_rois=4)
     ext = pkg.SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0),
