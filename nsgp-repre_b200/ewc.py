@@ -85,6 +85,23 @@ class EWCImportance:
                                       float(len_dataloader), table.data_ptr(), table.numel(),
                                       _lib.current_stream(dev)), "nsgp_ewc_accumulate")
 
+    def all_reduce(self, group=None, average=True):
+        """Not in the reference: there every rank keeps the importance of its own data shard
+        (``calculate_save_importance`` never reduces over ranks) and rank 0's file
+        wins.  Call this before ``finish`` to use the whole dataset: mean (default) or sum of
+        the per-rank importances, one all-reduce per tensor issued together."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+                 for t in self.importance.values()]
+        for w in works:
+            w.wait()
+        if average:
+            world = dist.get_world_size(group)
+            for t in self.importance.values():
+                t.div_(world)
+
     def finish(self, ewc_reg_terms: dict = None) -> dict:
         """:951-953, 985-987 - append this task's importance and parameters."""
         if not ewc_reg_terms:

@@ -58,6 +58,14 @@ def _worker(rank, world, port, ret):
           torch.ones(n), torch.zeros(n, 4), torch.ones(n, 4), torch.zeros(n, 5))
     res = h.finish()
     ok &= len(res) == 6 and res[0].shape == (5, 8) and res[1].tolist() == [0, 0, 1, 1, 1]
+    # EWC importance over ranks (not reduced in the reference; optional here)
+    from nsgp_repre_b200.ewc import EWCImportance
+    lin = torch.nn.BatchNorm1d(4)
+    acc = EWCImportance({"bn.weight": lin.weight, "bn.bias": lin.bias})
+    acc.importance["bn.weight"].fill_(float(rank + 1))
+    acc.importance["bn.bias"].fill_(10.0 * (rank + 1))
+    acc.all_reduce()
+    ok &= bool((acc.importance["bn.weight"] == 1.5).all() and (acc.importance["bn.bias"] == 15.0).all())
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
