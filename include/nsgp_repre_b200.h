@@ -164,9 +164,10 @@ int nsgp_sgd_nscl_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
  * changes (gradient and momentum pointers may change freely between steps). */
 typedef struct {
   int kind;
-  int n_problems[3], n_items[3];   /* [0] single-CTA kernel, [1] CTA-pair (cta_group::2) kernel,
-                                      [2] sliding-window autocorrelation kernel */
-  size_t off_probs[3], off_items[3];
+  int n_problems[4], n_items[4];   /* [0] single-CTA kernel, [1] CTA-pair (cta_group::2) kernel,
+                                      [2] sliding-window autocorrelation kernel,
+                                      [3] wide-tile (128 x 256) Gram kernel */
+  size_t off_probs[4], off_items[4];
   size_t bytes;
 } nsgp_group_t;
 

@@ -36,8 +36,8 @@ class ProjLayer(C.Structure):
 
 
 class Group(C.Structure):
-    _fields_ = [("kind", c_int), ("n_problems", c_int * 3), ("n_items", c_int * 3),
-                ("off_probs", c_size_t * 3), ("off_items", c_size_t * 3), ("bytes", c_size_t)]
+    _fields_ = [("kind", c_int), ("n_problems", c_int * 4), ("n_items", c_int * 4),
+                ("off_probs", c_size_t * 4), ("off_items", c_size_t * 4), ("bytes", c_size_t)]
 
 
 class SgdPlan(C.Structure):

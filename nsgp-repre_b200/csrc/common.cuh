@@ -135,7 +135,8 @@ struct SubGroup {
   size_t off_probs, off_items;
 };
 struct GroupInfo {
-  SubGroup sub[3];                 // [0] single-CTA kernel, [1] CTA-pair kernel,
+  SubGroup sub[4];                 // [3] wide-tile Gram kernel (contraction_wide.cu),
+                                   // [0] single-CTA kernel, [1] CTA-pair kernel,
                                    // [2] sliding-window autocorrelation kernel
   int kind;                        // ProfKind of the launches (kProfGram / kProfGemm)
   size_t bytes;
@@ -161,6 +162,14 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
                          int n, void* table_dev, size_t table_bytes, SubGroup* sg,
                          cudaStream_t stream);
 int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream);
+
+// wide-tile Gram kernel (contraction_wide.cu)
+struct ContractionArgs;
+bool gram_wide_eligible(const ContractionArgs& a);
+size_t gram_wide_table_bytes(const ContractionArgs* probs, int n);
+int gram_wide_table_build(const ContractionArgs* probs, int n, void* table_dev, size_t table_bytes,
+                          SubGroup* sg, cudaStream_t stream);
+int gram_wide_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream);
 
 // engines
 int contraction_simt(const ContractionArgs& a, cudaStream_t stream);

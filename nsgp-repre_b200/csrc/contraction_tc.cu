@@ -756,6 +756,7 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
     off = (size_t)round_up((long long)(sg.off_items + items[k].size() * sizeof(TcItem)), 64);
   }
   info->sub[2] = SubGroup{0, 0, 0, 0};
+  info->sub[3] = SubGroup{0, 0, 0, 0};
   info->bytes = off;
   NSGP_REQUIRE(info->bytes <= table_bytes, "group_build: table too small (%zu < %zu)",
                table_bytes, info->bytes);
@@ -784,6 +785,8 @@ int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stre
     int rc = launch_kernel(k == 1, dummy_maps, dummy, probs, items, sg.n_items, info.kind, stream);
     if (rc) return rc;
   }
+  int rc = gram_wide_launch(table_dev, info.sub[3], stream);
+  if (rc) return rc;
   // autocorrelation sub-table last: its long items fill the machine best once the small
   // problems are out of the way
   return autocorr_launch(table_dev, info.sub[2], stream);

@@ -54,7 +54,7 @@ def timeline():
     ev = [(buf[2 * i], buf[2 * i + 1], kinds[i]) for i in range(m)]
     ev = ev[-15:]
     t0 = min(e[0] for e in ev)
-    names = {2: "stage", 0: "gram-generic", 10: "gram-autocorr"}
+    names = {2: "stage", 0: "gram-generic", 10: "gram-autocorr", 11: "gram-wide"}
     for a, b, k in sorted(ev):
         print("   %-14s %8.3f -> %8.3f ms  (%.3f)" % (names.get(k, k), (a - t0) / 1e6, (b - t0) / 1e6, (b - a) / 1e6))
 
