@@ -89,7 +89,8 @@ __device__ unsigned long long g_ac_counters[160 * 8];
 
 __global__ void __launch_bounds__(kThreadsAc, 1)
 autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict__ items,
-                   int n_items, int dbg, int sa_n, unsigned long long* tl) {
+                   int n_items, int dbg, int sa_n, unsigned long long* tl,
+                   int wide_n) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,10 +152,12 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
           mbar_wait_warp(&b_empty[s], par ^ 1, lane);
           if (dbg) c0 += clock64() - q0;
           mbar_expect_tx_elect(&b_full[s], kTile);
-          const uint32_t dst = smem_u32(b_ring + s * kTile);
+          // B ring = [hi planes of the SB slots | lo planes]: neighbouring window tiles are
+          // contiguous per plane, so one N = 256 MMA can cover two of them
+          const uint32_t dst = smem_u32(b_ring + s * kPlane);
           const int row = (int)((tile0 + (long long)i * p.NS) * BM);
           tma_load_2d_elect(dst, &p.maps[0], &b_full[s], 0, row);
-          tma_load_2d_elect(dst + kPlane, &p.maps[1], &b_full[s], 0, row);
+          tma_load_2d_elect(dst + SB * kPlane, &p.maps[1], &b_full[s], 0, row);
           ++cnt;
         }
       } else {
@@ -188,6 +191,9 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
       int n_valid = p.C - it.cb * BM;
       if (n_valid > BM) n_valid = BM;
       const uint32_t idesc = make_idesc_tf32(BM, (n_valid + 15) & ~15);
+      // two accumulators at once need full 128-column tiles (the second starts at column 128)
+      const uint32_t idesc2 = make_idesc_tf32(BM, 2 * BM);
+      const bool wide = wide_n != 0 && n_valid == BM;
       const int n = it.u1 - it.u0;
       long long q0 = dbg ? clock64() : 0;
       mbar_wait_warp(tmem_empty, (n_done & 1) ^ 1, lane);     // epilogue drained the accumulators
@@ -211,13 +217,20 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
         const uint32_t abase = smem_u32(a_ring + as * kTile);
         const uint64_t a_hi = make_kmajor_sw128_desc(abase);
         const uint64_t a_lo = make_kmajor_sw128_desc(abase + kPlane);
-        for (int dy = dy0; dy < 3; ++dy) {
+        // An M128 x N128 x K8 tf32 MMA reads 8 KB of operands per 64 cycles = the SM's whole
+        // shared-memory bandwidth.  Two neighbouring window tiles that are also
+        // neighbours in the ring (no wrap) go through ONE N = 256 MMA into their two
+        // neighbouring accumulators: A is read once for both.
+        for (int dy = dy0; dy < 3;) {
           const uint32_t bs = (b_cnt + dy) % SB;
-          const uint32_t bbase = smem_u32(b_ring + bs * kTile);
+          const bool two = wide && dy + 1 < 3 && bs + 1 < SB;
+          const uint32_t bbase = smem_u32(b_ring + bs * kPlane);
           const uint64_t b_hi = make_kmajor_sw128_desc(bbase);
-          const uint64_t b_lo = make_kmajor_sw128_desc(bbase + kPlane);
+          const uint64_t b_lo = make_kmajor_sw128_desc(bbase + SB * kPlane);
           const uint32_t d = tmem_base + dy * BM;
-          tc_mma_kblock_3xtf32(d, d, a_hi, a_lo, b_hi, b_lo, idesc, j > 0 ? 1u : 0u, 1u);
+          tc_mma_kblock_3xtf32(d, d, a_hi, a_lo, b_hi, b_lo, two ? idesc2 : idesc,
+                               j > 0 ? 1u : 0u, 1u);
+          dy += two ? 2 : 1;
         }
         tc_commit_elect(&a_empty[as]);                // A(j) free when these MMAs retire
         tc_commit_elect(&b_empty[b_cnt % SB]);        // B(j) is not needed after row j
@@ -428,6 +441,10 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
     const char* e = getenv("NSGP_AC_SA");
     return (e && e[0] == '2') ? 2 : 3;
   }();
+  static const int wide_n = [] {
+    const char* e = getenv("NSGP_AC_WIDE");            // 0: three N = 128 MMAs per product
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
   const size_t smem_bytes = (size_t)(sa_n + SB) * kTile + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -441,7 +458,8 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   const int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
   ProfScope prof(kProfGram, stream);
   static const int dbg = getenv("NSGP_DBG_COUNTERS") ? 1 : 0;
-  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10));
+  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10),
+                                                           wide_n);
   NSGP_LAUNCHED();
   return 0;
 }
