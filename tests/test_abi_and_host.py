@@ -187,3 +187,21 @@ def test_roi_selection_matches_reference_fixture(golden_dir):
             assert torch.equal(a, b), case["kind"]
         assert got[1].shape[0] == (3 if case["kind"] == "tiny" else 5)
         assert sum(counter.values()) == case["n_counted"]
+
+
+def test_bench_workload_matches_survey_appendix_a():
+    """bench.py's layer trace of the stand-in detector: 61 hooked backbone+neck convs, 50 of
+    them trainable (protected), 1 856.5 / 118.3 algorithmic GFLOP at 800x1344 and 1 075.0 at
+    608x1024 - the workload the metric is quoted on."""
+    import bench
+    from nsgp_repre_b200 import standin
+    layers = bench.trace_layers(800, 1344, standin)
+    assert len(layers) == 61
+    assert sum(1 for r in layers if r["trainable"]) == 50
+    assert abs(sum(r["cov_flops"] for r in layers) / 1e9 - 1856.488) < 0.01
+    assert abs(sum(r["proj_flops"] for r in layers) / 1e9 - 118.313) < 0.01
+    assert sum(1 for r in layers if r["k"] == 3 and r["s"] == 1) == 17
+    small = bench.trace_layers(608, 1024, standin)
+    assert abs(sum(r["cov_flops"] for r in small) / 1e9 - 1074.995) < 0.01
+    feats, lab = bench.synthetic_rois(8, 7)
+    assert feats.shape == (4096, 12544) and int((lab < 19).sum()) == 1024
