@@ -31,7 +31,7 @@ from .optim import SGDNSCL  # noqa: F401
 from .prototypes import (MultiPrototypeReplay, StandardMultiPrototypeReplayHead,  # noqa: F401
                          kmeans_prototypes)
 from .rois import all_gather_different_shape, RoIHarvest  # noqa: F401
-from .roi_extract import SingleRoIExtractor  # noqa: F401
+from .roi_extract import SingleRoIExtractor, reduce_class_sums  # noqa: F401
 from .ewc import EWCHook, EWCImportance, register_params  # noqa: F401
 from .pseudo_labels import merge_pseudo_labels, merge_into_samples  # noqa: F401
 from . import registry  # noqa: F401

@@ -179,3 +179,20 @@ class SingleRoIExtractor(nn.Module):
         prototypes ``mean(F[label == c], 0)`` of standard_roi_replay_head.py:411-415."""
         out, sums, counts, _ = self._launch(feats, rois, None, labels, num_classes, return_feats)
         return (sums, counts, out) if return_feats else (sums, counts)
+
+
+def reduce_class_sums(sums: torch.Tensor, counts: torch.Tensor, group=None):
+    """Data-parallel coarse prototypes: every rank pools its own RoIs into per-class
+    sums / counts (``SingleRoIExtractor.class_sums``), ONE all-reduce of the (C, D) sums and
+    the (C,) counts makes them global - no RoI feature ever crosses the fabric - and
+    ``sums / counts`` is ``mean(F[label == c], 0)`` over the RoIs of all ranks
+    (standard_roi_replay_head.py:411-415).  Classes without RoIs come back as NaN like
+    ``torch.mean`` of an empty slice.  Returns (means (C, D), counts (C,) int64)."""
+    import torch.distributed as dist
+    counts = counts.to(torch.int64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        w1 = dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w2 = dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w1.wait()
+        w2.wait()
+    return sums / counts.to(sums.dtype).unsqueeze(1), counts

@@ -66,6 +66,19 @@ def _worker(rank, world, port, ret):
     acc.importance["bn.bias"].fill_(10.0 * (rank + 1))
     acc.all_reduce()
     ok &= bool((acc.importance["bn.weight"] == 1.5).all() and (acc.importance["bn.bias"] == 15.0).all())
+    # data-parallel coarse prototypes: per-rank class sums -> one all-reduce -> global means
+    from nsgp_repre_b200.roi_extract import reduce_class_sums
+    gg = torch.Generator().manual_seed(5)
+    F_all = torch.randn(12, 6, generator=gg)
+    lab_all = torch.tensor([0, 1, 2, 0, 1, 1, 2, 2, 0, 0, 1, 3])
+    sel = slice(0, 7) if rank == 0 else slice(7, 12)
+    sums = torch.zeros(5, 6); cnt = torch.zeros(5, dtype=torch.int32)
+    for f, l in zip(F_all[sel], lab_all[sel]):
+        sums[l] += f; cnt[l] += 1
+    means, tot = reduce_class_sums(sums, cnt)
+    for c in range(4):
+        ok &= bool(torch.allclose(means[c], F_all[lab_all == c].mean(0), atol=1e-6))
+    ok &= tot.tolist() == [4, 4, 3, 1, 0] and bool(torch.isnan(means[4]).all())
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
