@@ -208,7 +208,14 @@ class CovarianceHooks:
             # concurrently - next to the HBM-bound staging kernel the operand-delivery-bound
             # contraction kernels run 1.5-3x slower - so they are serialised and the
             # caller's stream stays free for the rest of the step
-            self._stage_deferred(js, side)
+            try:
+                self._stage_deferred(js, side)
+            except Exception:
+                # drop the recorded forward so that the hooks stay usable after the error
+                js.pos = 0
+                js.keep.clear()
+                js.xs, js.versions = [], []
+                raise
         else:
             js.keep.clear()
         if js.sig is None:
