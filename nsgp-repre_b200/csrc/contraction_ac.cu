@@ -90,7 +90,7 @@ __device__ unsigned long long g_ac_counters[160 * 8];
 __global__ void __launch_bounds__(kThreadsAc, 1)
 autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict__ items,
                    int n_items, int dbg, int sa_n, unsigned long long* tl,
-                   int wide_n) {
+                   int wide_n, int tmem_a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -221,6 +221,22 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
         // shared-memory bandwidth.  Two neighbouring window tiles that are also
         // neighbours in the ring (no wrap) go through ONE N = 256 MMA into their two
         // neighbouring accumulators: A is read once for both.
+        if (tmem_a) {
+          // A from tensor memory: copy the A tile once (64 columns next to the accumulators,
+          // two buffers alternate), every MMA then reads only its B slice from shared memory
+          const uint32_t t_hi = tmem_base + 384 + (a_cnt & 1) * 64, t_lo = t_hi + 32;
+          tc_cp_a_kblock(t_hi, t_lo, a_hi, a_lo);
+          for (int dy = dy0; dy < 3;) {
+            const uint32_t bs = (b_cnt + dy) % SB;
+            const bool two = wide && dy + 1 < 3 && bs + 1 < SB;
+            const uint32_t bbase = smem_u32(b_ring + bs * kPlane);
+            tc_mma_kblock_3xtf32_ta(tmem_base + dy * BM, t_hi, t_lo,
+                                    make_kmajor_sw128_desc(bbase),
+                                    make_kmajor_sw128_desc(bbase + SB * kPlane),
+                                    two ? idesc2 : idesc, j > 0 ? 1u : 0u);
+            dy += two ? 2 : 1;
+          }
+        } else
         for (int dy = dy0; dy < 3;) {
           const uint32_t bs = (b_cnt + dy) % SB;
           const bool two = wide && dy + 1 < 3 && bs + 1 < SB;
@@ -445,6 +461,10 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
     const char* e = getenv("NSGP_AC_WIDE");            // 0: three N = 128 MMAs per product
     return (e && e[0] == '0') ? 0 : 1;
   }();
+  static const int tmem_a = [] {
+    const char* e = getenv("NSGP_AC_TMEMA");           // 1: A operand from tensor memory
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
   const size_t smem_bytes = (size_t)(sa_n + SB) * kTile + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -459,7 +479,7 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   ProfScope prof(kProfGram, stream);
   static const int dbg = getenv("NSGP_DBG_COUNTERS") ? 1 : 0;
   autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10),
-                                                           wide_n);
+                                                           wide_n, tmem_a);
   NSGP_LAUNCHED();
   return 0;
 }
