@@ -844,3 +844,32 @@ def test_roi_extract_empty_and_errors(pkg):
         ext(feats, rois)                                   # host tensors: no CPU fallback
     with pytest.raises(pkg._lib.NsgpError):
         pkg.SingleRoIExtractor(dict(type="RoIPool", output_size=7), 8, [4])
+
+
+# ------------------------------------------------------------------------- bench contract
+def test_bench_line_contract():
+    """`python bench.py` prints ONE JSON line with the keys the driver reads (small run)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2",
+                          "--warmup", "3", "--cpu-budget-s", "0.5"], capture_output=True,
+                         text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks",
+              "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert d["roofline"]["bound"] == "tensor" and 0.3 < d["roofline"]["frac"] < 1.5
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert d["cpu_baseline"]["kind"] == "port"
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 3e8 and d["e2e"]["value"] < d["value"]
+    assert d["gpu_launches"] > 0 and "workload" in d["config"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
