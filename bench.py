@@ -294,7 +294,7 @@ def main():
         dist.init_process_group(backend="nccl", device_id=dev)
     import nsgp_repre_b200 as pkg
     from nsgp_repre_b200 import standin, _lib
-    assert pkg._lib.lib.nsgp_get_engine() == 0
+    assert pkg._lib.engine() == 0
 
     torch.manual_seed(1234)
     model = standin.FasterRCNNStandIn(with_rpn=False, with_roi=False).to(dev).eval()

@@ -34,10 +34,6 @@ const char* nsgp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py reports
  * the delta over the timed region as "gpu_launches") */
 unsigned long long nsgp_launch_count(void);
-/* contraction engine: 0 = tcgen05/TMA 3xTF32 (product), 1 = SIMT fp32 FFMA
- * (bring-up / on-device cross-check).  Returns the previous value. */
-int nsgp_set_engine(int engine);
-int nsgp_get_engine(void);
 
 /* Optional device timing per kernel kind (bench.py's roofline leg): when enabled,
  * every launch of that kind is bracketed by a cudaEvent pair on its stream.
@@ -188,6 +184,8 @@ int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                         float* t_arena, size_t t_elems,
                         void* plan_dev /* 256-byte aligned */, size_t plan_bytes,
                         nsgp_sgd_plan_t* plan /* host, out */, void* stream);
+/* tensors == NULL: reuse the tensor table uploaded by the previous nsgp_sgd_plan_step of this
+ * plan (valid while no gradient / momentum pointer and no first_step flag has changed). */
 int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                        const nsgp_proj_layer_t* layers, int n_layers, void* plan_dev,
                        const nsgp_sgd_plan_t* plan /* host */, double lr, double momentum,
@@ -280,6 +278,18 @@ int repre_cosine_count_batched(const float* F, int D, const int32_t* rows,
  * (seed, p, column/4). */
 int repre_replay_gather(const float* protos, const float* sigma, const int64_t* idx, int P,
                         int D, uint64_t seed, float* out, void* stream);
+
+/* a12  sampled RoI replay: StandardRoIReplayHead.loss
+ * (mmdet/models/roi_heads/standard_roi_replay_head.py:53-69) draws idx = randperm(M)[:64] and
+ * gathers the six tensors of rois_etc.pth at idx.  All six live on the device; one launch
+ * gathers feats (M,D), cls_targets (M,) int64, cls_weights (M,), bbox_targets (M,4),
+ * bbox_weights (M,4), rois (M,5) into the P-row outputs. */
+int repre_replay_gather_rois(const float* feats, const int64_t* cls_targets,
+                             const float* cls_weights, const float* bbox_targets,
+                             const float* bbox_weights, const float* rois, const int64_t* idx,
+                             int P, int D, float* out_feats, int64_t* out_cls_targets,
+                             float* out_cls_weights, float* out_bbox_targets,
+                             float* out_bbox_weights, float* out_rois, void* stream);
 
 /* extension (no reference counterpart; sklearn KMeans is imported at
  * standard_roi_replay_head.py:18 and never called): Lloyd assignment
@@ -381,6 +391,26 @@ int nsgp_pseudo_label_merge(const float* gt_boxes, const int32_t* gt_offsets,
                             float rpn_thresh, float roi_thresh, double iou_thresh,
                             uint8_t* keep_rpn, uint8_t* keep_roi, int32_t* counts, void* stream);
 
+/* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
+int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
+
+/* C (M x ldc) += A (M x K) * B^T (B is N x K) through the 3xTF32 tcgen05 contraction engine;
+ * a_/b_ are tf32 hi/lo pairs (nsgp_split_tf32) with pitch K. */
+int nsgp_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
+                       const float* b_lo, int M, int N, int K, float* C, int ldc,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Bring-up build only (make BRINGUP=1 -> libnsgp_repre_b200_bringup.so, -DNSGP_BRINGUP):
+ * a second (SIMT fp32) contraction engine for on-device cross-checks, experiment kernels and
+ * in-kernel counters.  None of this is in the shipped library.
+ * ------------------------------------------------------------------------- */
+#ifdef NSGP_BRINGUP
+/* contraction engine: 0 = tcgen05/TMA 3xTF32 (product), 1 = SIMT fp32 FFMA.  Returns the
+ * previous value. */
+int nsgp_set_engine(int engine);
+int nsgp_get_engine(void);
+
 /* bring-up: per-CTA wait/issue cycle counters of the last tcgen05 contraction launched
  * with NSGP_DBG_COUNTERS=1 in the environment (8 counters per CTA, host buffer) */
 int nsgp_debug_read_counters(unsigned long long* out /* host */, int n);
@@ -407,14 +437,7 @@ int nsgp_debug_timeline_read(unsigned long long* out /* host */, int* kinds /* h
  * `cycles` SM clocks, no memory traffic (co-residency probe, scripts/overlap_probe.py) */
 int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, void* stream);
 
-/* generic tf32 hi/lo split of n floats (used by tests and the host layer) */
-int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream);
-
-/* test hook: C (M x ldc) += A (M x K) * B^T (B is N x K), 3xTF32 on the selected
- * engine; a_/b_ are hi/lo pairs with pitch K. */
-int nsgp_debug_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
-                       const float* b_lo, int M, int N, int K, float* C, int ldc,
-                       void* stream);
+#endif /* NSGP_BRINGUP */
 
 #ifdef __cplusplus
 }

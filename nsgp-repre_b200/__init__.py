@@ -17,8 +17,10 @@ sm_100a kernels reached through the C ABI of ``include/nsgp_repre_b200.h``:
   (mmdet/engine/runner/nsrunner_roi_replay.py:946-1073)
 * ``pseudo_labels``                - teacher pseudo-label merge
   (mmdet/models/detectors/faster_rcnn_roi_replay.py:67-108)
-* ``registry``                     - registers the above into mmengine / mmdet
-  when those packages are importable.
+* ``runner.NullSpaceRunnerMixin``  - cal_fea_in / update_optim_transforms of BRNullSpaceRunner
+  (mmdet/engine/runner/nsrunner_roi_replay.py:634-763)
+* ``registry`` / ``mm``            - registers the above into mmengine / mmdet under the
+  reference's names (``import nsgp_repre_b200.mm`` or ``registry.register_all()``).
 
 There is no CPU fallback: importing ``_lib`` raises if the CUDA library has not
 been built (``python -c "import __graft_entry__ as g; g.build()"``).
@@ -29,7 +31,8 @@ from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
 from .covariance import CovarianceHooks, BRNullSpaceCovariance  # noqa: F401
 from .optim import SGDNSCL  # noqa: F401
 from .prototypes import (MultiPrototypeReplay, StandardMultiPrototypeReplayHead,  # noqa: F401
-                         kmeans_prototypes)
+                         StandardRoIReplayHead, SampledRoIReplay, kmeans_prototypes)
+from .runner import NullSpaceRunnerMixin  # noqa: F401
 from .rois import all_gather_different_shape, RoIHarvest  # noqa: F401
 from .roi_extract import SingleRoIExtractor, reduce_class_sums  # noqa: F401
 from .ewc import EWCHook, EWCImportance, register_params  # noqa: F401

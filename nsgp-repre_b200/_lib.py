@@ -6,6 +6,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnsgp_repre_b200.so")
+# developers only: the -DNSGP_BRINGUP build (make BRINGUP=1) with the SIMT cross-check engine
+if os.environ.get("NSGP_BRINGUP_LIB") == "1":
+    LIB_PATH = os.path.join(_HERE, "lib", "libnsgp_repre_b200_bringup.so")
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(
@@ -68,8 +71,6 @@ SIGNATURES = {
     "nsgp_abi_version": (c_int, []),
     "nsgp_last_error": (C.c_char_p, []),
     "nsgp_launch_count": (C.c_ulonglong, []),
-    "nsgp_set_engine": (c_int, [c_int]),
-    "nsgp_get_engine": (c_int, []),
     "nsgp_profile_enable": (c_int, [c_int]),
     "nsgp_profile_read": (c_int, [c_int, C.POINTER(c_double), C.POINTER(C.c_ulonglong)]),
     "nsgp_cov_conv2d_layout": (c_int, [c_int] * 9 + [C.POINTER(CovLayout)]),
@@ -126,6 +127,7 @@ SIGNATURES = {
                                        c_int, c_void_p, c_void_p]),
     "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     C.c_uint64, c_void_p, c_void_p]),
+    "repre_replay_gather_rois": (c_int, [c_void_p] * 7 + [c_int, c_int] + [c_void_p] * 7),
     "repre_kmeans_assign_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "repre_kmeans_assign": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
@@ -147,20 +149,38 @@ SIGNATURES = {
     "nsgp_pseudo_label_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                         c_int, c_float, c_float, c_double, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
+    "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nsgp_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
+}
+
+# symbols of the bring-up build only (include/nsgp_repre_b200.h, #ifdef NSGP_BRINGUP)
+BRINGUP_SIGNATURES = {
+    "nsgp_set_engine": (c_int, [c_int]),
+    "nsgp_get_engine": (c_int, []),
     "nsgp_debug_read_counters": (c_int, [C.POINTER(C.c_ulonglong), c_int]),
     "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                                      c_int, c_void_p]),
     "nsgp_debug_timeline_read": (c_int, [C.POINTER(C.c_ulonglong), C.POINTER(c_int), c_int]),
     "nsgp_debug_occupy": (c_int, [c_int, c_size_t, C.c_longlong, c_int, c_void_p]),
-    "nsgp_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "nsgp_debug_gemm_nt": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_int, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = ABI mismatch, fail loudly
     _fn.restype = _res
     _fn.argtypes = _args
+
+HAS_BRINGUP = hasattr(lib, "nsgp_set_engine")
+if HAS_BRINGUP:
+    for _name, (_res, _args) in BRINGUP_SIGNATURES.items():
+        _fn = getattr(lib, _name)
+        _fn.restype = _res
+        _fn.argtypes = _args
+
+
+def engine() -> int:
+    """0 = tcgen05 (the only engine of the shipped library)."""
+    return int(lib.nsgp_get_engine()) if HAS_BRINGUP else 0
 
 if lib.nsgp_abi_version() != 1:
     raise ImportError("nsgp_repre_b200: ABI version mismatch")

@@ -28,12 +28,13 @@ from ._lib import lib, check, ptr, CovLayout, CovJob, Group, StageGroup
 
 
 class _LayerAcc:
-    __slots__ = ("layout", "acc", "calls")
+    __slots__ = ("layout", "acc", "calls", "in_arena")
 
-    def __init__(self, layout, acc):
+    def __init__(self, layout, acc, in_arena=False):
         self.layout = layout
         self.acc = acc
         self.calls = 0
+        self.in_arena = in_arena
 
 
 class _JobSet:
@@ -103,6 +104,8 @@ class CovarianceHooks:
         self._workspace = None
         self._handles = []
         self._merged = {}           # key -> dense tensor added at finalize (old tasks)
+        self._arena = None          # ONE flat fp32 buffer holding every planned accumulator
+        self._alt = {}              # key -> _LayerAcc of the other layout kind (see _layer)
 
     # ------------------------------------------------------------------ hooks
     def check_if_ignore(self, n: str) -> bool:
@@ -114,8 +117,45 @@ class CovarianceHooks:
         return [(n, m) for n, m in self.model.named_modules()
                 if hasattr(m, "weight") and not self.check_if_ignore(n)]
 
+    def _plan_arena(self):
+        """All accumulators of the hooked Conv2d / Linear modules as views of ONE flat fp32
+        arena, so that the end-of-accumulation SUM over ranks (:746-749) is a single
+        ``ncclAllReduce`` over one buffer.  The accumulator layout of a layer depends only on
+        (Cin, kernel, stride, padding), never on the extent of the map it sees, so it can be
+        planned before the first forward.  Keys that only appear later (``update_cov`` with a
+        foreign key) get their own allocation and join the reduce as extra buffers."""
+        if self._arena is not None or self._layers:
+            return
+        dev = next((p.device for p in self.model.parameters()), None)
+        if dev is None or dev.type != "cuda":
+            return
+        plan, total = [], 0
+        for n, m in self.hooked_modules():
+            layout = CovLayout()
+            if isinstance(m, nn.Conv2d):
+                kh, kw = m.kernel_size
+                sh, sw = m.stride
+                ph, pw = m.padding if not isinstance(m.padding, str) else (0, 0)
+                if lib.nsgp_cov_conv2d_layout(m.in_channels, 64, 64, kh, kw, sh, sw, ph, pw,
+                                              layout) != 0:
+                    continue
+            elif isinstance(m, nn.Linear):
+                if lib.nsgp_cov_linear_layout(m.in_features, layout) != 0:
+                    continue
+            else:
+                continue
+            elems = (layout.acc_bytes // 4 + 63) // 64 * 64         # 256-byte aligned views
+            plan.append((n + ".weight", layout, total, layout.acc_bytes // 4))
+            total += elems
+        if not plan:
+            return
+        self._arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        for key, layout, off, elems in plan:
+            self._layers[key] = _LayerAcc(layout, self._arena[off:off + elems], in_arena=True)
+
     def register(self):
         self._names = {m: n for n, m in self.model.named_modules()}
+        self._plan_arena()
         for _, m in self.hooked_modules():
             self._handles.append(m.register_forward_hook(self.compute_cov))
         # end of a forward of the whole model: launch the grouped contraction
@@ -311,13 +351,30 @@ class CovarianceHooks:
 
     def _layer(self, key: str, layout: CovLayout, device) -> _LayerAcc:
         la = self._layers.get(key)
-        if la is None:
+        if la is None or la.acc.device != device:
+            if la is not None and la.calls:
+                raise _lib.NsgpError("covariance of %s moved from %s to %s" %
+                                     (key, la.acc.device, device))
             acc = torch.zeros(layout.acc_bytes // 4, dtype=torch.float32, device=device)
             la = _LayerAcc(layout, acc)
             self._layers[key] = la
-        elif la.layout.d != layout.d or la.layout.d_int != layout.d_int:
+        elif la.layout.d != layout.d:
             raise _lib.NsgpError("covariance dimension of %s changed (%d -> %d)" %
                                  (key, la.layout.d, layout.d))
+        elif la.layout.kind != layout.kind or la.layout.d_int != layout.d_int:
+            # One key hooked at several extents (the RPN convs are shared by the five FPN
+            # levels, :893-896): a map smaller than 3 px cannot use the autocorrelation form
+            # of a 3x3 conv.  The reference simply adds the Grams; here such a call goes to a
+            # second accumulator of the generic layout and the two are summed on read.
+            alt = self._alt.get(key)
+            if alt is None or alt.acc.device != device:
+                alt = _LayerAcc(layout, torch.zeros(layout.acc_bytes // 4, dtype=torch.float32,
+                                                    device=device))
+                self._alt[key] = alt
+            elif alt.layout.kind != layout.kind or alt.layout.d_int != layout.d_int:
+                raise _lib.NsgpError("%s: a third accumulator layout (kind %d, %d rows) for one "
+                                     "key" % (key, layout.kind, layout.d_int))
+            return alt
         return la
 
     @torch.no_grad()
@@ -349,7 +406,7 @@ class CovarianceHooks:
               "nsgp_cov_conv2d_layout")
         la = self._layer(key, layout, x.device)
         mode = self.mode
-        if mode in ("grouped", "deferred") and lib.nsgp_get_engine() != 0:
+        if mode in ("grouped", "deferred") and _lib.engine() != 0:
             mode = "overlap"            # the bring-up engine has no grouped launch
         if mode in ("grouped", "deferred"):
             self._stage_job(x, key, (Cin, H, W, kh, kw, sh, sw, ph, pw), B, layout, la)
@@ -419,22 +476,41 @@ class CovarianceHooks:
         out = torch.empty(d, d, dtype=torch.float32, device=la.acc.device)
         check(lib.nsgp_cov_finalize(ptr(la.acc), la.layout, ptr(out), 0,
                                     _lib.current_stream(out.device)), "nsgp_cov_finalize")
+        alt = self._alt.get(key)
+        if alt is not None:
+            check(lib.nsgp_cov_finalize(ptr(alt.acc), alt.layout, ptr(out), 1,
+                                        _lib.current_stream(out.device)), "nsgp_cov_finalize")
         if key in self._merged:
             out += self._merged[key].to(out.device)
         return out
 
+    def _live(self):
+        """Keys that received at least one hook call (the reference only creates a key when
+        its module fires, :931-934)."""
+        return [k for k, la in self._layers.items()
+                if la.calls or (k in self._alt and self._alt[k].calls)]
+
     @property
     def fea_in(self) -> dict:
         """dict "<module path>.weight" -> (d,d) fp32, reference layout (:931-934)."""
-        return {k: self._finalize(k) for k in self._layers}
+        return {k: self._finalize(k) for k in self._live()}
 
     def keys(self):
-        return list(self._layers.keys())
+        return self._live()
+
+    def reduce_buffers(self):
+        """The fp32 buffers the SUM over ranks runs on: the arena first, then every
+        accumulator allocated outside it."""
+        bufs = [] if self._arena is None else [self._arena]
+        bufs += [la.acc for la in self._layers.values() if not la.in_arena]
+        bufs += [la.acc for la in self._alt.values()]
+        return bufs
 
     def reset(self):
         self.join()
-        for la in self._layers.values():
-            la.acc.zero_()
+        for b in self.reduce_buffers():
+            b.zero_()
+        for la in list(self._layers.values()) + list(self._alt.values()):
             la.calls = 0
         self._merged = {}
 
@@ -447,12 +523,14 @@ class CovarianceHooks:
                 dist.get_world_size(group) == 1 or not self._layers:
             return
         self.join()
-        # in place, one collective per accumulator, all in flight together: no 0.6 GB
-        # flatten-and-copy round trip; NCCL pipelines them back to back over NVLink
-        accs = [la.acc for la in self._layers.values()]
+        # in place on the flat arena: ONE ncclAllReduce over NVLink for every planned layer;
+        # accumulators outside the arena (foreign update_cov keys, second-layout keys) follow
+        # as one coalesced group call
+        accs = self.reduce_buffers()
+        if len(accs) == 1:
+            dist.all_reduce(accs[0], op=dist.ReduceOp.SUM, group=group)
+            return
         if dist.get_backend(group) == "nccl":
-            # one NCCL group call for all accumulators: a single fused launch instead of 61
-            # latency-bound ones (5.6 MB each on average)
             try:
                 from torch.distributed.distributed_c10d import _coalescing_manager
                 with _coalescing_manager(group=group, device=accs[0].device, async_ops=True) as cm:
@@ -470,7 +548,7 @@ class CovarianceHooks:
         """``fea_in[k] + old_fea_in[k]`` for task_id != 1 (:750-753); keys of the
         current run that are ignored are dropped there, missing old keys raise
         KeyError like the reference's dict lookup."""
-        for k in self._layers:
+        for k in self._live():
             self._merged[k] = old_fea_in[k] if k not in self._merged else \
                 self._merged[k] + old_fea_in[k]
 

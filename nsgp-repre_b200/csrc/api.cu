@@ -13,7 +13,9 @@ namespace nsgp {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+#ifdef NSGP_BRINGUP
 int g_engine = 0;
+#endif
 
 int g_profile = 0;
 namespace {
@@ -28,7 +30,7 @@ int g_tl_n = 0;
 int g_tl_kind[kTlSlots];
 }
 unsigned long long* timeline_slot(int kind) {
-  static const bool on = getenv("NSGP_TIMELINE") != nullptr;
+  static const bool on = nsgp_env("NSGP_TIMELINE") != nullptr;
   if (!on || g_tl_n >= kTlSlots) return nullptr;
   if (g_tl_dev == nullptr) {
     if (cudaMalloc(&g_tl_dev, kTlSlots * 2 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
@@ -60,7 +62,10 @@ void set_error(const char* fmt, ...) {
 }
 
 int contraction(const ContractionArgs& a, cudaStream_t stream) {
-  return g_engine == 1 ? contraction_simt(a, stream) : contraction_tc(a, stream);
+#ifdef NSGP_BRINGUP
+  if (g_engine == 1) return contraction_simt(a, stream);
+#endif
+  return contraction_tc(a, stream);
 }
 
 static int pick_splits(int tiles, int nkb) {
@@ -85,12 +90,14 @@ extern "C" {
 int nsgp_abi_version(void) { return NSGP_ABI_VERSION; }
 const char* nsgp_last_error(void) { return g_err; }
 unsigned long long nsgp_launch_count(void) { return g_launches; }
+#ifdef NSGP_BRINGUP
 int nsgp_set_engine(int engine) {
   int prev = g_engine;
   if (engine == 0 || engine == 1) g_engine = engine;
   return prev;
 }
 int nsgp_get_engine(void) { return g_engine; }
+#endif
 
 int nsgp_profile_enable(int on) {
   int prev = g_profile;
@@ -180,12 +187,17 @@ static int cov_layers_group_build(const ConvGeom* geoms, float* const* stages, f
       ac_s.push_back(stages[i]);
       ac_a.push_back(accs[i]);
     }
-    for (int q = 0; q < np; ++q)            // plain Grams of one operand: wide-tile kernel
-      (gram_wide_eligible(p[q]) ? wide : probs).push_back(p[q]);
+    for (int q = 0; q < np; ++q) {
+#ifdef NSGP_BRINGUP
+      if (gram_wide_eligible(p[q])) { wide.push_back(p[q]); continue; }   // NSGP_WIDE_KERNEL=1
+#endif
+      probs.push_back(p[q]);
+    }
   }
   int rc = group_table_build(probs.data(), (int)probs.size(), kProfGram, table_dev, table_bytes,
                              gi, stream);
   if (rc) return rc;
+#ifdef NSGP_BRINGUP
   if (!wide.empty()) {
     const size_t off = (size_t)round_up((long long)gi->bytes, 256);
     NSGP_REQUIRE(off <= table_bytes, "cov group: table too small");
@@ -198,6 +210,7 @@ static int cov_layers_group_build(const ConvGeom* geoms, float* const* stages, f
     gi->sub[3] = sg;
     gi->bytes = sg.off_items + (size_t)sg.n_items * 32;
   }
+#endif
   if (!ac_g.empty()) {
     const size_t off = (size_t)round_up((long long)gi->bytes, 256);
     NSGP_REQUIRE(off <= table_bytes, "cov group: table too small");
@@ -225,7 +238,9 @@ static size_t cov_layers_group_bytes(const ConvGeom* geoms, int n) {
   }
   // eligible problems move to the wide table: bound both tables by the full list
   return group_table_bytes(probs.data(), (int)probs.size()) + 1024 +
+#ifdef NSGP_BRINGUP
          gram_wide_table_bytes(probs.data(), (int)probs.size()) +
+#endif
          autocorr_table_bytes(ac_g.data(), (int)ac_g.size());
 }
 
@@ -546,6 +561,7 @@ int nsgp_sgd_plan_build(const nsgp_sgd_tensor_t* tensors, int n_tensors,
   if (rc) return rc;
   plan->n_tensors = n_tensors;
   plan->total_chunks = 0;
+  for (int i = 0; i < n_tensors; ++i) plan->total_chunks += sgd_chunks(tensors[i].numel);
   plan->all_have_buf = 0;
   plan->off_chunks = off_chunks;
   plan->off_group = off_group;
@@ -563,23 +579,29 @@ int nsgp_sgd_plan_step(const nsgp_sgd_tensor_t* tensors, int n_tensors,
                        const nsgp_sgd_plan_t* plan, double lr, double momentum, double dampening,
                        double weight_decay, int nesterov, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  NSGP_REQUIRE(tensors && plan_dev && plan, "sgd_plan_step: null pointer");
+  NSGP_REQUIRE(plan_dev && plan, "sgd_plan_step: null pointer");
   NSGP_REQUIRE(n_tensors == plan->n_tensors, "sgd_plan_step: plan was built for %d tensors",
                plan->n_tensors);
-  // the tensor table (weights, gradients, momentum buffers, first-step flags) is
-  // re-uploaded every step - gradients are usually fresh allocations; the grouped
-  // GEMM table (staged updates, projectors, weights) is the part that is reused
-  std::vector<SgdTensorDev> host;
-  std::vector<int> chunk_start;
-  int rc = sgd_tables(tensors, n_tensors, layers, n_layers, momentum, &host, &chunk_start);
-  if (rc) return rc;
+  // The tensor table (weights, gradients, momentum buffers, first-step flags) is uploaded
+  // when the caller passes it; tensors == NULL means "the table uploaded by the previous
+  // step is still valid" (same gradient / momentum pointers, same first-step flags).  The
+  // grouped GEMM table (staged updates, projectors, weights) is always reused.
   SgdTensorDev* dev_t = reinterpret_cast<SgdTensorDev*>(plan_dev);
   int* dev_c = reinterpret_cast<int*>((char*)plan_dev + plan->off_chunks);
-  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_t, host.data(), host.size() * sizeof(SgdTensorDev),
-                                  cudaMemcpyHostToDevice, stream));
-  NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_c, chunk_start.data(), chunk_start.size() * sizeof(int),
-                                  cudaMemcpyHostToDevice, stream));
-  rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, chunk_start[n_tensors], (float)lr,
+  int rc = 0;
+  if (tensors != nullptr) {
+    std::vector<SgdTensorDev> host;
+    std::vector<int> chunk_start;
+    rc = sgd_tables(tensors, n_tensors, layers, n_layers, momentum, &host, &chunk_start);
+    if (rc) return rc;
+    NSGP_REQUIRE(chunk_start[n_tensors] == plan->total_chunks,
+                 "sgd_plan_step: tensor sizes differ from the plan");
+    NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_t, host.data(), host.size() * sizeof(SgdTensorDev),
+                                    cudaMemcpyHostToDevice, stream));
+    NSGP_CHECK_CUDA(cudaMemcpyAsync(dev_c, chunk_start.data(), chunk_start.size() * sizeof(int),
+                                    cudaMemcpyHostToDevice, stream));
+  }
+  rc = launch_sgd_prologue(dev_t, dev_c, n_tensors, plan->total_chunks, (float)lr,
                            (float)momentum, (float)(1.0 - dampening), (float)weight_decay,
                            nesterov, stream);
   if (rc) return rc;
@@ -922,6 +944,24 @@ int repre_replay_gather(const float* protos, const float* sigma, const int64_t* 
                               (cudaStream_t)stream_);
 }
 
+int repre_replay_gather_rois(const float* feats, const int64_t* cls_targets,
+                             const float* cls_weights, const float* bbox_targets,
+                             const float* bbox_weights, const float* rois, const int64_t* idx,
+                             int P, int D, float* out_feats, int64_t* out_cls_targets,
+                             float* out_cls_weights, float* out_bbox_targets,
+                             float* out_bbox_weights, float* out_rois, void* stream_) {
+  NSGP_REQUIRE(feats && cls_targets && cls_weights && bbox_targets && bbox_weights && rois &&
+                   idx && out_feats && out_cls_targets && out_cls_weights && out_bbox_targets &&
+                   out_bbox_weights && out_rois,
+               "replay_gather_rois: null pointer");
+  NSGP_REQUIRE(P >= 0 && D > 0, "replay_gather_rois: bad sizes");
+  return launch_replay_gather_rois(feats, (const long long*)cls_targets, cls_weights,
+                                   bbox_targets, bbox_weights, rois, (const long long*)idx, P, D,
+                                   out_feats, (long long*)out_cls_targets, out_cls_weights,
+                                   out_bbox_targets, out_bbox_weights, out_rois,
+                                   (cudaStream_t)stream_);
+}
+
 size_t repre_kmeans_assign_workspace_bytes(int n, int k, int D) {
   size_t n8 = (size_t)round_up(n, 8), k8 = (size_t)round_up(k, 8);
   return 2 * (n8 + k8) * (size_t)D * 4 + n8 * (size_t)round_up(k, 4) * 4 + k8 * 4 + 4096;
@@ -966,6 +1006,7 @@ int repre_kmeans_assign(const float* X, int n, int D, const float* centres, int 
   return launch_kmeans_argmin(dots, n, k, ld, cn, (long long*)labels, stream);
 }
 
+#ifdef NSGP_BRINGUP
 int nsgp_debug_read_counters(unsigned long long* out, int n) {
   NSGP_REQUIRE(out && n != 0 && n <= 160 * 8 && n >= -160 * 8, "debug_read_counters: bad arguments");
   if (n < 0) return debug_read_ac_counters(out, -n);     // autocorrelation kernel's counters
@@ -1007,15 +1048,17 @@ int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int ro
                          (cudaStream_t)stream_);
 }
 
+#endif  // NSGP_BRINGUP
+
 int nsgp_split_tf32(const float* src, float* hi, float* lo, size_t n, void* stream_) {
   NSGP_REQUIRE(src && hi && lo, "split: null pointer");
   return launch_split(src, hi, lo, (long long)n, (cudaStream_t)stream_);
 }
 
-int nsgp_debug_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
+int nsgp_gemm_nt(const float* a_hi, const float* a_lo, const float* b_hi,
                        const float* b_lo, int M, int N, int K, float* C, int ldc,
                        void* stream_) {
-  NSGP_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "debug_gemm: null pointer");
+  NSGP_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "gemm_nt: null pointer");
   ContractionArgs a{};
   a.A = matrix_operand(a_hi, a_lo, M, K, K);
   a.B = matrix_operand(b_hi, b_lo, N, K, K);

@@ -175,7 +175,15 @@ int gram_wide_launch(const void* table_dev, const SubGroup& sg, cudaStream_t str
 int contraction_simt(const ContractionArgs& a, cudaStream_t stream);
 int contraction_tc(const ContractionArgs& a, cudaStream_t stream);      // tcgen05/TMA
 int contraction(const ContractionArgs& a, cudaStream_t stream);         // dispatch on g_engine
+// One engine ships: tcgen05.  A -DNSGP_BRINGUP build (make BRINGUP=1) adds the SIMT
+// cross-check engine, the experiment kernels and the environment switches of DESIGN.md 6b.
+#ifdef NSGP_BRINGUP
 extern int g_engine;   // 0 = tcgen05 (product), 1 = SIMT (bring-up / cross-check)
+static inline const char* nsgp_env(const char* name) { return getenv(name); }
+#else
+constexpr int g_engine = 0;
+static inline const char* nsgp_env(const char*) { return nullptr; }
+#endif
 
 // number of 32-wide K blocks of an operand
 static inline int k_blocks(const Operand& o) { return ceil_div(o.K, 32); }

@@ -41,7 +41,7 @@ constexpr uint32_t kTile = 2 * kPlane;      // hi | lo
 // accumulate ~1.9e-8 per step); NSGP_AC_ROWS overrides for experiments
 static int rows_per_item() {
   static const int v = [] {
-    const char* e = getenv("NSGP_AC_ROWS");
+    const char* e = nsgp_env("NSGP_AC_ROWS");
     const int r = e ? atoi(e) : 48;
     return r >= 4 && r <= 256 ? r : 48;
   }();
@@ -354,7 +354,7 @@ int debug_read_ac_counters(unsigned long long* out, int n) {
 
 bool autocorr_kernel_enabled() {
   static const bool on = [] {
-    const char* e = getenv("NSGP_AC_KERNEL");          // 0 disables (generic GEMM problems)
+    const char* e = nsgp_env("NSGP_AC_KERNEL");          // 0 disables (generic GEMM problems)
     return !(e && e[0] == '0');
   }();
   return on;
@@ -454,15 +454,15 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   // L1 of co-resident staging kernels - measured equal end to end (scripts/overlap_probe.py:
   // what the staging kernels lose next to this kernel is L1 capacity for loads in flight)
   static const int sa_n = [] {
-    const char* e = getenv("NSGP_AC_SA");
+    const char* e = nsgp_env("NSGP_AC_SA");
     return (e && e[0] == '2') ? 2 : 3;
   }();
   static const int wide_n = [] {
-    const char* e = getenv("NSGP_AC_WIDE");            // 0: three N = 128 MMAs per product
+    const char* e = nsgp_env("NSGP_AC_WIDE");            // 0: three N = 128 MMAs per product
     return (e && e[0] == '0') ? 0 : 1;
   }();
   static const int tmem_a = [] {
-    const char* e = getenv("NSGP_AC_TMEMA");           // 1: A operand from tensor memory
+    const char* e = nsgp_env("NSGP_AC_TMEMA");           // 1: A operand from tensor memory
     return (e && e[0] == '1') ? 1 : 0;
   }();
   const size_t smem_bytes = (size_t)(sa_n + SB) * kTile + 1024 + 256;
@@ -477,7 +477,7 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   const AcItem* items = reinterpret_cast<const AcItem*>((const char*)table_dev + sg.off_items);
   const int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
   ProfScope prof(kProfGram, stream);
-  static const int dbg = getenv("NSGP_DBG_COUNTERS") ? 1 : 0;
+  static const int dbg = nsgp_env("NSGP_DBG_COUNTERS") ? 1 : 0;
   autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10),
                                                            wide_n, tmem_a);
   NSGP_LAUNCHED();

@@ -490,15 +490,15 @@ void fill_operand(const Operand& o, int br, TcOperand* d) {
 constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 + 256;
 
 int dbg_counters() {
-  static const int d = (getenv("NSGP_DBG_COUNTERS") ? 1 : 0) | (getenv("NSGP_DBG_MMA2") ? 2 : 0) |
-                       (getenv("NSGP_DBG_HALFLOAD") ? 4 : 0) | (getenv("NSGP_DBG_ALLPOLL") ? 8 : 0);
+  static const int d = (nsgp_env("NSGP_DBG_COUNTERS") ? 1 : 0) | (nsgp_env("NSGP_DBG_MMA2") ? 2 : 0) |
+                       (nsgp_env("NSGP_DBG_HALFLOAD") ? 4 : 0) | (nsgp_env("NSGP_DBG_ALLPOLL") ? 8 : 0);
   return d;
 }
 
 // K blocks the L2 prefetch cursor runs ahead of the loads (NSGP_PREFETCH overrides)
 int prefetch_distance() {
   static const int d = [] {
-    const char* e = getenv("NSGP_PREFETCH");
+    const char* e = nsgp_env("NSGP_PREFETCH");
     return e ? atoi(e) : 8;
   }();
   return d;
@@ -521,6 +521,9 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
                   const TcItem* gitems, int n_items, int kind, cudaStream_t stream) {
   if (n_items <= 0) return 0;
   ProfScope prof(kind, stream);
+#ifndef NSGP_BRINGUP
+  NSGP_REQUIRE(!pair, "the CTA-pair kernel is a bring-up build feature");
+#else
   if (pair) {
     int rc = configure_kernel<true>();
     if (rc) return rc;
@@ -541,7 +544,11 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
     NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<true>, maps, p, gprobs, gitems,
                                        n_items, prefetch_distance(), dbg_counters(),
                                        (unsigned long long*)nullptr));
-  } else {
+    NSGP_LAUNCHED();
+    return 0;
+  }
+#endif
+  {
     int rc = configure_kernel<false>();
     if (rc) return rc;
     const int grid = n_items < sm_count() ? n_items : sm_count();
@@ -562,8 +569,12 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
 // pair for covariance problems whose rows are a multiple of 256 (no padding waste);
 // NSGP_PAIR_KERNEL=0 never, 1 every same-operand Gram, 3 everything with > 128 rows.
 bool want_pair(const ContractionArgs& a) {
+#ifndef NSGP_BRINGUP
+  (void)a;
+  return false;      // measured slower end to end: bring-up builds only
+#else
   static const int force = [] {
-    const char* e = getenv("NSGP_PAIR_KERNEL");
+    const char* e = nsgp_env("NSGP_PAIR_KERNEL");
     return e ? atoi(e) : -1;
   }();
   const bool gram = a.epi == kEpiGramAtomic;
@@ -574,6 +585,7 @@ bool want_pair(const ContractionArgs& a) {
   if (force == 1) return gram && same;
   // default: autocorrelation-layout problems (they carry an l2_group) on 256-multiples
   return a.l2_group > 0 && a.A.rows % 256 == 0 && a.n_cols % 256 == 0 && a.A.K >= 1024;
+#endif
 }
 
 // Validates one problem, encodes its tensor maps and fills every field of the
@@ -613,7 +625,7 @@ int build_problem(const ContractionArgs& a, bool pair, TcProblem* out) {
   NSGP_REQUIRE(!p.gram || p.tiles_m == p.tiles_n, "Gram: operands must have the same rows");
   p.n_tiles = p.gram ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   static const int vec_red = [] {
-    const char* e = getenv("NSGP_VEC_RED");
+    const char* e = nsgp_env("NSGP_VEC_RED");
     return (e && e[0] == '0') ? 0 : 1;
   }();
   p.vec_red = (vec_red && a.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
@@ -627,7 +639,7 @@ int build_problem(const ContractionArgs& a, bool pair, TcProblem* out) {
 // accumulator for all three products (12 steps per K block).
 int chain_limit(const TcParams& p) {
   static const int gram_chain = [] {
-    const char* e = getenv("NSGP_CHAIN");             // bring-up override
+    const char* e = nsgp_env("NSGP_CHAIN");             // bring-up override
     return e ? atoi(e) : kChainGram;
   }();
   if (p.chain > 0) return p.pair && p.chain > 32 ? 32 : p.chain;
@@ -785,8 +797,11 @@ int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stre
     int rc = launch_kernel(k == 1, dummy_maps, dummy, probs, items, sg.n_items, info.kind, stream);
     if (rc) return rc;
   }
-  int rc = gram_wide_launch(table_dev, info.sub[3], stream);
+  int rc = 0;
+#ifdef NSGP_BRINGUP
+  rc = gram_wide_launch(table_dev, info.sub[3], stream);
   if (rc) return rc;
+#endif
   // autocorrelation sub-table last: its long items fill the machine best once the small
   // problems are out of the way
   return autocorr_launch(table_dev, info.sub[2], stream);

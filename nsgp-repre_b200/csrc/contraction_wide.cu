@@ -237,7 +237,7 @@ bool gram_wide_enabled() {
     // measured at configs[1] (scripts/bench_cov.py, NSGP_TIMELINE=1): parity-green, but the
     // 2-stage ring loses more than the wider tile gains - 1.53 ms + 0.16 ms of left-over
     // generic problems against 1.34 ms for the generic kernel alone -> opt-in
-    const char* e = getenv("NSGP_WIDE_KERNEL");
+    const char* e = nsgp_env("NSGP_WIDE_KERNEL");
     return e && e[0] == '1';
   }();
   return on;

@@ -64,7 +64,7 @@ static inline bool flat_tiled_enabled() {
   static const bool on = [] {
     // measured (scripts/bench_cov.py, NSGP_TIMELINE=1): correct, but the generic contraction
     // launch takes 1.33 ms either way and staging gets 2 % slower -> opt-in
-    const char* e = getenv("NSGP_FLAT_TILED");
+    const char* e = nsgp_env("NSGP_FLAT_TILED");
     return e && e[0] == '1';
   }();
   return on;
@@ -89,14 +89,14 @@ static inline int make_conv_geom(int C, int H, int W, int kh, int kw, int sh, in
   g.d = C * kh * kw;
   g.ncopy = 1; g.nrowphase = 1;
   const bool one_by_one = (kh == 1 && kw == 1 && ph == 0 && pw == 0);
-  static const bool no_autocorr = getenv("NSGP_NO_AUTOCORR") != nullptr;   // bring-up switch
+  static const bool no_autocorr = nsgp_env("NSGP_NO_AUTOCORR") != nullptr;   // bring-up switch
   if (!no_autocorr && kh == 3 && kw == 3 && sh == 1 && sw == 1 && ph == 1 && pw == 1 &&
       C % 8 == 0 && H >= 3 && W >= 3) {
     g.mode = kModeAutocorr;
     g.T = 9; g.Cs = C; g.ncopy = 3;
     g.Hs = H + 2;                                  // two zero rows below
     static const int ws_align = [] {
-      const char* e = getenv("NSGP_WS_ALIGN");      // bring-up: row pitch alignment (floats)
+      const char* e = nsgp_env("NSGP_WS_ALIGN");      // bring-up: row pitch alignment (floats)
       return e ? atoi(e) : 4;
     }();
     g.Ws = (int)round_up(W + 2, ws_align);         // >= two zero columns on the right

@@ -509,6 +509,53 @@ int launch_replay_gather(const float* protos, const float* sigma, const long lon
 }
 
 // ---------------------------------------------------------------------------
+// Sampled RoI replay (StandardRoIReplayHead.loss, standard_roi_replay_head.py:53-69):
+// idx = randperm(M)[:64]; the six stored tensors are gathered at idx.  One launch: the
+// feature rows (D = 12544) as float4 columns, the five small per-RoI records by the
+// first threads of the row's first block.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+replay_gather_rois_kernel(const float* __restrict__ feats, const long long* __restrict__ cls_t,
+                          const float* __restrict__ cls_w, const float* __restrict__ bbox_t,
+                          const float* __restrict__ bbox_w, const float* __restrict__ rois,
+                          const long long* __restrict__ idx, int D, float* __restrict__ o_feats,
+                          long long* __restrict__ o_cls_t, float* __restrict__ o_cls_w,
+                          float* __restrict__ o_bbox_t, float* __restrict__ o_bbox_w,
+                          float* __restrict__ o_rois) {
+  const int p = blockIdx.y;
+  const long long src = idx[p];
+  const int q = blockIdx.x * 128 + threadIdx.x;
+  if (q * 4 < D)
+    reinterpret_cast<float4*>(o_feats + (long long)p * D)[q] =
+        __ldg(reinterpret_cast<const float4*>(feats + src * D) + q);
+  if (blockIdx.x == 0) {
+    const int t = threadIdx.x;
+    if (t == 0) { o_cls_t[p] = cls_t[src]; o_cls_w[p] = cls_w[src]; }
+    if (t < 4) {
+      o_bbox_t[p * 4 + t] = bbox_t[src * 4 + t];
+      o_bbox_w[p * 4 + t] = bbox_w[src * 4 + t];
+    }
+    if (t < 5) o_rois[p * 5 + t] = rois[src * 5 + t];
+  }
+}
+
+int launch_replay_gather_rois(const float* feats, const long long* cls_t, const float* cls_w,
+                              const float* bbox_t, const float* bbox_w, const float* rois,
+                              const long long* idx, int P, int D, float* o_feats,
+                              long long* o_cls_t, float* o_cls_w, float* o_bbox_t,
+                              float* o_bbox_w, float* o_rois, cudaStream_t stream) {
+  NSGP_REQUIRE(D % 4 == 0, "replay_gather_rois: D must be a multiple of 4");
+  if (P == 0) return 0;
+  dim3 grid(ceil_div(D / 4, 128), P);
+  ProfScope prof(kProfRepre, stream);
+  replay_gather_rois_kernel<<<grid, 128, 0, stream>>>(feats, cls_t, cls_w, bbox_t, bbox_w, rois,
+                                                      idx, D, o_feats, o_cls_t, o_cls_w, o_bbox_t,
+                                                      o_bbox_w, o_rois);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // k-means assignment epilogue (extension, parity unpinned): given the dot
 // products X C^T from the contraction engine and the centre norms, label =
 // argmin_k (|c_k|^2 - 2 x.c_k), ties -> lowest k.

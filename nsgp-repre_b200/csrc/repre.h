@@ -37,6 +37,11 @@ int launch_threshold_count_batched(const float* S_all, const ClassExtent* ext_de
                                    int* counts_all, cudaStream_t s);
 int launch_replay_gather(const float* protos, const float* sigma, const long long* idx, int P,
                          int D, unsigned long long seed, float* out, cudaStream_t s);
+int launch_replay_gather_rois(const float* feats, const long long* cls_t, const float* cls_w,
+                              const float* bbox_t, const float* bbox_w, const float* rois,
+                              const long long* idx, int P, int D, float* o_feats,
+                              long long* o_cls_t, float* o_cls_w, float* o_bbox_t,
+                              float* o_bbox_w, float* o_rois, cudaStream_t s);
 int launch_row_sqnorm(const float* X, int n, int D, int ld, float* out, cudaStream_t s);
 int launch_kmeans_argmin(const float* dots, int n, int k, int ld, const float* cnorm,
                          long long* labels, cudaStream_t s);

@@ -607,7 +607,7 @@ static void stage_prefer_shared_carveout() {
   static const bool once = [] {
     // measured: slower on its own (5.6 -> 6.1 ms per covariance pass) and no better when
     // overlapped (5.0 -> 5.2 ms), so it is opt-in
-    const char* e = getenv("NSGP_STAGE_CARVEOUT");
+    const char* e = nsgp_env("NSGP_STAGE_CARVEOUT");
     if (!(e && e[0] == '1')) return true;
     const int co = cudaSharedmemCarveoutMaxShared;
 #define NSGP_CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
@@ -891,7 +891,7 @@ int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const 
                        cudaStream_t stream) {
   if (info.n_jobs == 0) return 0;
   static const bool carve_once = [] {
-    const char* e = getenv("NSGP_STAGE_GROUP_CARVEOUT");
+    const char* e = nsgp_env("NSGP_STAGE_GROUP_CARVEOUT");
     const int co = e ? atoi(e) : -1;
     if (co >= 0)
       cudaFuncSetAttribute(stage_group_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
@@ -911,7 +911,7 @@ int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const 
     // blocks per SM: few enough that the persistent contraction CTA (224 threads, ~16 K
     // registers) of the previous forward always finds room next to them
     static const int per_sm = [] {
-      const char* e = getenv("NSGP_STAGE_BLOCKS_PER_SM");
+      const char* e = nsgp_env("NSGP_STAGE_BLOCKS_PER_SM");
       const int v = e ? atoi(e) : 3;
       return v > 0 && v <= 8 ? v : 3;
     }();

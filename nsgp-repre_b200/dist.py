@@ -50,3 +50,49 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def shard_by_cost(costs, world: int):
+    """Owner rank of every item, longest-processing-time first: items sorted by descending
+    cost, each to the currently least-loaded rank (ties -> lowest rank).  Deterministic, so
+    every rank computes the same plan without communication (projector build
+    shards by layer, balance by d^3)."""
+    load = [0.0] * max(1, world)
+    owner = [0] * len(costs)
+    for i in sorted(range(len(costs)), key=lambda k: (-float(costs[k]), k)):
+        r = min(range(len(load)), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += float(costs[i])
+    return owner
+
+
+def sharded_compute(shapes, costs, compute, device, dtype=torch.float32, group=None):
+    """``compute(i) -> tuple of tensors`` (shapes[i] = their shapes) evaluated by item i's owner
+    only; every rank ends up with every result.  One flat buffer per owner travels in ONE
+    broadcast (NCCL over NVLink; gloo in the CPU tests) - ``world`` collectives in total,
+    all in flight together.  Returns list[tuple[Tensor]] (views of the flat buffers)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    owner = shard_by_cost(costs, world)
+    numel = [[int(torch.Size(sh).numel()) for sh in shp] for shp in shapes]
+    flat = [torch.empty(sum(sum(numel[i]) for i in range(len(shapes)) if owner[i] == r),
+                        dtype=dtype, device=device) for r in range(world)]
+    off = [0] * world
+    out = []
+    for i, shp in enumerate(shapes):
+        r = owner[i]
+        views = []
+        for sh, n in zip(shp, numel[i]):
+            views.append(flat[r][off[r]:off[r] + n].view(sh))
+            off[r] += n
+        if r == rank:
+            for v, t in zip(views, compute(i)):
+                v.copy_(t)
+        out.append(tuple(views))
+    if world > 1:
+        works = [dist.broadcast(flat[r], src=dist.get_global_rank(group, r) if group is not None
+                                else r, group=group, async_op=True)
+                 for r in range(world) if flat[r].numel()]
+        for w in works:
+            w.wait()
+    return out

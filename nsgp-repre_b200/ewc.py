@@ -29,20 +29,14 @@ from ._lib import lib, check, EwcTensor
 
 
 def register_params(model, must_names=("bn",), ignore_names=("teacher_model",)) -> dict:
-    """:1006-1031 - ``{name: parameter}`` of the tensors EWC regularises."""
-    reg = {}
-    for n, p in model.named_parameters():
-        ignore = True
-        must = False if len(must_names) != 0 else True
-        for ignore_name in ignore_names:
-            if ignore_name in n:
-                ignore = False
-        for must_name in must_names:
-            if must_name in n:
-                must = True
-        if ignore and must:
-            reg[n] = p
-    return reg
+    """:1006-1031 - ``{name: parameter}`` of the tensors EWC regularises: names that contain
+    one of ``must_names`` (every name when that tuple is empty) and none of ``ignore_names``."""
+    def wanted(name):
+        if any(tag in name for tag in ignore_names):
+            return False
+        return not must_names or any(tag in name for tag in must_names)
+
+    return {name: param for name, param in model.named_parameters() if wanted(name)}
 
 
 def _table(n: int, device, cache: dict) -> torch.Tensor:
@@ -196,7 +190,10 @@ class EWCHook:
 
     def _tensor_table(self, params):
         """Host table of the registered tensors; rebuilt only when an address changes."""
-        key = tuple(p.data_ptr() for p in params)
+        # parameter addresses AND the stacks they are paired with: a rebuilt stack (a task was
+        # appended to ewc_reg_terms) has new storage even when no parameter moved
+        key = (tuple(p.data_ptr() for p in params), self._stack_key,
+               tuple((imp.data_ptr(), old.data_ptr()) for imp, old, _ in self._stacks))
         if self._cache.get("arr_key") != key:
             arr = (EwcTensor * len(params))()
             for k, (p, (imp, old, tasks)) in enumerate(zip(params, self._stacks)):

@@ -45,10 +45,9 @@ class SGDNSCL(Optimizer):
         self._prepared = {}     # name -> (key, pt_hi, pt_lo)
         self._stage = {}        # name -> (u_hi, u_lo)
         self._workspace = None
-        self._plans = {}        # group index -> (signature, device buffer, SgdPlan)
+        self._plans = {}        # group index -> cached tables / T arena / plan (_build_group_cache)
         self._lowrank = {}      # name -> (P tensor, P._version, U (d,r), scale) from get_transforms
         self._lowrank_prepared = {}
-        self._t_arena = None
         self.lowrank_max_ratio = 0.25   # use G - (G U) U^T while r <= ratio * d
 
     def __setstate__(self, state):
@@ -87,22 +86,40 @@ class SGDNSCL(Optimizer):
 
     @torch.no_grad()
     def get_eigens(self, fea_in, distinguisher=None):
-        """Spectrum + basis of every protected layer's covariance (:360-380)."""
+        """Spectrum + basis of every protected layer's covariance (:360-380).
+
+        The layers are independent d x d problems: under ``torch.distributed`` they are
+        sharded over the ranks (owner by descending d^3, ``dist.shard_by_cost``), every owner
+        runs cuSOLVER syevd on its layers and one broadcast per owner hands the results to
+        everybody - the reference runs all of them on every rank, twice."""
+        from . import dist as D
+        jobs = []
         for group in self.param_groups:
             if group["svd"] is False:
                 continue
             for n, p in zip(group["names"], group["params"]):
                 if n not in fea_in.keys():
                     continue
-                cov = fea_in[n]
-                _lib.require_cuda(cov, "covariance of %s" % n)
-                work = cov.to(self.eig_dtype)
-                work = (work + work.t()) * 0.5
-                evals, evecs = torch.linalg.eigh(work)          # cuSOLVER syevd
-                order = torch.argsort(evals.abs(), descending=True)
-                eigen = self.eigens[n]
-                eigen["eigen_value"] = evals.abs()[order].to(torch.float32)
-                eigen["eigen_vector"] = evecs[:, order].to(torch.float32)
+                _lib.require_cuda(fea_in[n], "covariance of %s" % n)
+                jobs.append(n)
+        if not jobs:
+            return
+
+        def eig(i):
+            cov = fea_in[jobs[i]]
+            work = cov.to(self.eig_dtype)
+            work = (work + work.t()) * 0.5
+            evals, evecs = torch.linalg.eigh(work)          # cuSOLVER syevd
+            order = torch.argsort(evals.abs(), descending=True)
+            return evals.abs()[order].to(torch.float32), evecs[:, order].to(torch.float32)
+
+        dims = [int(fea_in[n].shape[0]) for n in jobs]
+        res = D.sharded_compute([((d,), (d, d)) for d in dims], [float(d) ** 3 for d in dims],
+                                eig, fea_in[jobs[0]].device)
+        for n, (vals, vecs) in zip(jobs, res):
+            eigen = self.eigens[n]
+            eigen["eigen_value"] = vals
+            eigen["eigen_vector"] = vecs
 
     @torch.no_grad()
     def get_transforms(self, offset=0.0):
@@ -186,6 +203,87 @@ class SGDNSCL(Optimizer):
             self._stage[name] = st
         return st
 
+    def _build_group_cache(self, gi, group, device):
+        """Everything of a param group that survives from step to step: the ctypes tensor /
+        layer tables, the T arena of its low-rank layers and the prepared plan.  Rebuilt when a
+        parameter, a projector or the set of names changes (``_group_key``)."""
+        names, params = group["names"], group["params"]
+        n_t = len(params)
+        tensors = (SgdTensor * n_t)()
+        layers, t_need, protos = [], [], []
+        svd = group["svd"]
+        for i, (n, p) in enumerate(zip(names, params)):
+            t = tensors[i]
+            t.w, t.numel, t.layer = p.data_ptr(), p.numel(), -1
+            if svd and len(self.transforms) > 0 and n in self.transforms.keys():
+                P = self.transforms[n]
+                cout = p.shape[0]
+                dd = p.numel() // cout
+                u_hi, u_lo = self._staging(n, p)
+                low = self._prepare_lowrank(n, P)
+                if low is None:
+                    hi, lo = self._prepare(n, P)
+                    L = ProjLayer(cout, dd, hi.data_ptr(), lo.data_ptr(),
+                                  u_hi.data_ptr(), u_lo.data_ptr())
+                else:
+                    r, scale, ut_hi, ut_lo, un_hi, un_lo = low
+                    L = ProjLayer(cout, dd, None, None, u_hi.data_ptr(), u_lo.data_ptr(),
+                                  r, scale, ut_hi.data_ptr(), ut_lo.data_ptr(),
+                                  un_hi.data_ptr(), un_lo.data_ptr())
+                    t_need.append((len(layers), cout * ((r + 3) // 4 * 4)))
+                t.layer = len(layers)
+                layers.append(L)
+                protos.append((n, P, P._version))
+        # one arena [T | T_hi | T_lo] per group for its low-rank layers
+        t_elems = sum(e for _, e in t_need)
+        t_arena = None
+        if t_elems:
+            old = self._plans.get(gi)
+            t_arena = old["t_arena"] if old is not None and old["t_arena"] is not None and \
+                old["t_arena"].numel() == 3 * t_elems and old["t_arena"].device == device else \
+                torch.empty(3 * t_elems, dtype=torch.float32, device=device)
+            base, off = t_arena.data_ptr(), 0
+            for li, e in t_need:
+                layers[li].t = base + 4 * off
+                layers[li].t_hi = base + 4 * (t_elems + off)
+                layers[li].t_lo = base + 4 * (2 * t_elems + off)
+                off += e
+        n_l = len(layers)
+        layer_arr = (ProjLayer * max(n_l, 1))(*layers)
+        cache = dict(tensors=tensors, layer_arr=layer_arr, n_t=n_t, n_l=n_l, t_arena=t_arena,
+                     t_elems=t_elems, protos=protos, w_ptrs=[p.data_ptr() for p in params],
+                     g_ptrs=[0] * n_t, buf_ptrs=[0] * n_t, first=[-1] * n_t, plan=None,
+                     buf=None, names=list(names), n_transforms=len(self.transforms),
+                     uploaded=False)
+        if _lib.engine() == 0:
+            # ctypes fields read 0 until the first step fills g / buf; the plan only encodes the
+            # weights, projectors and staging buffers
+            need = int(lib.nsgp_sgd_plan_bytes(tensors, n_t, layer_arr, n_l))
+            old = self._plans.get(gi)
+            buf = old["buf"] if old is not None and old["buf"] is not None and \
+                old["buf"].numel() >= need and old["buf"].device == device else \
+                torch.empty(need, dtype=torch.uint8, device=device)
+            plan = SgdPlan()
+            check(lib.nsgp_sgd_plan_build(tensors, n_t, layer_arr, n_l, ptr(t_arena), t_elems,
+                                          ptr(buf), buf.numel(), ctypes.byref(plan),
+                                          _lib.current_stream(device)), "nsgp_sgd_plan_build")
+            cache["plan"], cache["buf"] = plan, buf
+        self._plans[gi] = cache
+        return cache
+
+    def _group_cache_valid(self, cache, group) -> bool:
+        if cache is None or cache["names"] != group["names"] or \
+                cache["n_transforms"] != len(self.transforms):
+            return False
+        for p, w in zip(group["params"], cache["w_ptrs"]):
+            if p.data_ptr() != w:
+                return False
+        for n, P, ver in cache["protos"]:
+            cur = self.transforms.get(n) if n in self.transforms.keys() else None
+            if cur is not P or P._version != ver:
+                return False
+        return True
+
     @torch.no_grad()
     def step(self, closure=None):
         """One optimisation step (:59-96)."""
@@ -193,17 +291,15 @@ class SGDNSCL(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
-            svd = group["svd"]
+        for gi, group in enumerate(self.param_groups):
             names, params = group["names"], group["params"]
             if len(params) == 0:
                 continue
-            n_t = len(params)
-            tensors = (SgdTensor * n_t)()
-            layers = []
-            t_need = []             # (layer index, T elements) of the low-rank layers
             device = params[0].device
-            for i, (n, p) in enumerate(zip(names, params)):
+            svd = group["svd"]
+            # ---- validate everything before any state is touched
+            grads = []
+            for n, p in zip(names, params):
                 grad = p.grad.data          # AttributeError when grad is None, like :75
                 if grad.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients, please "
@@ -212,58 +308,41 @@ class SGDNSCL(Optimizer):
                 if p.dtype != torch.float32 or grad.dtype != torch.float32 or \
                         not p.is_contiguous() or not grad.is_contiguous():
                     raise _lib.NsgpError("parameter %s: fp32 contiguous tensors required" % n)
-                state = self.state[p]
-                if len(state) == 0:
-                    state["step"] = 0
-                    state["previous_grad"] = torch.zeros_like(p.data)
-                state["step"] += 1
-                t = tensors[i]
-                t.w, t.g, t.buf = p.data_ptr(), grad.data_ptr(), state["previous_grad"].data_ptr()
-                t.numel = p.numel()
-                t.first_step = 1 if state["step"] == 1 else 0
-                t.layer = -1
                 if svd and len(self.transforms) > 0 and n in self.transforms.keys():
-                    P = self.transforms[n]
                     if p.dim() not in (2, 4):
                         raise _lib.NsgpError("parameter %s: projection needs a 2-D or 4-D "
                                              "tensor" % n)
+                    P = self.transforms[n]
                     cout = p.shape[0]
                     dd = p.numel() // cout
                     if P.shape[0] != dd:
                         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied "
                                            "(%dx%d and %dx%d)" % (cout, dd, P.shape[0], P.shape[1]))
-                    u_hi, u_lo = self._staging(n, p)
-                    low = self._prepare_lowrank(n, P)
-                    if low is None:
-                        hi, lo = self._prepare(n, P)
-                        L = ProjLayer(cout, dd, hi.data_ptr(), lo.data_ptr(),
-                                      u_hi.data_ptr(), u_lo.data_ptr())
-                    else:
-                        r, scale, ut_hi, ut_lo, un_hi, un_lo = low
-                        L = ProjLayer(cout, dd, None, None, u_hi.data_ptr(), u_lo.data_ptr(),
-                                      r, scale, ut_hi.data_ptr(), ut_lo.data_ptr(),
-                                      un_hi.data_ptr(), un_lo.data_ptr())
-                        t_need.append((len(layers), cout * ((r + 3) // 4 * 4)))
-                    t.layer = len(layers)
-                    layers.append(L)
-            n_l = len(layers)
-            # one arena [T | T_hi | T_lo] for the low-rank layers
-            t_elems = sum(e for _, e in t_need)
-            if t_elems:
-                if self._t_arena is None or self._t_arena.numel() != 3 * t_elems or \
-                        self._t_arena.device != device:
-                    self._t_arena = torch.empty(3 * t_elems, dtype=torch.float32, device=device)
-                base, off = self._t_arena.data_ptr(), 0
-                for li, e in t_need:
-                    layers[li].t = base + 4 * off
-                    layers[li].t_hi = base + 4 * (t_elems + off)
-                    layers[li].t_lo = base + 4 * (2 * t_elems + off)
-                    off += e
-            layer_arr = (ProjLayer * max(n_l, 1))(*layers)
+                grads.append(grad)
+            cache = self._plans.get(gi)
+            if not self._group_cache_valid(cache, group):
+                cache = self._build_group_cache(gi, group, device)
+            tensors = cache["tensors"]
+            changed = not cache["uploaded"]
+            g_ptrs, buf_ptrs, first = cache["g_ptrs"], cache["buf_ptrs"], cache["first"]
+            for i, (p, grad) in enumerate(zip(params, grads)):
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = 0
+                    state["previous_grad"] = torch.zeros_like(p.data)
+                state["step"] += 1
+                f = 1 if state["step"] == 1 else 0
+                gp, bp = grad.data_ptr(), state["previous_grad"].data_ptr()
+                if gp != g_ptrs[i] or bp != buf_ptrs[i] or f != first[i]:
+                    t = tensors[i]
+                    t.g, t.buf, t.first_step = gp, bp, f
+                    g_ptrs[i], buf_ptrs[i], first[i] = gp, bp, f
+                    changed = True
             stream = _lib.current_stream(device)
             hyper = (float(group["lr"]), float(group["momentum"]), float(group["dampening"]),
                      float(group["weight_decay"]), 1 if group["nesterov"] else 0)
-            if lib.nsgp_get_engine() != 0:
+            n_t, n_l, layer_arr = cache["n_t"], cache["n_l"], cache["layer_arr"]
+            if cache["plan"] is None:
                 # bring-up engine: one-shot call, per-layer launches
                 need = lib.nsgp_sgd_step_workspace_bytes(n_t, n_l)
                 if self._workspace is None or self._workspace.numel() < need or \
@@ -273,25 +352,10 @@ class SGDNSCL(Optimizer):
                                              ptr(self._workspace), self._workspace.numel(),
                                              stream), "nsgp_sgd_nscl_step")
                 continue
-            # prepared plan: rebuilt only when a weight / projector pointer or a shape changes
-            sig = (tuple((t.w, t.numel, t.layer) for t in tensors),
-                   tuple((L.cout, L.d, L.pt_hi, L.pt_lo, L.u_hi, L.u_lo, L.r, L.scale, L.ut_hi,
-                          L.un_hi, L.t) for L in layers))
-            gi = id(group)
-            hit = self._plans.get(gi)
-            if hit is None or hit[0] != sig:
-                need = int(lib.nsgp_sgd_plan_bytes(tensors, n_t, layer_arr, n_l))
-                buf = hit[1] if hit is not None and hit[1].numel() >= need and \
-                    hit[1].device == device else \
-                    torch.empty(need, dtype=torch.uint8, device=device)
-                plan = SgdPlan()
-                check(lib.nsgp_sgd_plan_build(tensors, n_t, layer_arr, n_l,
-                                              ptr(self._t_arena) if t_elems else None, t_elems,
-                                              ptr(buf), buf.numel(), ctypes.byref(plan), stream),
-                      "nsgp_sgd_plan_build")
-                hit = (sig, buf, plan)
-                self._plans[gi] = hit
-            check(lib.nsgp_sgd_plan_step(tensors, n_t, layer_arr, n_l, ptr(hit[1]),
-                                         ctypes.byref(hit[2]), *hyper, stream),
-                  "nsgp_sgd_plan_step")
+            # the tensor table travels only when a gradient / momentum pointer or a first-step
+            # flag changed since the last upload
+            check(lib.nsgp_sgd_plan_step(tensors if changed else None, n_t, layer_arr, n_l,
+                                         ptr(cache["buf"]), ctypes.byref(cache["plan"]), *hyper,
+                                         stream), "nsgp_sgd_plan_step")
+            cache["uploaded"] = True
         return loss

@@ -91,109 +91,7 @@ class MultiPrototypeReplay:
                 raise IndexError("class %d has no stored RoI feature "
                                  "(index 0 is out of bounds for dimension 0 with size 0)" % c)
             sizes.append(n)
-        if lib.nsgp_get_engine() == 0:
-            return self._build_device(feats, rows, h_off, previous_cls, sizes, save_idx, stream)
-
-        # neighbour masks / counts of every class, launched back to back into ONE
-        # device buffer [masks | counts | rows] that comes back in a single D2H copy
-        mask_bytes = sum(n * n for n in sizes)
-        mask_pad = (mask_bytes + 15) // 16 * 16
-        cnt_elems = sum(sizes)
-        pack = torch.empty(mask_pad + 4 * cnt_elems + 4 * max(M, 1), dtype=torch.uint8,
-                           device=dev)
-        cnt_all = pack[mask_pad:mask_pad + 4 * cnt_elems].view(torch.int32)
-        pack[mask_pad + 4 * cnt_elems:].view(torch.int32).copy_(rows)
-        if lib.nsgp_get_engine() == 0:
-            # all classes at once: normalise, clear, ONE grouped tcgen05 Gram, threshold
-            import ctypes
-            ncls = len(sizes)
-            sizes_arr = (ctypes.c_int32 * ncls)(*sizes)
-            need = int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D))
-            ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
-                self._ws.device == dev else torch.empty(need, dtype=torch.uint8, device=dev)
-            self._ws = ws
-            consecutive = all(b == a + 1 for a, b in zip(previous_cls, previous_cls[1:]))
-            if consecutive:
-                rows_sel = rows[h_off[previous_cls[0]]:h_off[previous_cls[-1] + 1]]
-            else:
-                rows_sel = torch.cat([rows[h_off[c]:h_off[c + 1]] for c in previous_cls])
-            check(lib.repre_cosine_count_batched(
-                ptr(feats), D, ptr(rows_sel), sizes_arr, ncls, float(self.thresh),
-                pack.data_ptr(), cnt_all.data_ptr(), ptr(ws), ws.numel(), stream),
-                "repre_cosine_count_batched")
-        else:
-            need = max(lib.repre_cosine_count_workspace_bytes(n, D) for n in sizes)
-            ws = self._ws if self._ws is not None and self._ws.numel() >= need and \
-                self._ws.device == dev else torch.empty(int(need), dtype=torch.uint8, device=dev)
-            self._ws = ws
-            m_off = c_off = 0
-            for c, n in zip(previous_cls, sizes):
-                check(lib.repre_cosine_count(
-                    ptr(feats), D, rows.data_ptr() + 4 * h_off[c], n, float(self.thresh),
-                    pack.data_ptr() + m_off, cnt_all.data_ptr() + 4 * c_off, None, ptr(ws),
-                    ws.numel(), stream), "repre_cosine_count")
-                m_off += n * n
-                c_off += n
-        host = pack.cpu().numpy()                                   # the one sync
-        h_cnt = host[mask_pad:mask_pad + 4 * cnt_elems].view(np.int32)
-        h_rows_np = host[mask_pad + 4 * cnt_elems:].view(np.int32)
-
-        # host: density order + greedy cover (sequential, <= max_proto-1 picks)
-        seg_rows, seg_off, seg_label = [], [0], []
-        m_off = c_off = 0
-        for c, n in zip(previous_cls, sizes):
-            sim_mask = host[m_off:m_off + n * n].reshape(n, n).astype(bool)
-            cnt_np = h_cnt[c_off:c_off + n]
-            m_off += n * n
-            c_off += n
-            cls_rows = h_rows_np[h_off[c]:h_off[c + 1]]
-            # coarse prototype: all rows of the class (:412-414)
-            seg_rows.append(cls_rows)
-            seg_off.append(seg_off[-1] + n)
-            seg_label.append(c)
-            # stable, like the reference's sort under its pinned torch 1.12 (equal counts keep
-            # ascending row order; the device path ranks the same way)
-            sim_sum, idx = torch.from_numpy(cnt_np.astype(np.int64)).sort(
-                dim=-1, descending=True, stable=True)                    # :421
-            thr = int(sim_sum[-n // 3])                                  # :422
-            covered = cnt_np <= thr                                      # :423
-            idx_np = idx.numpy()
-            tmp_mask = save_idx[c] if c < len(save_idx) else []          # :425-428
-            for proto_count in range(self.max_proto - 1):                # :430
-                if proto_count < len(tmp_mask):                          # replayed mask.pth entry
-                    m = tmp_mask[proto_count].cpu().numpy().astype(bool)
-                else:
-                    cand = idx_np[~covered[idx_np]]
-                    if cand.size == 0:
-                        continue
-                    m = sim_mask[cand[0]]
-                    tmp_mask.append(torch.from_numpy(m.copy()))
-                covered = covered | m
-                sel = cls_rows[m]
-                seg_rows.append(sel)
-                seg_off.append(seg_off[-1] + sel.size)
-                seg_label.append(c)
-            if c >= len(save_idx):
-                save_idx.append(tmp_mask)
-
-        # one launch: coarse + fine means of every class
-        nseg = len(seg_label)
-        idx_host = np.concatenate([np.asarray(seg_off, dtype=np.int32),
-                                   np.asarray(seg_label, dtype=np.int32)] +
-                                  [r.astype(np.int32, copy=False) for r in seg_rows])
-        idx_dev = torch.from_numpy(idx_host).to(dev)                 # one H2D copy
-        off_t = idx_dev[:nseg + 1]
-        all_rows = idx_dev[2 * nseg + 1:]
-        out = torch.empty(nseg, D, dtype=torch.float32, device=dev)
-        max_rows = max(b - a for a, b in zip(seg_off[:-1], seg_off[1:]))
-        check(lib.repre_segment_mean(ptr(feats), D, ptr(off_t), ptr(all_rows), nseg,
-                                     int(max_rows), ptr(out), stream), "repre_segment_mean")
-        self.bbox_featss = out
-        self.tmp_label = idx_dev[nseg + 1:2 * nseg + 1].to(torch.int64)
-        self.save_idx = save_idx
-        self._segments = (off_t, all_rows, max_rows)
-        self._feats = feats
-        return self
+        return self._build_device(feats, rows, h_off, previous_cls, sizes, save_idx, stream)
 
     def _build_device(self, feats, rows, h_off, previous_cls, sizes, saved_masks, stream):
         """tcgen05 engine: Gram, ordering, cover, segment table and means without leaving
@@ -333,6 +231,91 @@ class MultiPrototypeReplay:
         return out
 
 
+def exchange_by_class_owner(feats, labels, classes, group=None):
+    """The one exchange step of a data-parallel prototype build: class ``c``
+    is owned by rank ``classes.index(c) % W``; every rank sends the rows of each class to its
+    owner.  Returns ``(feats_owned, labels_owned, owned_classes)``; rows arrive in (source
+    rank, original row) order, i.e. the order they have in the reference's gathered
+    ``rois_etc.pth`` (``cat(all_gather_different_shape(...))``, nsrunner_roi_replay.py:815-820),
+    so neighbour masks and tie orders equal the single-process build."""
+    import torch.distributed as dist
+    classes = list(classes)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return feats, labels, classes
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    owner_of = torch.full((max(classes) + 2,), -1, dtype=torch.int64, device=labels.device)
+    for k, c in enumerate(classes):
+        owner_of[c] = k % world
+    lab = labels.to(torch.int64)
+    own = torch.where((lab >= 0) & (lab <= max(classes)), owner_of[lab.clamp(0, max(classes))],
+                      torch.full_like(lab, -1))
+    order = torch.argsort(own, stable=True)               # by destination, original order kept
+    order = order[own[order] >= 0]
+    send_counts = torch.bincount(own[order], minlength=world)[:world]
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group) \
+        if dist.get_backend(group) == "nccl" else _gloo_counts(recv_counts, send_counts, group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    send_f = feats.reshape(feats.shape[0], -1)[order].contiguous()
+    send_l = lab[order].contiguous()
+    recv_f = send_f.new_empty((sum(rc), send_f.shape[1]))
+    recv_l = send_l.new_empty((sum(rc),))
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv_f, send_f, rc, sc, group=group)
+        dist.all_to_all_single(recv_l, send_l, rc, sc, group=group)
+    else:                                                  # gloo (CPU tests): var-len gathers
+        from .rois import all_gather_different_shape
+        offs = [0]
+        for n in sc:
+            offs.append(offs[-1] + n)
+        f_parts, l_parts = [], []
+        for dst in range(world):
+            fp = all_gather_different_shape(send_f[offs[dst]:offs[dst + 1]], group)
+            lp = all_gather_different_shape(send_l[offs[dst]:offs[dst + 1]], group)
+            if dst == rank:
+                f_parts, l_parts = fp, lp
+        recv_f, recv_l = torch.cat(f_parts), torch.cat(l_parts)
+    owned = [c for k, c in enumerate(classes) if k % world == rank]
+    return recv_f, recv_l, owned
+
+
+def _gloo_counts(recv_counts, send_counts, group):
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    table = [torch.empty_like(send_counts) for _ in range(world)]
+    dist.all_gather(table, send_counts, group=group)
+    for src in range(world):
+        recv_counts[src] = table[src][rank]
+
+
+def gather_prototypes(protos, tmp_label, group=None):
+    """All ranks' prototypes in the reference order (classes ascending, coarse prototype
+    first, then the fine ones in pick order): var-len all-gather + stable sort by class."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return protos, tmp_label
+    from .rois import all_gather_different_shape
+    p_all = torch.cat(all_gather_different_shape(protos, group))
+    l_all = torch.cat(all_gather_different_shape(tmp_label, group))
+    order = torch.argsort(l_all, stable=True)
+    return p_all[order].contiguous(), l_all[order].contiguous()
+
+
+@torch.no_grad()
+def build_prototypes_sharded(feats, cls_targets, previous_cls, max_prototype=10, group=None):
+    """Data-parallel form of the prototype build: every rank passes the RoI features it
+    harvested; classes are sharded over the ranks (one all-to-all of the foreground rows),
+    each owner runs the device build for its classes, the (<= 20 MB of) prototypes are
+    all-gathered.  Returns a ``MultiPrototypeReplay`` holding all prototypes on every rank."""
+    f_own, l_own, owned = exchange_by_class_owner(feats, cls_targets, previous_cls, group)
+    mp = MultiPrototypeReplay(max_prototype).build(f_own, l_own, owned)
+    protos, labels = gather_prototypes(mp.bbox_featss, mp.tmp_label, group)
+    out = MultiPrototypeReplay(max_prototype)
+    out.bbox_featss, out.tmp_label = protos, labels
+    out.local = mp                     # this rank's classes: masks / segments for mask.pth
+    return out
+
+
 @torch.no_grad()
 def kmeans_prototypes(feats: torch.Tensor, init_centres: torch.Tensor, iters: int = 10):
     """Extension (BASELINE north_star item 3; the reference imports sklearn's KMeans at
@@ -370,26 +353,106 @@ def kmeans_prototypes(feats: torch.Tensor, init_centres: torch.Tensor, iters: in
     return centres, labels
 
 
-class StandardMultiPrototypeReplayHead(nn.Module):
-    """Constructor keywords and attributes of the reference head (:377-390):
-    ``previous_path, task_id, task_split, max_prototype, work_dir``; attributes
-    ``replay``, ``bbox_featss``, ``tmp_label``; ``loss`` adds ``replay_loss_cls``.
+class SampledRoIReplay:
+    """Device-resident store of ``rois_etc.pth`` and the sampled gather of
+    ``StandardRoIReplayHead.loss`` (standard_roi_replay_head.py:53-69): the reference keeps
+    the six tensors wherever ``torch.load`` put them, indexes all six with
+    ``randperm(M)[:64]`` and moves the 64 rows to the model's device every step (3.2 MB
+    pageable H2D).  Here the six tensors live on the device, the 64 indices (512 B) are the
+    only H2D traffic and ONE launch gathers all six (``repre_replay_gather_rois``).  The
+    indices are drawn exactly like the reference (``torch.randperm`` on the default CPU
+    generator), so a seeded run replays the same RoIs."""
 
-    Stand-alone form: ``bbox_head`` is any module mapping (P,12544)-features to
-    ``(cls_score, bbox_pred)``.  When mmdet is importable ``registry.py`` builds
-    the real subclass of ``StandardRoIHead`` from the same mixin logic.
-    """
+    FIELDS = ("bbox_featss", "cls_targets", "cls_weights", "bbox_targets", "bbox_weights",
+              "roiss")
 
-    def __init__(self, bbox_head: nn.Module = None, previous_path=None, task_id=1,
-                 task_split=(0, 10, 20), max_prototype=10, work_dir=None, device=None,
-                 **kwargs):
-        super().__init__()
-        self.bbox_head = bbox_head
+    def __init__(self, tensors, device=None, sample_size=64):
+        if len(tensors) != 6:
+            raise ValueError("rois_etc.pth holds a list of 6 tensors")
+        dev = torch.device(device) if device is not None else torch.device("cuda")
+        f, ct, cw, bt, bw, r = tensors
+        M = f.shape[0]
+        self.bbox_featss = f.detach().reshape(M, -1).to(dev, torch.float32).contiguous()
+        self.cls_targets = ct.detach().reshape(M).to(dev, torch.int64).contiguous()
+        self.cls_weights = cw.detach().reshape(M).to(dev, torch.float32).contiguous()
+        self.bbox_targets = bt.detach().reshape(M, 4).to(dev, torch.float32).contiguous()
+        self.bbox_weights = bw.detach().reshape(M, 4).to(dev, torch.float32).contiguous()
+        self.roiss = r.detach().reshape(M, 5).to(dev, torch.float32).contiguous()
+        _lib.require_cuda(self.bbox_featss, "rois_etc.pth tensors")
+        self.sample_size = sample_size
+        self._out = None
+
+    @classmethod
+    def load(cls, previous_path, device=None, **kw):
+        return cls(torch.load(osp.join(previous_path, "rois_etc.pth"), map_location="cpu"),
+                   device=device, **kw)
+
+    @torch.no_grad()
+    def sample(self, idx=None):
+        """(bbox_featss, cls_targets, cls_weights, bbox_targets, bbox_weights, roiss) at
+        ``idx`` (default ``torch.randperm(M)[:64]``, :58)."""
+        M, D = self.bbox_featss.shape
+        if idx is None:
+            idx = torch.randperm(M)[:self.sample_size]
+        dev = self.bbox_featss.device
+        idx = idx.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        P = idx.shape[0]
+        if self._out is None or self._out[0].shape[0] != P:
+            self._out = (torch.empty(P, D, dtype=torch.float32, device=dev),
+                         torch.empty(P, dtype=torch.int64, device=dev),
+                         torch.empty(P, dtype=torch.float32, device=dev),
+                         torch.empty(P, 4, dtype=torch.float32, device=dev),
+                         torch.empty(P, 4, dtype=torch.float32, device=dev),
+                         torch.empty(P, 5, dtype=torch.float32, device=dev))
+        o = self._out
+        check(lib.repre_replay_gather_rois(
+            ptr(self.bbox_featss), ptr(self.cls_targets), ptr(self.cls_weights),
+            ptr(self.bbox_targets), ptr(self.bbox_weights), ptr(self.roiss), ptr(idx), P, D,
+            ptr(o[0]), ptr(o[1]), ptr(o[2]), ptr(o[3]), ptr(o[4]), ptr(o[5]),
+            _lib.current_stream(dev)), "repre_replay_gather_rois")
+        return o
+
+
+class ReplayHeadMixin:
+    """The replay logic of both reference heads, written once and bound onto whatever
+    ``StandardRoIHead`` is available (mmdet's when importable - ``registry.py`` - or the
+    stand-alone ``nn.Module`` below).  The host class provides ``bbox_head``,
+    ``with_shared_head`` / ``shared_head`` and, for the sampled head, ``teacher_model``."""
+
+    # ---- StandardRoIReplayHead (:32-50): sampled replay against the teacher -------------
+    def init_sampled_replay(self, previous_path, device=None):
+        self.replay = False
+        self.counter = [0] * 80                                       # :44
+        if previous_path is not None and osp.exists(previous_path):
+            self.replay = True
+            self._sampled = SampledRoIReplay.load(previous_path, device=device)
+            (self.bbox_featss, self.cls_targets, self.cls_weights, self.bbox_targets,
+             self.bbox_weights, self.roiss) = (getattr(self._sampled, f)
+                                               for f in SampledRoIReplay.FIELDS)
+
+    def sampled_replay_losses(self) -> dict:
+        """:55-69 - draw 64 stored RoIs, student vs teacher class scores (MSE)."""
+        feats, cls_t, cls_w, bbox_t, bbox_w, rois = self._sampled.sample()
+        res = self.teacher_replay_loss(feats, [cls_t, cls_w, bbox_t, bbox_w], rois)
+        return res["replay_loss"]
+
+    def teacher_replay_loss(self, bbox_feats, sampling_results=None, rois=None) -> dict:
+        """:71-104."""
+        if getattr(self, "with_shared_head", False):
+            bbox_feats = self.shared_head(bbox_feats)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+        teacher_cls_score, _ = self.teacher_model.bbox_head(bbox_feats)
+        losses = {"replay_loss_cls": F.mse_loss(cls_score, teacher_cls_score)}
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats,
+                    replay_loss=losses)
+
+    # ---- StandardMultiPrototypeReplayHead (:377-501): prototype replay -------------------
+    def init_prototype_replay(self, previous_path, task_id, task_split, max_prototype,
+                              device=None):
         self.replay = False
         self.task_split = list(task_split)
         self.task_id = task_id
         self.max_proto = max_prototype
-        self.with_shared_head = False
         self._proto = MultiPrototypeReplay(max_prototype)
         if previous_path is not None and osp.exists(previous_path):
             assert task_id != 1
@@ -405,12 +468,16 @@ class StandardMultiPrototypeReplayHead(nn.Module):
             self._proto.build(bbox_featss, self.cls_targets, previous_cls, saved)
             self.bbox_featss = self._proto.bbox_featss
             self.tmp_label = self._proto.tmp_label
-            out_dir = work_dir if work_dir is not None else get_work_dir(previous_path)
-            torch.save(self._proto.save_idx, osp.join(out_dir, "mask.pth"))
+            # like the reference (:451-452) the masks go next to the NEXT task's outputs,
+            # whatever ``work_dir`` was passed
+            torch.save(self._proto.save_idx,
+                       osp.join(get_work_dir(previous_path), "mask.pth"))
 
     def replay_loss(self, bbox_feats, sampling_results=None, rois=None) -> dict:
         """:468-501 - logits of classes < task_split[task_id] plus background;
         cross-entropy on the softmax output (double softmax kept on purpose)."""
+        if getattr(self, "with_shared_head", False):                  # :488-489
+            bbox_feats = self.shared_head(bbox_feats)
         cls_score, bbox_pred = self.bbox_head(bbox_feats)
         pre_idx = self.task_split[self.task_id]
         kept = torch.cat([cls_score[:, :pre_idx], cls_score[:, -1:]], dim=-1)
@@ -419,10 +486,52 @@ class StandardMultiPrototypeReplayHead(nn.Module):
         return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats,
                     replay_loss=losses)
 
+    def prototype_replay_losses(self) -> dict:
+        """:458-466 - every prototype, every step, gathered on the device."""
+        return self.replay_loss(self._proto.staged())["replay_loss"]
+
+
+class StandardRoIReplayHead(ReplayHeadMixin, nn.Module):
+    """Stand-alone form of the sampled-replay head (:32-69): ``bbox_head`` maps
+    (P,12544)-features to ``(cls_score, bbox_pred)``; ``teacher_model`` is attached by the
+    runner (nsrunner_roi_replay.py:533)."""
+
+    def __init__(self, bbox_head: nn.Module = None, previous_path=None, device=None, **kwargs):
+        super().__init__()
+        self.bbox_head = bbox_head
+        self.with_shared_head = False
+        self.init_sampled_replay(previous_path, device)
+
+    def loss(self, x=None, rpn_results_list=None, batch_data_samples=None, replay=True,
+             base_losses=None):
+        losses = dict(base_losses or {})
+        if self.replay and replay:
+            losses.update(self.sampled_replay_losses())
+        return losses
+
+
+class StandardMultiPrototypeReplayHead(ReplayHeadMixin, nn.Module):
+    """Constructor keywords and attributes of the reference head (:377-390):
+    ``previous_path, task_id, task_split, max_prototype, work_dir``; attributes
+    ``replay``, ``bbox_featss``, ``tmp_label``; ``loss`` adds ``replay_loss_cls``.
+
+    Stand-alone form: ``bbox_head`` is any module mapping (P,12544)-features to
+    ``(cls_score, bbox_pred)``.  When mmdet is importable ``registry.py`` binds the same
+    mixin onto the reference's ``StandardRoIReplayHead``.
+    """
+
+    def __init__(self, bbox_head: nn.Module = None, previous_path=None, task_id=1,
+                 task_split=(0, 10, 20), max_prototype=10, work_dir=None, device=None,
+                 **kwargs):
+        super().__init__()
+        self.bbox_head = bbox_head
+        self.with_shared_head = False
+        self.counter = [0] * 80
+        self.init_prototype_replay(previous_path, task_id, task_split, max_prototype, device)
+
     def loss(self, x=None, rpn_results_list=None, batch_data_samples=None, base_losses=None):
-        """:454-466.  ``base_losses`` stands for ``super().loss(...)``."""
+        """:454-466.  ``base_losses`` stands for ``super().loss(..., replay=False)``."""
         losses = dict(base_losses or {})
         if self.replay:
-            staged = self._proto.staged()
-            losses.update(self.replay_loss(staged)["replay_loss"])
+            losses.update(self.prototype_replay_losses())
         return losses

@@ -1,15 +1,26 @@
-"""Registers the drop-in classes into the mmengine / mmdet registries when those
-packages are importable (they are not vendored by the reference:
-requirements/mminstall.txt:1-2).  Names equal the reference's registry entries
-(mmdet/registry.py:35,62,75) so ``cl_faster_rcnn_cfgs`` configs resolve unchanged:
-``optimizer=dict(type='SGDNSCL', ...)`` (_base_/schedules/schedule_1x_sgdnscl.py:21)
-and ``roi_head=dict(type='StandardMultiPrototypeReplayHead', ...)``
-(incremental_task/cl_faster_rcnn_nsgp_repre_19_1_2.py).  Without mmengine the
-local ``REGISTRY`` dict is the lookup table."""
+"""Registers the drop-in classes into the mmengine / mmdet registries (the reference's
+plug-in surface, mmdet/registry.py:35,62,75), under the reference's own names, so that
+``cl_faster_rcnn_cfgs`` configs resolve unchanged:
+
+* ``optimizer=dict(type='SGDNSCL', ...)``       _base_/schedules/schedule_1x_sgdnscl.py:21
+* ``runner_type = "BRNullSpaceRunner"``         _base_/brnsrunetime.py:26
+* ``roi_head=dict(type='StandardMultiPrototypeReplayHead', ...)``
+                                                incremental_task/cl_faster_rcnn_nsgp_repre_19_1_2.py:65
+* ``StandardRoIReplayHead``                     mmdet/models/roi_heads/standard_roi_replay_head.py:31
+
+Importing the package fills the local ``REGISTRY`` table only.  Replacing the entries of
+the mm registries is an explicit step: ``register_all(force=True)``, or - from a config,
+without touching the fork - ``custom_imports = dict(imports=['nsgp_repre_b200.mm'])``.
+A registration that fails is logged and re-raised with ``strict=True``; it is never
+swallowed."""
 from __future__ import annotations
+
+import logging
 
 REGISTRY = {}
 MMENGINE_AVAILABLE = False
+MM_REGISTERED = {}          # registry name -> [entry names] actually replaced
+_log = logging.getLogger("nsgp_repre_b200.registry")
 
 
 def _register_local(name, obj):
@@ -17,70 +28,113 @@ def _register_local(name, obj):
     return obj
 
 
-def register_all(force=True):
-    """Idempotent; returns the dict of registered names."""
-    global MMENGINE_AVAILABLE
+def register_local():
     from .optim import SGDNSCL
-    from .prototypes import StandardMultiPrototypeReplayHead
+    from .prototypes import StandardMultiPrototypeReplayHead, StandardRoIReplayHead
     from .covariance import CovarianceHooks
-    _register_local("SGDNSCL", SGDNSCL)
-    _register_local("StandardMultiPrototypeReplayHead", StandardMultiPrototypeReplayHead)
-    _register_local("BRNullSpaceCovariance", CovarianceHooks)
+    from .runner import NullSpaceRunnerMixin
     from .roi_extract import SingleRoIExtractor
     from .ewc import EWCHook
+    _register_local("SGDNSCL", SGDNSCL)
+    _register_local("StandardMultiPrototypeReplayHead", StandardMultiPrototypeReplayHead)
+    _register_local("StandardRoIReplayHead", StandardRoIReplayHead)
+    _register_local("BRNullSpaceCovariance", CovarianceHooks)
+    _register_local("BRNullSpaceRunner", NullSpaceRunnerMixin)
     # local names only: mmdet's own 'SingleRoIExtractor' is replaced explicitly by the
     # integrator (INTEGRATION.md), not behind the user's back
     _register_local("SingleRoIExtractor", SingleRoIExtractor)
     _register_local("EWCHook", EWCHook)
-    try:
+    return dict(REGISTRY)
+
+
+def _mm_heads(ref_sampled_head):
+    """The two replay heads bound onto the reference's ``StandardRoIReplayHead`` (so that
+    ``get_bbox_stuff`` / ``counter`` of ``mode='roi_replay'`` and the whole StandardRoIHead
+    machinery stay the fork's own code); only the replay paths change."""
+    from .prototypes import ReplayHeadMixin
+
+    class StandardRoIReplayHead(ReplayHeadMixin, ref_sampled_head):
+        def __init__(self, *args, previous_path=None, **kwargs):
+            # the fork's constructor would torch.load the six tensors onto the CPU and index
+            # them there every step; it is given no path and the device store is built here
+            super().__init__(*args, **kwargs)
+            dev = next((p.device for p in self.parameters()), None)
+            self.init_sampled_replay(previous_path, dev)
+
+        replay_loss = ReplayHeadMixin.teacher_replay_loss
+
+        def loss(self, x, rpn_results_list, batch_data_samples, replay=True):
+            # the grandparent's plain RoI-head loss; the fork's own replay branch is replaced
+            losses = super().loss(x, rpn_results_list, batch_data_samples, replay=False)
+            if self.replay and replay:
+                losses.update(self.sampled_replay_losses())
+            return losses
+
+    class StandardMultiPrototypeReplayHead(ReplayHeadMixin, ref_sampled_head):
+        def __init__(self, *args, previous_path=None, task_id=1, task_split=(0, 10, 20),
+                     max_prototype=10, work_dir=None, **kwargs):
+            super().__init__(*args, **kwargs)
+            dev = next((p.device for p in self.parameters()), None)
+            self.init_prototype_replay(previous_path, task_id, task_split, max_prototype, dev)
+
+        def loss(self, x, rpn_results_list, batch_data_samples):
+            losses = super().loss(x, rpn_results_list, batch_data_samples, replay=False)
+            if self.replay:
+                losses.update(self.prototype_replay_losses())
+            return losses
+
+    return StandardRoIReplayHead, StandardMultiPrototypeReplayHead
+
+
+def register_all(force=True, strict=False):
+    """Local table + (when importable) the mm registries.  Returns the local table."""
+    global MMENGINE_AVAILABLE
+    register_local()
+    MM_REGISTERED.clear()
+
+    def attempt(what, fn):
+        try:
+            fn()
+            return True
+        except ImportError as e:
+            _log.info("nsgp_repre_b200: %s not registered (%s)", what, e)
+        except Exception:
+            _log.exception("nsgp_repre_b200: registering %s failed", what)
+            if strict:
+                raise
+        return False
+
+    def reg_optimizer():
         from mmengine.registry import OPTIMIZERS
-        OPTIMIZERS.register_module(name="SGDNSCL", module=SGDNSCL, force=force)
-        MMENGINE_AVAILABLE = True
-    except Exception:        # mmengine absent: local registry only
-        MMENGINE_AVAILABLE = False
-    try:
+        OPTIMIZERS.register_module(name="SGDNSCL", module=REGISTRY["SGDNSCL"], force=force)
+        MM_REGISTERED.setdefault("OPTIMIZERS", []).append("SGDNSCL")
+
+    def reg_heads():
         from mmdet.registry import MODELS
-        from mmdet.models.roi_heads import StandardRoIHead
-        from .prototypes import MultiPrototypeReplay, get_work_dir
-        import os.path as osp
-        import torch
+        from mmdet.models.roi_heads.standard_roi_replay_head import \
+            StandardRoIReplayHead as ref_head
+        sampled, multi = _mm_heads(ref_head)
+        MODELS.register_module(name="StandardRoIReplayHead", module=sampled, force=force)
+        MODELS.register_module(name="StandardMultiPrototypeReplayHead", module=multi,
+                               force=force)
+        MM_REGISTERED.setdefault("MODELS", []).extend(
+            ["StandardRoIReplayHead", "StandardMultiPrototypeReplayHead"])
 
-        class _MMDetMultiPrototypeReplayHead(StandardRoIHead):
-            """The same build/replay logic bound onto mmdet's StandardRoIHead."""
+    def reg_runner():
+        from mmdet.registry import RUNNERS
+        from mmdet.engine.runner.nsrunner_roi_replay import BRNullSpaceRunner as ref_runner
+        from .runner import NullSpaceRunnerMixin
 
-            def __init__(self, *args, previous_path=None, task_id=1, task_split=(0, 10, 20),
-                         max_prototype=10, work_dir=None, **kwargs):
-                super().__init__(*args, **kwargs)
-                self.replay = False
-                self.task_split, self.task_id, self.max_proto = list(task_split), task_id, max_prototype
-                self._proto = MultiPrototypeReplay(max_prototype)
-                if previous_path is not None and osp.exists(previous_path):
-                    assert task_id != 1
-                    self.replay = True
-                    data = torch.load(osp.join(previous_path, "rois_etc.pth"), map_location="cuda")
-                    (feats, self.cls_targets, self.cls_weights, self.bbox_targets,
-                     self.bbox_weights, self.roiss) = data
-                    saved = None
-                    if osp.exists(osp.join(previous_path, "mask.pth")):
-                        saved = torch.load(osp.join(previous_path, "mask.pth"), map_location="cpu")
-                    self._proto.build(feats, self.cls_targets,
-                                      range(self.task_split[0], self.task_split[task_id - 1]), saved)
-                    self.bbox_featss, self.tmp_label = self._proto.bbox_featss, self._proto.tmp_label
-                    torch.save(self._proto.save_idx,
-                               osp.join(work_dir or get_work_dir(previous_path), "mask.pth"))
+        class BRNullSpaceRunner(NullSpaceRunnerMixin, ref_runner):
+            pass
 
-            replay_loss = StandardMultiPrototypeReplayHead.replay_loss
+        RUNNERS.register_module(name="BRNullSpaceRunner", module=BRNullSpaceRunner, force=force)
+        REGISTRY["BRNullSpaceRunner"] = BRNullSpaceRunner
+        MM_REGISTERED.setdefault("RUNNERS", []).append("BRNullSpaceRunner")
 
-            def loss(self, x, rpn_results_list, batch_data_samples):
-                losses = super().loss(x, rpn_results_list, batch_data_samples)
-                if self.replay:
-                    losses.update(self.replay_loss(self._proto.staged())["replay_loss"])
-                return losses
-
-        MODELS.register_module(name="StandardMultiPrototypeReplayHead",
-                               module=_MMDetMultiPrototypeReplayHead, force=force)
-    except Exception:
-        pass
+    MMENGINE_AVAILABLE = attempt("OPTIMIZERS['SGDNSCL']", reg_optimizer)
+    attempt("MODELS replay heads", reg_heads)
+    attempt("RUNNERS['BRNullSpaceRunner']", reg_runner)
     return dict(REGISTRY)
 
 
@@ -92,4 +146,4 @@ def build(cfg: dict, **extra):
     return cls(**cfg)
 
 
-register_all()
+register_local()

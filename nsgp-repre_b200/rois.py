@@ -41,21 +41,22 @@ def select_rois(cls_target: torch.Tensor, bg_class_id: int, target_count: int = 
     (label != ``bg_class_id`` = num_classes), topped up with random background RoIs or thinned
     by random removal to exactly ``target_count`` (all RoIs when there are fewer).  The random
     picks are ``torch.randperm(n)[:k]`` on the default CPU generator, as in the reference."""
-    mask = cls_target != bg_class_id
-    current_count = int(torch.sum(mask).item())
-    delta = target_count - current_count
-    if delta > 0:
-        false_indices = torch.where(mask == False)[0]      # noqa: E712  (reference spelling)
-        if len(false_indices) < delta:
-            mask[:] = True
+    keep = cls_target != bg_class_id
+    missing = target_count - int(keep.sum().item())
+    if missing > 0:
+        # too few foreground RoIs: top up with random background ones (:171-183)
+        background = torch.where(~keep)[0]
+        if len(background) < missing:
+            keep[:] = True
         else:
-            indices_to_add = torch.randperm(len(false_indices))[:delta]
-            mask[false_indices[indices_to_add.to(false_indices.device)]] = True
-    elif delta < 0:
-        true_indices = torch.where(mask == True)[0]        # noqa: E712
-        indices_to_remove = torch.randperm(len(true_indices))[:-delta]
-        mask[true_indices[indices_to_remove.to(true_indices.device)]] = False
-    return mask
+            chosen = torch.randperm(len(background))[:missing]
+            keep[background[chosen.to(background.device)]] = True
+    elif missing < 0:
+        # too many: drop random foreground RoIs (:184-191)
+        foreground = torch.where(keep)[0]
+        dropped = torch.randperm(len(foreground))[:-missing]
+        keep[foreground[dropped.to(foreground.device)]] = False
+    return keep
 
 
 class RoIHarvest:

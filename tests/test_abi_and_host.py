@@ -10,20 +10,35 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
+def _header_symbols(bringup=False):
+    """Function names the header declares: the product part, or the #ifdef NSGP_BRINGUP part."""
     text = open(os.path.join(ROOT, "include", "nsgp_repre_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:nsgp|repre)_[a-z0-9_]+)\s*\(", text)))
+    m = re.search(r"#ifdef NSGP_BRINGUP(.*?)#endif", text, flags=re.S)
+    assert m, "header lost its bring-up section"
+    part = m.group(1) if bringup else text[:m.start()] + text[m.end():]
+    return sorted(set(re.findall(r"\b((?:nsgp|repre)_[a-z0-9_]+)\s*\(", part)))
 
 
 def test_library_exports_every_header_symbol():
+    import subprocess
     import nsgp_repre_b200 as pkg
     syms = _header_symbols()
-    assert len(syms) >= 20
+    assert len(syms) >= 40
     for s in syms:
         assert hasattr(pkg._lib.lib, s), "missing export %s" % s
         assert s in pkg._lib.SIGNATURES, "ctypes signature missing for %s" % s
+    assert set(pkg._lib.SIGNATURES) == set(syms), "ctypes table and header disagree"
     assert pkg._lib.lib.nsgp_abi_version() == 1
+    # one engine in the shipped library: no engine switch, no debug entry points, and nothing
+    # exported besides the C ABI of the header
+    assert not pkg._lib.HAS_BRINGUP and pkg._lib.engine() == 0
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True,
+                         text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert exported == set(syms), sorted(exported ^ set(syms))
+    for s in _header_symbols(bringup=True):
+        assert s in pkg._lib.BRINGUP_SIGNATURES and not hasattr(pkg._lib.lib, s)
 
 
 def test_layout_queries_are_host_only():
