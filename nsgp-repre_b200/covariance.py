@@ -336,6 +336,18 @@ class CovarianceHooks:
                                               xs, stream.cuda_stream),
               "nsgp_cov_stage_group_launch")
 
+    def consumed_event(self):
+        """Event that fires when everything launched on the side stream so far has run, i.e.
+        when the layer inputs recorded by the forwards flushed up to now have been read
+        (``mode="deferred"`` stages at the end of the forward: a caller that recycles an input
+        buffer - the image tensor is the stem's input - waits on this).  None before the
+        first flush."""
+        if self._side is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        return ev
+
     def join(self):
         """Make the current stream wait for every contraction issued on the side stream."""
         self.flush()

@@ -79,6 +79,51 @@ def _worker(rank, world, port, ret):
     for c in range(4):
         ok &= bool(torch.allclose(means[c], F_all[lab_all == c].mean(0), atol=1e-6))
     ok &= tot.tolist() == [4, 4, 3, 1, 0] and bool(torch.isnan(means[4]).all())
+    # layer-sharded projector build: every rank ends up with every owner's result
+    dims = [12, 7, 9, 5]
+    covs = []
+    for i, d in enumerate(dims):
+        a = torch.randn(d, d, generator=torch.Generator().manual_seed(40 + i))
+        covs.append(a @ a.t())
+    owners = D.shard_by_cost([float(d) ** 3 for d in dims], world)
+    ok &= owners == [0, 1, 1, 1]                     # LPT: 1728 | 343 + 729 + 125
+    calls = []
+
+    def eig(i):
+        calls.append(i)
+        w, v = torch.linalg.eigh(covs[i].double())
+        return w.flip(0).float(), v.flip(1).float()
+
+    res = D.sharded_compute([((d,), (d, d)) for d in dims], [float(d) ** 3 for d in dims], eig,
+                            "cpu")
+    ok &= calls == [i for i in range(len(dims)) if owners[i] == rank]
+    for i, (w, v) in enumerate(res):
+        rebuilt = (v * w) @ v.t()
+        ok &= bool(torch.allclose(rebuilt, covs[i], rtol=1e-4, atol=1e-4))
+    # class-sharded prototype exchange: rows of class c go to rank (index of c) % W in
+    # (source rank, original row) order; prototypes come back in class order
+    from nsgp_repre_b200.prototypes import exchange_by_class_owner, gather_prototypes
+    gg = torch.Generator().manual_seed(60 + rank)
+    n_loc = 9 + 3 * rank
+    lab_loc = torch.randint(0, 5, (n_loc,), generator=gg)        # class 4 = background here
+    f_loc = lab_loc.float().unsqueeze(1) * 100 + rank * 10 + torch.arange(n_loc).float().unsqueeze(1) * 0.01
+    f_loc = f_loc.repeat(1, 3)
+    f_own, l_own, owned = exchange_by_class_owner(f_loc, lab_loc, [0, 1, 2, 3])
+    ok &= owned == ([0, 2] if rank == 0 else [1, 3])
+    both = [all_gather_different_shape(t) for t in (f_loc, lab_loc)]
+    F_glob, L_glob = torch.cat(both[0]), torch.cat(both[1])
+    sel = torch.zeros_like(L_glob, dtype=torch.bool)
+    for c in owned:
+        sel |= L_glob == c
+    # same multiset AND, per class, the reference's gathered order
+    for c in owned:
+        ok &= bool(torch.equal(f_own[l_own == c], F_glob[L_glob == c]))
+    ok &= int(sel.sum()) == f_own.shape[0]
+    protos = torch.stack([f_own[l_own == c].mean(0) for c in owned])
+    p_all, l_all = gather_prototypes(protos, torch.tensor(owned))
+    ok &= l_all.tolist() == [0, 1, 2, 3]
+    for c in range(4):
+        ok &= bool(torch.allclose(p_all[c], F_glob[L_glob == c].mean(0)))
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
