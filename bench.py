@@ -333,6 +333,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--stage-sms", type=int, default=None,
+                    help="SMs of the staging half of the pipelined covariance pass (0: serial)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = dict(CONFIGS[args.config])
@@ -433,6 +435,8 @@ def main():
     torch.cuda.synchronize()
     input_bytes = sum(t.numel() * 4 for t in layer_inputs.values())
 
+    if args.stage_sms is not None:
+        pkg.CovarianceHooks.stage_sms = args.stage_sms
     hooks = pkg.CovarianceHooks(model, ignore_keys=IGNORE_KEYS)
     hooks._plan_arena()
     hooked = [(r["name"], modules[r["name"]]) for r in layers]
@@ -614,9 +618,26 @@ def main():
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    cov_ms = phase_ms(cov_pass)
+    cov_ms = phase_ms(cov_pass, reps=4)
     sgd_ms = phase_ms(sgd_step)
     repre_ms = phase_ms(lambda: repre_step(feats_d, labels_d))
+
+    # host (CPU) time the training thread spends issuing each phase, GPU idle-waits excluded
+    # as far as possible: the queue is drained before every call
+    def host_ms_of(fn, reps=5):
+        tot = 0.0
+        for _ in range(reps):
+            hooks.join(); torch.cuda.synchronize()
+            h0 = time.perf_counter()
+            fn()
+            tot += time.perf_counter() - h0
+        hooks.join(); torch.cuda.synchronize()
+        return 1e3 * tot / reps
+
+    host_phase = {"covariance_hooks_and_flush": host_ms_of(cov_pass),
+                  "sgdnscl_step": host_ms_of(sgd_step),
+                  "repre_build_gather_incl_host_reads": host_ms_of(
+                      lambda: repre_step(feats_d, labels_d))}
     torch.cuda.synchronize()
     _lib.profile_read()
     _lib.profile_enable(True)
@@ -809,7 +830,8 @@ def main():
             "roofline_repre": roofline_repre,
             "cpu_baseline": cpu_baseline,
             "per_rank_ms_per_step": [m / args.steps for m in per_rank_ms],
-            "host_ms_per_step": host_ms,
+            "host_ms_per_step": host_ms, "host_ms_per_phase": host_phase,
+            "stage_sms": int(pkg.CovarianceHooks.stage_sms),
             "phase_ms": {"covariance_61_layers": cov_ms, "sgdnscl_step_projection": sgd_ms,
                          "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms,
                          "allreduce_bytes": sum(b.numel() * 4 for b in hooks.reduce_buffers()),

@@ -226,6 +226,18 @@ int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs
 int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg /* host */,
                                 const void* const* xs /* host */, void* stream);
 
+/* Pipelined covariance pass (a1 + a2): the tensor-bound contraction of the PREVIOUS forward
+ * (prev_table / prev_group from nsgp_cov_group_build, may be NULL) and the HBM-bound staging of
+ * THIS forward (stage_table / sg / xs as for nsgp_cov_stage_group_launch, may be NULL) issued
+ * so that they run side by side: the contraction kernels take (SMs - stage_sms) SMs, the
+ * first staging phase the other stage_sms, started through programmatic dependent launch as
+ * soon as the contraction CTAs are resident.  stage_sms <= 0, or only one of the two halves
+ * given: plain back-to-back launches on the whole GPU.  The two halves must use different
+ * workspace sets. */
+int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_group,
+                             void* stage_table, const nsgp_stage_group_t* sg,
+                             const void* const* xs /* host */, int stage_sms, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * a9/a10/a11  RePRE prototypes
  *   replaces the prototype build of StandardMultiPrototypeReplayHead.__init__

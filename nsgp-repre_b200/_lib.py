@@ -105,6 +105,9 @@ SIGNATURES = {
     "nsgp_cov_stage_group_launch": (c_int, [c_void_p, C.POINTER(StageGroup),
                                             C.POINTER(c_void_p), c_void_p]),
     "nsgp_group_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p]),
+    "nsgp_cov_pipeline_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p,
+                                         C.POINTER(StageGroup), C.POINTER(c_void_p), c_int,
+                                         c_void_p]),
     "repre_class_index": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
     "repre_segment_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -20,6 +20,8 @@ from __future__ import annotations
 import re
 from collections import OrderedDict
 
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -54,6 +56,8 @@ class _JobSet:
         self.stage_sig = None   # (unique job indices, B) the staging table was built for
         self.stage_table = None
         self.stage_group = None
+        self.rev = 0            # bumped whenever the job list changes (tables are rebuilt)
+        self.xs_arr = None      # reusable ctypes pointer table of the staging launch
 
 
 class CovarianceHooks:
@@ -66,6 +70,10 @@ class CovarianceHooks:
     """
 
     DEFAULT_IGNORE = ["roi_head.bbox_head.fc_cls", "roi_head.bbox_head.fc_reg", "teacher"]
+
+    # SMs the HBM-bound staging of forward i gets while the tensor-bound contraction of forward
+    # i-1 runs on the others (mode="deferred", nsgp_cov_pipeline_launch); 0 = no partitioning
+    stage_sms = 40
 
     def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
                  mode="deferred", ring=3):
@@ -104,6 +112,8 @@ class CovarianceHooks:
         self._workspace = None
         self._handles = []
         self._merged = {}           # key -> dense tensor added at finalize (old tasks)
+        self._inflight = None       # deferred mode: the set staged but not yet contracted
+        self._geom_cache = {}       # (key, input shape, kernel, stride, padding) -> layout, layer
         self._arena = None          # ONE flat fp32 buffer holding every planned accumulator
         self._alt = {}              # key -> _LayerAcc of the other layout kind (see _layer)
 
@@ -217,6 +227,7 @@ class CovarianceHooks:
                 torch.empty(int(layout.workspace_bytes), dtype=torch.uint8, device=dev)
             js.jobs.append([key, geom, ws, la, src])
             js.sig = None
+            js.rev += 1
         if src is None:
             if not deferred:
                 check(lib.nsgp_cov_conv2d_stage(ptr(x), B, *geom, ptr(ws), ws.numel(),
@@ -229,12 +240,15 @@ class CovarianceHooks:
         la.calls += 1
 
     def flush(self):
-        """Launch the grouped contraction of every layer staged since the last flush
+        """Launch the device work of every layer recorded / staged since the last flush
         (called automatically after each forward of the hooked model and by ``join``)."""
         js = self._sets[self._cur]
         if js.pos == 0:
             return
-        del js.jobs[js.pos:]
+        if len(js.jobs) != js.pos:
+            del js.jobs[js.pos:]
+            js.sig = None
+            js.rev += 1
         js.seen.clear()
         dev = js.jobs[0][2].device
         main = torch.cuda.current_stream(dev)
@@ -243,13 +257,8 @@ class CovarianceHooks:
         staged.record(main)
         side.wait_event(staged)               # the inputs exist / are staged
         if self.mode == "deferred":
-            # staging and contraction back to back on the side stream: measured
-            # (scripts/bench_cov.py, NSGP_TIMELINE=1) the two do not gain from running
-            # concurrently - next to the HBM-bound staging kernel the operand-delivery-bound
-            # contraction kernels run 1.5-3x slower - so they are serialised and the
-            # caller's stream stays free for the rest of the step
             try:
-                self._stage_deferred(js, side)
+                self._flush_deferred(js, side)
             except Exception:
                 # drop the recorded forward so that the hooks stay usable after the error
                 js.pos = 0
@@ -258,38 +267,44 @@ class CovarianceHooks:
                 raise
         else:
             js.keep.clear()
-        if js.sig is None:
-            n = len(js.jobs)
-            arr = (CovJob * n)()
-            for i, (key, geom, ws, la, _alias) in enumerate(js.jobs):
-                j = arr[i]
-                (j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw) = geom
-                j.acc, j.workspace, j.workspace_bytes = la.acc.data_ptr(), ws.data_ptr(), ws.numel()
-            need = int(lib.nsgp_cov_group_bytes(arr, n))
-            if need == 0:
-                raise _lib.NsgpError("nsgp_cov_group_bytes failed: %s" %
-                                     lib.nsgp_last_error().decode("utf-8", "replace"))
-            if js.table is None or js.table.numel() < need or js.table.device != dev:
-                js.table = torch.empty(need, dtype=torch.uint8, device=dev)
-            js.group = Group()
-            import ctypes
-            check(lib.nsgp_cov_group_build(arr, n, ptr(js.table), js.table.numel(),
-                                           ctypes.byref(js.group), side.cuda_stream),
-                  "nsgp_cov_group_build")
-            js.sig = True
-        import ctypes
-        check(lib.nsgp_group_launch(ptr(js.table), ctypes.byref(js.group), side.cuda_stream),
-              "nsgp_group_launch")
+            self._build_group(js, side)
+            check(lib.nsgp_group_launch(ptr(js.table), ctypes.byref(js.group), side.cuda_stream),
+                  "nsgp_group_launch")
         js.done = torch.cuda.Event()
         js.done.record(side)
         js.pos = 0
         self._cur ^= 1
         self._pending = True
 
-    def _stage_deferred(self, js, stream):
-        """Stage every recorded input of the set: one grouped launch (per-layer launches when
-        the inputs are not uniformly batched / 16-byte aligned)."""
-        import ctypes
+    def _build_group(self, js, stream):
+        """(Re)build the contraction table of a job set when its job list changed."""
+        if js.sig is not None:
+            return
+        n = len(js.jobs)
+        arr = (CovJob * n)()
+        for i, (key, geom, ws, la, _alias) in enumerate(js.jobs):
+            j = arr[i]
+            (j.Cin, j.H, j.W, j.kh, j.kw, j.sh, j.sw, j.ph, j.pw) = geom
+            j.acc, j.workspace, j.workspace_bytes = la.acc.data_ptr(), ws.data_ptr(), ws.numel()
+        need = int(lib.nsgp_cov_group_bytes(arr, n))
+        if need == 0:
+            raise _lib.NsgpError("nsgp_cov_group_bytes failed: %s" %
+                                 lib.nsgp_last_error().decode("utf-8", "replace"))
+        dev = js.jobs[0][2].device
+        if js.table is None or js.table.numel() < need or js.table.device != dev:
+            js.table = torch.empty(need, dtype=torch.uint8, device=dev)
+        js.group = Group()
+        check(lib.nsgp_cov_group_build(arr, n, ptr(js.table), js.table.numel(),
+                                       ctypes.byref(js.group), stream.cuda_stream),
+              "nsgp_cov_group_build")
+        js.sig = True
+
+    def _flush_deferred(self, js, side):
+        """Deferred mode, pipelined over forwards: this call stages forward i and contracts
+        forward i-1 - the HBM-bound staging kernel and the tensor-bound contraction kernels
+        run side by side on disjoint sets of SMs (``nsgp_cov_pipeline_launch``); the
+        contraction of the last forward is launched by ``join``.  Round 1 ran the two halves
+        back to back (they are a third each of the step) because sharing SMs slowed both."""
         uniq = [i for i, x in enumerate(js.xs) if x is not None]
         for i in uniq:
             if js.xs[i]._version != js.versions[i][0]:
@@ -297,17 +312,22 @@ class CovarianceHooks:
                     "input of %s was modified in place after its forward hook ran; "
                     "CovarianceHooks(mode='deferred') stages at the end of the forward - "
                     "use mode='grouped' for this model" % js.jobs[i][0])
+        self._build_group(js, side)
+        prev = self._inflight
         Bs = {js.versions[i][1] for i in uniq}
         ok = len(Bs) == 1 and all(js.xs[i].data_ptr() % 16 == 0 for i in uniq)
         if not ok:
+            # ragged batch sizes / unaligned inputs: per-layer staging launches, no pipelining
+            self._launch_inflight(side)
             for i in uniq:
                 key, geom, ws, la, _ = js.jobs[i]
                 check(lib.nsgp_cov_conv2d_stage(ptr(js.xs[i]), js.versions[i][1], *geom, ptr(ws),
-                                                ws.numel(), stream.cuda_stream),
+                                                ws.numel(), side.cuda_stream),
                       "nsgp_cov_conv2d_stage")
+            self._inflight = js
             return
         B = Bs.pop()
-        sig = (tuple(uniq), B, tuple((js.jobs[i][1], js.jobs[i][2].data_ptr()) for i in uniq))
+        sig = (js.rev, B)
         if js.stage_sig != sig:
             n = len(uniq)
             arr = (CovJob * n)()
@@ -328,13 +348,30 @@ class CovarianceHooks:
             check(lib.nsgp_cov_stage_group_build(arr, n, B, ptr(js.stage_table),
                                                  js.stage_table.numel(),
                                                  ctypes.byref(js.stage_group),
-                                                 stream.cuda_stream),
+                                                 side.cuda_stream),
                   "nsgp_cov_stage_group_build")
             js.stage_sig = sig
-        xs = (ctypes.c_void_p * len(uniq))(*[js.xs[i].data_ptr() for i in uniq])
-        check(lib.nsgp_cov_stage_group_launch(ptr(js.stage_table), ctypes.byref(js.stage_group),
-                                              xs, stream.cuda_stream),
-              "nsgp_cov_stage_group_launch")
+            js.xs_arr = (ctypes.c_void_p * n)()
+        xs = js.xs_arr
+        for k, i in enumerate(uniq):
+            xs[k] = js.xs[i].data_ptr()
+        have_prev = prev is not None and prev is not js
+        if prev is js:                        # the other set was never used: contract first
+            self._launch_inflight(side)
+        check(lib.nsgp_cov_pipeline_launch(
+            ptr(prev.table) if have_prev else None,
+            ctypes.byref(prev.group) if have_prev else None,
+            ptr(js.stage_table), ctypes.byref(js.stage_group), xs,
+            int(self.stage_sms), side.cuda_stream), "nsgp_cov_pipeline_launch")
+        self._inflight = js
+
+    def _launch_inflight(self, side):
+        """Contract the set that is staged but not yet contracted (no staging to pair with)."""
+        prev, self._inflight = self._inflight, None
+        if prev is not None:
+            check(lib.nsgp_cov_pipeline_launch(ptr(prev.table), ctypes.byref(prev.group), None,
+                                               None, None, 0, side.cuda_stream),
+                  "nsgp_cov_pipeline_launch")
 
     def consumed_event(self):
         """Event that fires when everything launched on the side stream so far has run, i.e.
@@ -351,6 +388,8 @@ class CovarianceHooks:
     def join(self):
         """Make the current stream wait for every contraction issued on the side stream."""
         self.flush()
+        if self._inflight is not None:
+            self._launch_inflight(self._side)
         if self._pending and self._side is not None:
             torch.cuda.current_stream(self._side.device).wait_stream(self._side)
             self._pending = False
@@ -370,6 +409,7 @@ class CovarianceHooks:
             acc = torch.zeros(layout.acc_bytes // 4, dtype=torch.float32, device=device)
             la = _LayerAcc(layout, acc)
             self._layers[key] = la
+            self._geom_cache.clear()
         elif la.layout.d != layout.d:
             raise _lib.NsgpError("covariance dimension of %s changed (%d -> %d)" %
                                  (key, la.layout.d, layout.d))
@@ -409,14 +449,22 @@ class CovarianceHooks:
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        B, Cin, H, W = x.shape
-        kh, kw = kernel_size
-        sh, sw = stride
-        ph, pw = padding
-        layout = CovLayout()
-        check(lib.nsgp_cov_conv2d_layout(Cin, H, W, kh, kw, sh, sw, ph, pw, layout),
-              "nsgp_cov_conv2d_layout")
-        la = self._layer(key, layout, x.device)
+        # layout + accumulator of (key, extent): looked up once, the hook runs per layer per
+        # forward on the training thread
+        ck = (key, x.shape, kernel_size, stride, padding, x.device)
+        hit = self._geom_cache.get(ck)
+        if hit is None:
+            B, Cin, H, W = x.shape
+            kh, kw = kernel_size
+            sh, sw = stride
+            ph, pw = padding
+            layout = CovLayout()
+            check(lib.nsgp_cov_conv2d_layout(Cin, H, W, kh, kw, sh, sw, ph, pw, layout),
+                  "nsgp_cov_conv2d_layout")
+            la = self._layer(key, layout, x.device)
+            hit = ((Cin, H, W, kh, kw, sh, sw, ph, pw), B, layout, la)
+            self._geom_cache[ck] = hit
+        (Cin, H, W, kh, kw, sh, sw, ph, pw), B, layout, la = hit
         mode = self.mode
         if mode in ("grouped", "deferred") and _lib.engine() != 0:
             mode = "overlap"            # the bring-up engine has no grouped launch

@@ -714,6 +714,73 @@ int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg,
   return stage_group_launch(table_dev, gi, xs, (cudaStream_t)stream_);
 }
 
+// ---- pipelined covariance pass: contraction of forward i-1 || staging of forward i ----
+static StageGroupInfo stage_from_abi(const nsgp_stage_group_t* sg) {
+  StageGroupInfo gi{};
+  gi.n_jobs = sg->n_jobs; gi.B = sg->B;
+  gi.n_items[0] = sg->n_items[0]; gi.n_items[1] = sg->n_items[1];
+  gi.off_jobs = sg->off_jobs;
+  gi.off_items[0] = sg->off_items[0]; gi.off_items[1] = sg->off_items[1];
+  gi.off_xs = sg->off_xs; gi.bytes = sg->bytes;
+  return gi;
+}
+
+int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_group,
+                             void* stage_table, const nsgp_stage_group_t* sg,
+                             const void* const* xs, int stage_sms, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool have_prev = prev_table && prev_group;
+  const bool have_stage = stage_table && sg && xs;
+  NSGP_REQUIRE(have_prev || have_stage, "cov_pipeline_launch: nothing to launch");
+  StageGroupInfo si{};
+  int rc = 0;
+  if (have_stage) {
+    si = stage_from_abi(sg);
+    // the pointer table travels BEFORE the kernels: a copy between two kernels would break
+    // their programmatic pairing
+    rc = stage_group_upload(stage_table, si, xs, stream);
+    if (rc) return rc;
+  }
+  const int sms = tc::sm_count();
+  const bool overlap = have_prev && have_stage && stage_sms > 0 && stage_sms <= sms - 16 &&
+                       si.n_items[0] > 0;
+  if (!overlap) {
+    if (have_prev) {
+      rc = group_launch(prev_table, group_from_abi(*prev_group), stream);
+      if (rc) return rc;
+    }
+    if (have_stage)
+      for (int ph = 0; ph < 2; ++ph) {
+        rc = stage_group_launch_phase(stage_table, si, ph, 0, 0, stream);
+        if (rc) return rc;
+      }
+    return 0;
+  }
+  // Partitioned: the two persistent contraction kernels take sms - stage_sms SMs (one CTA
+  // each, a whole SM's shared memory), the HBM-bound first staging phase the other stage_sms.
+  //   sliding-window(i-1) -> staging phase 0 (i) [starts as soon as every contraction CTA is
+  //   resident] -> generic(i-1) [its CTAs take over the SMs the sliding-window CTAs leave]
+  //   -> staging phase 1 (i) [ordinary launch: needs the batch means of phase 0]
+  const GroupInfo gi = group_from_abi(*prev_group);
+  const int ctas = sms - stage_sms;
+  const bool have_ac = gi.sub[2].n_items > 0, have_gen = gi.sub[0].n_items > 0;
+  NSGP_REQUIRE(gi.sub[1].n_items == 0 && gi.sub[3].n_items == 0,
+               "cov_pipeline_launch: bring-up sub-tables are not pipelined");
+  if (have_ac) {
+    rc = group_launch_sub(prev_table, gi, 2, ctas, 0, stream);
+    if (rc) return rc;
+    rc = stage_group_launch_phase(stage_table, si, 0, 1, stage_sms, stream);
+    if (rc) return rc;
+    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, ctas, 1, stream);
+  } else {
+    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, ctas, 0, stream);
+    if (rc) return rc;
+    rc = stage_group_launch_phase(stage_table, si, 0, have_gen ? 1 : 0, stage_sms, stream);
+  }
+  if (rc) return rc;
+  return stage_group_launch_phase(stage_table, si, 1, 0, 0, stream);
+}
+
 // ---------------------------------------------------------------- RePRE
 int repre_class_index(const int64_t* labels, int M, int C, int32_t* counts, int32_t* offsets,
                       int32_t* rows, void* stream_) {

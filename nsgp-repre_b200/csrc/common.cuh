@@ -145,6 +145,11 @@ size_t group_table_bytes(const ContractionArgs* probs, int n);
 int group_table_build(const ContractionArgs* probs, int n, int kind, void* table_dev,
                       size_t table_bytes, GroupInfo* info, cudaStream_t stream);
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream);
+// one sub-table of a group (0 generic kernel, 2 sliding-window kernel) on at most max_ctas
+// SMs (0: all); pdl: programmatic dependent launch behind the kernel queued before it;
+// partitioned: the CTA claims a whole SM's shared memory so that nothing else joins it
+int group_launch_sub(const void* table_dev, const GroupInfo& info, int which, int max_ctas,
+                     int pdl, cudaStream_t stream);
 
 int debug_read_counters(unsigned long long* out, int n);
 int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
@@ -161,7 +166,8 @@ size_t autocorr_table_bytes(const ConvGeom* geoms, int n);
 int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, float* const* accs,
                          int n, void* table_dev, size_t table_bytes, SubGroup* sg,
                          cudaStream_t stream);
-int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream);
+int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream,
+                    int max_ctas = 0, int pdl = 0);
 
 // wide-tile Gram kernel (contraction_wide.cu)
 struct ContractionArgs;
@@ -184,6 +190,8 @@ static inline const char* nsgp_env(const char* name) { return getenv(name); }
 constexpr int g_engine = 0;
 static inline const char* nsgp_env(const char*) { return nullptr; }
 #endif
+
+namespace tc { int sm_count(); }
 
 // number of 32-wide K blocks of an operand
 static inline int k_blocks(const Operand& o) { return ceil_div(o.K, 32); }

@@ -108,6 +108,9 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   const int lane = threadIdx.x & 31;
   const long long t_start = clock64();
   long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  // programmatic dependent launch: the staging kernel of the NEXT forward, queued behind this
+  // launch, may start on the SMs this grid leaves free as soon as all CTAs are running
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tl_begin(tl);
 
   if (warp == 0 && lane == 0) {
@@ -448,7 +451,8 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
   return 0;
 }
 
-int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream) {
+int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stream, int max_ctas,
+                    int pdl) {
   if (sg.n_items == 0) return 0;
   // A-ring depth: 3 stages fill the SM; NSGP_AC_SA=2 (192 KB of ring) leaves ~34 KB for the
   // L1 of co-resident staging kernels - measured equal end to end (scripts/overlap_probe.py:
@@ -475,11 +479,22 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   }
   const AcProblem* probs = reinterpret_cast<const AcProblem*>((const char*)table_dev + sg.off_probs);
   const AcItem* items = reinterpret_cast<const AcItem*>((const char*)table_dev + sg.off_items);
-  const int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
+  int grid = sg.n_items < sm_count() ? sg.n_items : sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   ProfScope prof(kProfGram, stream);
   static const int dbg = nsgp_env("NSGP_DBG_COUNTERS") ? 1 : 0;
-  autocorr_tc_kernel<<<grid, kThreadsAc, smem_bytes, stream>>>(probs, items, sg.n_items, dbg, sa_n, timeline_slot(10),
-                                                           wide_n, tmem_a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsAc);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, autocorr_tc_kernel, probs, items, sg.n_items, dbg, sa_n,
+                                     timeline_slot(10), wide_n, tmem_a));
   NSGP_LAUNCHED();
   return 0;
 }

@@ -132,6 +132,7 @@ contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constan
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const long long t_start = clock64();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see autocorr_tc_kernel
   tl_begin(tl);
   long long c_wait = 0, c_issue = 0, c_acc = 0, c_kb = 0;
 
@@ -488,6 +489,9 @@ void fill_operand(const Operand& o, int br, TcOperand* d) {
 }
 
 constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 + 256;
+// partitioned launches (pipelined covariance pass): the CTA claims the whole SM's shared
+// memory, like the sliding-window kernel, so that no staging block can join its SM
+constexpr size_t kSmemBytesFullSm = (size_t)7 * 32768 + 1024 + 256;
 
 int dbg_counters() {
   static const int d = (nsgp_env("NSGP_DBG_COUNTERS") ? 1 : 0) | (nsgp_env("NSGP_DBG_MMA2") ? 2 : 0) |
@@ -510,7 +514,7 @@ int configure_kernel() {
   if (!configured) {
     NSGP_CHECK_CUDA(cudaFuncSetAttribute(contraction_tc_kernel<PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBytes));
+                                         (int)kSmemBytesFullSm));
     configured = true;
   }
   return 0;
@@ -518,7 +522,8 @@ int configure_kernel() {
 
 // Launch over `n_items` work items with `workers` CTAs (single) or CTA pairs (pair).
 int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProblem* gprobs,
-                  const TcItem* gitems, int n_items, int kind, cudaStream_t stream) {
+                  const TcItem* gitems, int n_items, int kind, cudaStream_t stream,
+                  int max_ctas = 0, int pdl = 0) {
   if (n_items <= 0) return 0;
   ProfScope prof(kind, stream);
 #ifndef NSGP_BRINGUP
@@ -551,10 +556,21 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
   {
     int rc = configure_kernel<false>();
     if (rc) return rc;
-    const int grid = n_items < sm_count() ? n_items : sm_count();
-    contraction_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(
-        maps, p, gprobs, gitems, n_items, prefetch_distance(), dbg_counters(),
-        kind == kProfGram ? timeline_slot(0) : nullptr);
+    int grid = n_items < sm_count() ? n_items : sm_count();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = max_ctas > 0 ? kSmemBytesFullSm : kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<false>, maps, p, gprobs, gitems,
+                                       n_items, prefetch_distance(), dbg_counters(),
+                                       kind == kProfGram ? timeline_slot(0) : nullptr));
   }
   NSGP_LAUNCHED();
   return 0;
@@ -784,6 +800,19 @@ int group_table_build(const ContractionArgs* probs, int n, int kind, void* table
                                     hi.size() * sizeof(TcItem), cudaMemcpyHostToDevice, stream));
   }
   return 0;
+}
+
+int group_launch_sub(const void* table_dev, const GroupInfo& info, int which, int max_ctas,
+                     int pdl, cudaStream_t stream) {
+  static const TcMaps dummy_maps{};
+  TcParams dummy{};
+  if (which == 2) return autocorr_launch(table_dev, info.sub[2], stream, max_ctas, pdl);
+  const SubGroup& sg = info.sub[0];
+  if (sg.n_items == 0) return 0;
+  const TcProblem* probs = reinterpret_cast<const TcProblem*>((const char*)table_dev + sg.off_probs);
+  const TcItem* items = reinterpret_cast<const TcItem*>((const char*)table_dev + sg.off_items);
+  return launch_kernel(false, dummy_maps, dummy, probs, items, sg.n_items, info.kind, stream,
+                       max_ctas, pdl);
 }
 
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream) {

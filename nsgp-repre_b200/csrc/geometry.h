@@ -323,6 +323,10 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
                       cudaStream_t stream);
 int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
                        cudaStream_t stream);
+int stage_group_upload(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
+                       cudaStream_t stream);
+int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, int ph, int pdl,
+                             int sms, cudaStream_t stream);
 int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,
                                  cudaStream_t s);
 int launch_linear_cov(const float* x, int R, int d, float* acc, int ld, float* mean_ws,

@@ -729,6 +729,10 @@ __global__ void __launch_bounds__(256, 4)
 stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restrict__ items,
                    int n_items, const float* const* __restrict__ xs, int B,
                    unsigned long long* tl) {
+  // programmatic dependent launch: a kernel queued behind this one with the programmatic
+  // stream-serialization attribute may start as soon as every block of this grid is running
+  // (the pipelined covariance pass puts a contraction kernel there, on the other SMs)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tl_begin(tl);
   for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
     const StageItem it = items[w];
@@ -887,9 +891,29 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
   return 0;
 }
 
-int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
+int stage_group_upload(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
                        cudaStream_t stream) {
   if (info.n_jobs == 0) return 0;
+  const char* t = (const char*)table_dev;
+  for (int i = 0; i < info.n_jobs; ++i)
+    NSGP_REQUIRE(xs[i] && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0,
+                 "stage group: input %d must be a 16-byte aligned device pointer", i);
+  NSGP_CHECK_CUDA(cudaMemcpyAsync((void*)(t + info.off_xs), xs,
+                                  (size_t)info.n_jobs * sizeof(void*), cudaMemcpyHostToDevice,
+                                  stream));
+  return 0;
+}
+
+// One phase of the grouped staging.  sms > 0: the launch is confined to `sms` SMs - every
+// block asks for kStagePartSmem bytes of (unused) dynamic shared memory, which does not fit
+// next to a resident contraction CTA (>= 225 KB), so the blocks only land on the SMs the
+// contraction grid left free; pdl: launched with the programmatic stream-serialization
+// attribute, i.e. it starts while the kernel queued before it is still running.
+constexpr int kStagePartBlocksPerSm = 4;              // 256 threads x <= 64 registers
+constexpr size_t kStagePartSmem = 8 * 1024;
+int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, int ph, int pdl,
+                             int sms, cudaStream_t stream) {
+  if (info.n_jobs == 0 || info.n_items[ph] == 0) return 0;
   static const bool carve_once = [] {
     const char* e = nsgp_env("NSGP_STAGE_GROUP_CARVEOUT");
     const int co = e ? atoi(e) : -1;
@@ -899,28 +923,41 @@ int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const 
   }();
   (void)carve_once;
   const char* t = (const char*)table_dev;
-  for (int i = 0; i < info.n_jobs; ++i)
-    NSGP_REQUIRE(xs[i] && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0,
-                 "stage group: input %d must be a 16-byte aligned device pointer", i);
-  NSGP_CHECK_CUDA(cudaMemcpyAsync((void*)(t + info.off_xs), xs,
-                                  (size_t)info.n_jobs * sizeof(void*), cudaMemcpyHostToDevice,
-                                  stream));
   ProfScope prof(kProfStage, stream);
+  // blocks per SM: few enough that the persistent contraction CTA (224 threads, ~16 K
+  // registers) of the previous forward always finds room next to them
+  static const int per_sm = [] {
+    const char* e = nsgp_env("NSGP_STAGE_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : 3;
+    return v > 0 && v <= 8 ? v : 3;
+  }();
+  int cap = sms > 0 ? sms * kStagePartBlocksPerSm : sm_count() * per_sm;
+  int grid = info.n_items[ph] < cap ? info.n_items[ph] : cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = sms > 0 ? kStagePartSmem : 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  NSGP_CHECK_CUDA(cudaLaunchKernelEx(
+      &cfg, stage_group_kernel, reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
+      reinterpret_cast<const StageItem*>(t + info.off_items[ph]), info.n_items[ph],
+      reinterpret_cast<const float* const*>(t + info.off_xs), info.B, timeline_slot(2)));
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
+                       cudaStream_t stream) {
+  int rc = stage_group_upload(table_dev, info, xs, stream);
+  if (rc) return rc;
   for (int ph = 0; ph < 2; ++ph) {
-    if (info.n_items[ph] == 0) continue;
-    // blocks per SM: few enough that the persistent contraction CTA (224 threads, ~16 K
-    // registers) of the previous forward always finds room next to them
-    static const int per_sm = [] {
-      const char* e = nsgp_env("NSGP_STAGE_BLOCKS_PER_SM");
-      const int v = e ? atoi(e) : 3;
-      return v > 0 && v <= 8 ? v : 3;
-    }();
-    int grid = info.n_items[ph] < sm_count() * per_sm ? info.n_items[ph] : sm_count() * per_sm;
-    stage_group_kernel<<<grid, 256, 0, stream>>>(
-        reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
-        reinterpret_cast<const StageItem*>(t + info.off_items[ph]), info.n_items[ph],
-        reinterpret_cast<const float* const*>(t + info.off_xs), info.B, timeline_slot(2));
-    NSGP_LAUNCHED();
+    rc = stage_group_launch_phase(table_dev, info, ph, 0, 0, stream);
+    if (rc) return rc;
   }
   return 0;
 }

@@ -428,7 +428,7 @@ def test_lowrank_projection_equals_dense(pkg, engine, name):
         assert rel_fro(opt.transforms[name], P_ref) < TOL
         p.grad = grad.clone().cuda()
         opt.step()
-        used_lowrank = opt._t_arena is not None
+        used_lowrank = opt._plans[0]["t_arena"] is not None
         assert used_lowrank == (ratio > 0)
         assert rel_fro(p, ref[name]) < TOL, ratio
         outs.append(p.detach().clone())
