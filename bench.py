@@ -550,6 +550,19 @@ def main():
                                                      reduce_tail if world > 1 else None)
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
+    if os.environ.get("NSGP_TIMELINE") and _lib.HAS_BRINGUP and rank == 0:
+        # developers only (bring-up library): kernel timeline of the last timed steps
+        import ctypes
+        nslot = 512
+        buf = (ctypes.c_ulonglong * (2 * nslot))()
+        kinds = (ctypes.c_int * nslot)()
+        m = _lib.lib.nsgp_debug_timeline_read(buf, kinds, nslot)
+        ev = sorted((buf[2 * i], buf[2 * i + 1], kinds[i]) for i in range(m))[-16:]
+        tnames = {2: "stage", 0: "gram-generic", 10: "gram-autocorr"}
+        for a, b, k in ev:
+            print("   %-14s %9.3f -> %9.3f ms  (%.3f)" % (tnames.get(k, k), (a - ev[0][0]) / 1e6,
+                                                          (b - ev[0][0]) / 1e6, (b - a) / 1e6),
+                  file=sys.stderr)
 
     # the one collective of this path alone + a check of what it produced: the finalised
     # covariance after the in-place reduce of the INTERNAL accumulators (29 matrices per 3x3

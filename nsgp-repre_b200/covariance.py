@@ -73,7 +73,7 @@ class CovarianceHooks:
 
     # SMs the HBM-bound staging of forward i gets while the tensor-bound contraction of forward
     # i-1 runs on the others (mode="deferred", nsgp_cov_pipeline_launch); 0 = no partitioning
-    stage_sms = 40
+    stage_sms = 72
 
     def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
                  mode="deferred", ring=3):

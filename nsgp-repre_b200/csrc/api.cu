@@ -756,11 +756,12 @@ int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_gr
       }
     return 0;
   }
-  // Partitioned: the two persistent contraction kernels take sms - stage_sms SMs (one CTA
-  // each, a whole SM's shared memory), the HBM-bound first staging phase the other stage_sms.
-  //   sliding-window(i-1) -> staging phase 0 (i) [starts as soon as every contraction CTA is
-  //   resident] -> generic(i-1) [its CTAs take over the SMs the sliding-window CTAs leave]
-  //   -> staging phase 1 (i) [ordinary launch: needs the batch means of phase 0]
+  // Partitioned: the sliding-window kernel (MMA-issue bound, barely affected by HBM traffic
+  // next to it: +6 % measured) takes sms - stage_sms SMs, the HBM-bound first staging phase
+  // the other stage_sms, started by programmatic dependent launch as soon as every
+  // contraction CTA is resident.  The generic kernel is bound by operand delivery and
+  // measured 2x slower next to the staging traffic, so it runs alone on the whole GPU:
+  //   sliding-window(i-1) || staging phase 0 (i)  ->  generic(i-1)  ->  staging phase 1 (i)
   const GroupInfo gi = group_from_abi(*prev_group);
   const int ctas = sms - stage_sms;
   const bool have_ac = gi.sub[2].n_items > 0, have_gen = gi.sub[0].n_items > 0;
@@ -771,11 +772,11 @@ int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_gr
     if (rc) return rc;
     rc = stage_group_launch_phase(stage_table, si, 0, 1, stage_sms, stream);
     if (rc) return rc;
-    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, ctas, 1, stream);
+    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, 0, 0, stream);
   } else {
-    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, ctas, 0, stream);
+    if (have_gen) rc = group_launch_sub(prev_table, gi, 0, 0, 0, stream);
     if (rc) return rc;
-    rc = stage_group_launch_phase(stage_table, si, 0, have_gen ? 1 : 0, stage_sms, stream);
+    rc = stage_group_launch_phase(stage_table, si, 0, 0, 0, stream);
   }
   if (rc) return rc;
   return stage_group_launch_phase(stage_table, si, 1, 0, 0, stream);

@@ -7,6 +7,8 @@ import nsgp_repre_b200 as pkg
 from nsgp_repre_b200 import standin, _lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+if os.environ.get("STAGE_SMS"):
+    pkg.CovarianceHooks.stage_sms = int(os.environ["STAGE_SMS"])
 layers = bench.trace_layers(800, 1344, standin)
 g = torch.Generator(device="cuda").manual_seed(0)
 xs = [torch.relu(torch.randn(B, r["Cin"], r["H"], r["W"], device="cuda", generator=g)) for r in layers]
@@ -52,7 +54,7 @@ def timeline():
     kinds = (ctypes.c_int * n)()
     m = _lib.lib.nsgp_debug_timeline_read(buf, kinds, n)
     ev = [(buf[2 * i], buf[2 * i + 1], kinds[i]) for i in range(m)]
-    ev = ev[-15:]
+    ev = ev[-int(os.environ.get('TL_N', '15')):]
     t0 = min(e[0] for e in ev)
     names = {2: "stage", 0: "gram-generic", 10: "gram-autocorr", 11: "gram-wide"}
     for a, b, k in sorted(ev):
