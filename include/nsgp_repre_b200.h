@@ -438,6 +438,11 @@ int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int ro
                          int depth, unsigned long long* out_dev /* device */, int n_ctas,
                          void* stream);
 
+/* bring-up: every CTA streams bytes_per_cta contiguous bytes of src into shared memory with
+ * `depth` cp.async.bulk chunks of `chunk` bytes in flight; out_dev: n_ctas u64 cycle counts */
+int nsgp_debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
+                          unsigned long long* out_dev /* device */, int n_ctas, void* stream);
+
 /* bring-up: with NSGP_TIMELINE=1 in the environment the grouped staging kernel (kind 2) and
  * the two covariance contraction kernels (kind 0 generic, kind 10 sliding-window) record
  * {first block start, last block end} in globaltimer ns per launch; returns the number of

@@ -426,6 +426,11 @@ static ContractionArgs proj_args(const nsgp_proj_layer_t& L, float* w) {
     a.out = L.t;
     a.ld = (int)round_up(L.r, 4);
     a.n_cols = L.r;
+    // T is a tall, narrow product (N = r, tens of columns) with K = d: one K chain per tile
+    // leaves ~170 latency-bound items for 148 SMs (0.23 ms measured).  T is zeroed before
+    // the launch and the epilogue is a red.add, so the chain is cut into 16-block pieces -
+    // ~5x the items, each a fifth as long; the fp32 partial sums meet in L2.
+    a.chain = 16;
   } else {
     a.B = matrix_operand(L.pt_hi, L.pt_lo, L.d, L.d, ldk);
     a.out = w;
@@ -1107,6 +1112,12 @@ int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, vo
   NSGP_REQUIRE(threads > 0 && threads <= 1024 && n_ctas > 0 && smem <= 227 * 1024,
                "debug_occupy: bad arguments");
   return debug_occupy(threads, smem, cycles, n_ctas, (cudaStream_t)stream_);
+}
+
+int nsgp_debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
+                          unsigned long long* out_dev, int n_ctas, void* stream_) {
+  NSGP_REQUIRE(src && out_dev && n_ctas > 0, "bulk_probe: bad arguments");
+  return debug_bulk_probe(src, bytes_per_cta, chunk, depth, out_dev, n_ctas, (cudaStream_t)stream_);
 }
 
 int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,

@@ -727,7 +727,9 @@ size_t group_table_bytes(const ContractionArgs* probs, int n) {
     const bool gram = probs[i].epi == kEpiGramAtomic;
     const size_t tiles = gram ? (size_t)tm * (tm + 1) / 2 : (size_t)tm * tn;
     // upper bound for either kernel: 128-tiles with the shortest chain
-    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, (gram || probs[i].chain > 0) ? 32 : kChainGemm);
+    const int chain = probs[i].chain > 0 ? (probs[i].chain < 32 ? probs[i].chain : 32)
+                                         : (gram ? 32 : kChainGemm);
+    items += tiles * (size_t)ceil_div(nkb > 0 ? nkb : 1, chain);
   }
   return (size_t)n * sizeof(TcProblem) + items * sizeof(TcItem) + 1024;
 }

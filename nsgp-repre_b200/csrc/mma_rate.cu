@@ -148,6 +148,62 @@ int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, i
   return 0;
 }
 
+// Bulk-copy probe: every CTA streams its own contiguous region of `src` into shared memory
+// with `depth` chunks of `chunk` bytes in flight (cp.async.bulk, mbarrier complete_tx) and
+// drops the data.  How much HBM bandwidth can n_ctas SMs pull when the in-flight bytes live
+// in shared memory instead of registers?  out[cta] = cycles.
+__global__ void __launch_bounds__(64, 1)
+bulk_probe_kernel(const uint8_t* __restrict__ src, long long bytes_per_cta, int chunk, int depth,
+                  unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full[16], empty[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  const uint8_t* base = src + (long long)blockIdx.x * bytes_per_cta;
+  const int iters = (int)(bytes_per_cta / chunk);
+  if (warp == 0) {
+    uint32_t st = 0, ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait_warp(&empty[st], ph ^ 1, lane);
+      mbar_expect_tx_elect(&full[st], (uint32_t)chunk);
+      if (lane == 0)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(smem_raw + (size_t)st * chunk)), "l"(base + (long long)it * chunk),
+              "r"(chunk), "r"(smem_u32(&full[st]))
+            : "memory");
+      __syncwarp();
+      if (++st == (uint32_t)depth) { st = 0; ph ^= 1; }
+    }
+  } else {
+    uint32_t st = 0, ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait_warp(&full[st], ph, lane);
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == (uint32_t)depth) { st = 0; ph ^= 1; }
+    }
+    if (lane == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+}
+
+int debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
+                     unsigned long long* out_dev, int n_ctas, cudaStream_t stream) {
+  NSGP_REQUIRE(depth >= 1 && depth <= 16 && chunk % 16 == 0 && (size_t)chunk * depth <= 220 * 1024,
+               "bulk_probe: bad arguments");
+  const size_t smem = (size_t)chunk * depth;
+  NSGP_CHECK_CUDA(cudaFuncSetAttribute(bulk_probe_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  bulk_probe_kernel<<<n_ctas, 64, smem, stream>>>((const uint8_t*)src, bytes_per_cta, chunk, depth,
+                                                  out_dev);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
 // Holds `threads` threads and `smem` bytes of shared memory on every SM for `cycles`
 // clocks without touching memory: separates the occupancy / L1-carve-out cost that a
 // persistent contraction kernel imposes on co-running HBM-bound kernels from the
