@@ -326,6 +326,28 @@ int repre_greedy_segments(const uint8_t* masks, const int32_t* counts, const int
                           const int32_t* n_saved /* host */, int32_t* seg_off, int32_t* seg_rows,
                           int32_t* seg_label, int32_t* info, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* The whole prototype build of StandardMultiPrototypeReplayHead.__init__ (:404-449) for the
+ * consecutive classes [class_first, class_first + n_classes) as a FIXED sequence of launches:
+ * no class size is ever read back, every buffer is sized from M.  rows / offsets: the class
+ * index (repre_class_index).  Steps: plan (device: per-class extents, the tile pairs of ONE Gram
+ * over the class-sorted foreground rows, its work items), L2-normalise + tf32 split, tcgen05
+ * Gram, threshold + neighbour counts, density ordering + greedy cover + segment table, segment
+ * means.  saved / n_saved / saved_len replay mask.pth (:425-433): n_saved[c] masks of
+ * saved_len[c] bytes per class, packed.
+ * Outputs (device): masks (class c's n_c x n_c mask at byte offset sum_{c'<c} n_c'^2; size
+ * M*M worst case), counts[M], seg_off[n_classes*(max_picks+1)+1], seg_rows[M*(max_picks+1)],
+ * seg_label, protos (n_classes*(max_picks+1), D),
+ * info = [n_segments | picks per class (n_classes) | picks (n_classes*max_picks) | status |
+ *         n_foreground]; status 1: a class has no rows (the reference raises IndexError at
+ *         :422), 2: a replayed mask does not match its class's row count. */
+size_t repre_build_prototypes_workspace_bytes(int M, int D, int n_classes, int max_picks);
+int repre_build_prototypes(const float* F, int D, int M, const int32_t* rows,
+                           const int32_t* offsets, int class_first, int n_classes, float thresh,
+                           int max_picks, const uint8_t* saved, const int32_t* n_saved /* host */,
+                           const int32_t* saved_len /* host */, uint8_t* masks, int32_t* counts,
+                           int32_t* seg_off, int32_t* seg_rows, int32_t* seg_label, int32_t* info,
+                           float* protos, void* workspace, size_t workspace_bytes, void* stream);
+
 /* repre_segment_mean over at most max_segments segments, the live count read on the device */
 int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
                            int max_segments, const int32_t* n_segments_dev, int max_seg_rows,

@@ -126,6 +126,12 @@ SIGNATURES = {
                                       C.POINTER(C.c_int32), c_int, c_int, c_void_p,
                                       C.POINTER(C.c_int32), c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+    "repre_build_prototypes_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "repre_build_prototypes": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                       c_float, c_int, c_void_p, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "repre_segment_mean_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                        c_int, c_void_p, c_void_p]),
     "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -792,8 +792,8 @@ int repre_class_index(const int64_t* labels, int M, int C, int32_t* counts, int3
                       int32_t* rows, void* stream_) {
   NSGP_REQUIRE(labels && counts && offsets && rows, "class_index: null pointer");
   NSGP_REQUIRE(M >= 0 && C > 0, "class_index: bad sizes");
-  return launch_class_index((const long long*)labels, M, C, counts, offsets, rows,
-                            (cudaStream_t)stream_);
+  return launch_class_index_fused((const long long*)labels, M, C, counts, offsets, rows,
+                                  (cudaStream_t)stream_);
 }
 
 int repre_segment_mean(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,
@@ -1008,6 +1008,132 @@ int repre_cosine_count_batched(const float* F, int D, const int32_t* rows, const
   if (rc) return rc;
   return launch_threshold_count_batched(S, ext_dev, n_classes, max_n, thresh, mask, counts,
                                         stream);
+}
+
+// ---- device-sized prototype build: fixed launch sequence, no host read in the middle ----
+namespace {
+struct ReBuildLayout {
+  size_t off_hi, off_lo, off_S, off_prob, off_items, off_pairs, off_ext, off_cls, off_hdr,
+      off_nsaved, off_savedlen, off_greedy, bytes;
+  int ld_s, max_items, max_pairs;
+};
+ReBuildLayout rebuild_layout(int M, int D, int n_classes, int max_picks) {
+  ReBuildLayout L{};
+  const size_t Mp = (size_t)round_up(M, 128);
+  L.ld_s = (int)Mp;
+  const size_t tiles = Mp / 128;
+  L.max_pairs = (int)(tiles * (tiles + 1) / 2);
+  // items: pairs x splits, capped (the plan lowers the split count to fit)
+  L.max_items = L.max_pairs * 8 > 4096 ? L.max_pairs * 8 : 4096;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (size_t)round_up((long long)(off + bytes), 1024); return o; };
+  L.off_hi = take(Mp * D * 4);
+  L.off_lo = take(Mp * D * 4);
+  L.off_S = take(Mp * Mp * 4);
+  L.off_prob = take(contraction_problem_bytes());
+  L.off_items = take((size_t)L.max_items * contraction_item_bytes());
+  L.off_pairs = take((size_t)L.max_pairs * 8);
+  L.off_ext = take((size_t)n_classes * sizeof(ClassExtent));
+  L.off_cls = take((size_t)n_classes * sizeof(GreedyClass));
+  L.off_hdr = take(64);
+  L.off_nsaved = take((size_t)n_classes * 4);
+  L.off_savedlen = take((size_t)n_classes * 4);
+  // greedy scratch: order (M ints), segment sizes / bases, covered flags (M bytes)
+  L.off_greedy = take((size_t)M * 4 + (size_t)n_classes * (max_picks + 2) * 4 + (size_t)M + 256);
+  L.bytes = off + 1024;
+  return L;
+}
+}  // namespace
+
+size_t repre_build_prototypes_workspace_bytes(int M, int D, int n_classes, int max_picks) {
+  if (M <= 0 || D <= 0 || n_classes <= 0 || max_picks < 0) return 1024;
+  return rebuild_layout(M, D, n_classes, max_picks).bytes;
+}
+
+int repre_build_prototypes(const float* F, int D, int M, const int32_t* rows,
+                           const int32_t* offsets, int class_first, int n_classes, float thresh,
+                           int max_picks, const uint8_t* saved, const int32_t* n_saved,
+                           const int32_t* saved_len, uint8_t* masks, int32_t* counts,
+                           int32_t* seg_off, int32_t* seg_rows, int32_t* seg_label, int32_t* info,
+                           float* protos, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NSGP_REQUIRE(F && rows && offsets && masks && counts && seg_off && seg_rows && seg_label &&
+                   info && protos && workspace,
+               "build_prototypes: null pointer");
+  NSGP_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && n_classes > 0 && class_first >= 0 && max_picks >= 0,
+               "build_prototypes: bad sizes");
+  NSGP_REQUIRE(g_engine == 0, "build_prototypes needs the tcgen05 engine");
+  const ReBuildLayout L = rebuild_layout(M, D, n_classes, max_picks);
+  char* ws = align_up((char*)workspace, 1024);
+  NSGP_REQUIRE(ws + L.bytes - 1024 <= (char*)workspace + workspace_bytes,
+               "build_prototypes: workspace too small (%zu < %zu)", workspace_bytes, L.bytes);
+  float* hi = reinterpret_cast<float*>(ws + L.off_hi);
+  float* lo = reinterpret_cast<float*>(ws + L.off_lo);
+  float* S = reinterpret_cast<float*>(ws + L.off_S);
+  ClassExtent* ext = reinterpret_cast<ClassExtent*>(ws + L.off_ext);
+  GreedyClass* cls = reinterpret_cast<GreedyClass*>(ws + L.off_cls);
+  int* hdr = reinterpret_cast<int*>(ws + L.off_hdr);
+  int* nsaved_dev = nullptr;
+  int* savedlen_dev = nullptr;
+  if (saved && n_saved && saved_len) {
+    nsaved_dev = reinterpret_cast<int*>(ws + L.off_nsaved);
+    savedlen_dev = reinterpret_cast<int*>(ws + L.off_savedlen);
+    for (int c = 0; c < n_classes; ++c)
+      NSGP_REQUIRE(n_saved[c] >= 0 && n_saved[c] <= max_picks, "build_prototypes: bad n_saved");
+    NSGP_CHECK_CUDA(cudaMemcpyAsync(nsaved_dev, n_saved, (size_t)n_classes * 4,
+                                    cudaMemcpyHostToDevice, stream));
+    NSGP_CHECK_CUDA(cudaMemcpyAsync(savedlen_dev, saved_len, (size_t)n_classes * 4,
+                                    cudaMemcpyHostToDevice, stream));
+  }
+  // the ONE Gram problem: all foreground rows (class-sorted, at most round_up(M,128) of them)
+  const int Mp = L.ld_s;
+  ContractionArgs a{};
+  a.A = matrix_operand(hi, lo, Mp, D, D);
+  a.B = a.A;
+  a.out = S;
+  a.ld = L.ld_s;
+  a.n_cols = Mp;
+  a.alpha = 1.f;
+  a.epi = kEpiGramAtomic;
+  a.splits = 1;
+  std::vector<char> prob_host(contraction_problem_bytes());
+  int rc = contraction_build_problem(a, prob_host.data());
+  if (rc) return rc;
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(ws + L.off_prob, prob_host.data(), prob_host.size(),
+                                  cudaMemcpyHostToDevice, stream));
+  const int nkb = ceil_div(D, 32);
+  rc = launch_repre_plan(offsets, class_first, n_classes, L.ld_s, nsaved_dev, savedlen_dev, nkb,
+                         L.max_items, ext, cls, ws + L.off_pairs, ws + L.off_items,
+                         ws + L.off_prob, hdr, stream);
+  if (rc) return rc;
+  rc = launch_repre_prepare(F, D, M, rows, offsets, class_first, hdr, hi, lo, ws + L.off_pairs, S,
+                            L.ld_s, stream);
+  if (rc) return rc;
+  rc = contraction_launch_dev_items(ws + L.off_prob, ws + L.off_items, L.max_items, hdr + 2,
+                                    kProfRepre, stream);
+  if (rc) return rc;
+  rc = launch_threshold_count_dev(S, ext, n_classes, M, hdr, thresh, masks, counts, stream);
+  if (rc) return rc;
+  // density ordering + greedy cover + segment table + segment rows (one CTA per class)
+  int* order_ws = reinterpret_cast<int*>(ws + L.off_greedy);
+  int* seg_sizes = order_ws + M;
+  int* seg_base = seg_sizes + (size_t)n_classes * (max_picks + 1);
+  unsigned char* covered_ws = reinterpret_cast<unsigned char*>(seg_base + n_classes);
+  int* nseg = info;
+  int* npicks = info + 1;
+  int* picks = info + 1 + n_classes;
+  rc = launch_greedy_segments(cls, n_classes, M, masks, counts, saved,
+                              rows, max_picks, order_ws, covered_ws, seg_sizes,
+                              seg_base, picks, npicks, seg_off, seg_rows, seg_label, nseg, stream,
+                              offsets + class_first);
+  if (rc) return rc;
+  // plan status behind the picks: info[1 + n_classes + n_classes * max_picks + {0, 1}]
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(info + 1 + n_classes + (size_t)n_classes * max_picks, hdr + 3,
+                                  4, cudaMemcpyDeviceToDevice, stream));
+  NSGP_CHECK_CUDA(cudaMemcpyAsync(info + 2 + n_classes + (size_t)n_classes * max_picks, hdr, 4,
+                                  cudaMemcpyDeviceToDevice, stream));
+  return launch_segment_mean(F, D, seg_off, seg_rows, n_classes * (max_picks + 1), M, nullptr, 0,
+                             protos, stream, nseg);
 }
 
 int repre_replay_gather(const float* protos, const float* sigma, const int64_t* idx, int P,

@@ -151,6 +151,12 @@ int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stre
 int group_launch_sub(const void* table_dev, const GroupInfo& info, int which, int max_ctas,
                      int pdl, cudaStream_t stream);
 
+int contraction_launch_dev_items(const void* prob_dev, const void* items_dev, int max_items,
+                                 const int* n_items_dev, int kind, cudaStream_t stream);
+int contraction_build_problem(const ContractionArgs& a, void* prob_host);
+size_t contraction_problem_bytes();
+size_t contraction_item_bytes();
+
 int debug_read_counters(unsigned long long* out, int n);
 int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
                     int depth, unsigned long long* out_dev, int n_ctas, cudaStream_t stream);

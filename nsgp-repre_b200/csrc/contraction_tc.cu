@@ -113,8 +113,10 @@ template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 contraction_tc_kernel(const __grid_constant__ TcMaps pmaps, const __grid_constant__ TcParams pp,
                       const TcProblem* __restrict__ gprobs, const TcItem* __restrict__ gitems,
-                      int n_items, int prefetch_dist, int dbg,
-                      unsigned long long* tl) {
+                      int n_items_max, int prefetch_dist, int dbg,
+                      unsigned long long* tl, const int* __restrict__ n_items_dev) {
+  // the item count may live in device memory (work lists generated on the device)
+  const int n_items = n_items_dev != nullptr ? min(n_items_max, __ldg(n_items_dev)) : n_items_max;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -523,7 +525,7 @@ int configure_kernel() {
 // Launch over `n_items` work items with `workers` CTAs (single) or CTA pairs (pair).
 int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProblem* gprobs,
                   const TcItem* gitems, int n_items, int kind, cudaStream_t stream,
-                  int max_ctas = 0, int pdl = 0) {
+                  int max_ctas = 0, int pdl = 0, const int* n_items_dev = nullptr) {
   if (n_items <= 0) return 0;
   ProfScope prof(kind, stream);
 #ifndef NSGP_BRINGUP
@@ -548,7 +550,7 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
     cfg.numAttrs = 1;
     NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<true>, maps, p, gprobs, gitems,
                                        n_items, prefetch_distance(), dbg_counters(),
-                                       (unsigned long long*)nullptr));
+                                       (unsigned long long*)nullptr, (const int*)nullptr));
     NSGP_LAUNCHED();
     return 0;
   }
@@ -570,7 +572,8 @@ int launch_kernel(bool pair, const TcMaps& maps, const TcParams& p, const TcProb
     cfg.numAttrs = pdl ? 1 : 0;
     NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, contraction_tc_kernel<false>, maps, p, gprobs, gitems,
                                        n_items, prefetch_distance(), dbg_counters(),
-                                       kind == kProfGram ? timeline_slot(0) : nullptr));
+                                       kind == kProfGram ? timeline_slot(0) : nullptr,
+                                       n_items_dev));
   }
   NSGP_LAUNCHED();
   return 0;
@@ -816,6 +819,25 @@ int group_launch_sub(const void* table_dev, const GroupInfo& info, int which, in
   return launch_kernel(false, dummy_maps, dummy, probs, items, sg.n_items, info.kind, stream,
                        max_ctas, pdl);
 }
+
+// one problem, work items written by a device kernel (at most max_items of them, the live
+// count in *n_items_dev): RePRE's Gram over the class-sorted foreground rows
+int contraction_launch_dev_items(const void* prob_dev, const void* items_dev, int max_items,
+                                 const int* n_items_dev, int kind, cudaStream_t stream) {
+  static const TcMaps dummy_maps{};
+  TcParams dummy{};
+  return launch_kernel(false, dummy_maps, dummy, reinterpret_cast<const TcProblem*>(prob_dev),
+                       reinterpret_cast<const TcItem*>(items_dev), max_items, kind, stream, 0, 0,
+                       n_items_dev);
+}
+// host part of the same: validates the problem and encodes its tensor maps
+int contraction_build_problem(const ContractionArgs& a, void* prob_host /* TcProblem */) {
+  int rc = build_problem(a, false, reinterpret_cast<TcProblem*>(prob_host));
+  NSGP_REQUIRE(rc != 1, "contraction_build_problem: empty problem");
+  return rc;
+}
+size_t contraction_problem_bytes() { return sizeof(TcProblem); }
+size_t contraction_item_bytes() { return sizeof(TcItem); }
 
 int group_launch(const void* table_dev, const GroupInfo& info, cudaStream_t stream) {
   static const TcMaps dummy_maps{};

@@ -3,6 +3,7 @@
 // (mmdet/models/roi_heads/standard_roi_replay_head.py:404-463).
 #include "common.cuh"
 #include "repre.h"
+#include "tc_common.cuh"
 
 namespace nsgp {
 
@@ -300,6 +301,10 @@ greedy_cover_kernel(const GreedyClass* __restrict__ cls, const unsigned char* __
   int* order = order_ws + e.row_off;
   unsigned char* cov = covered_ws + e.row_off;
   __shared__ int s_best, s_red[8];
+  if (n == 0) {                       // empty class: reported through the plan's status word
+    if (tid == 0) { npicks[ci] = 0; seg_sizes[ci * (max_picks + 1)] = 0; }
+    return;
+  }
   for (int i = tid; i < n; i += 256) {
     const int ci_cnt = cnt[i];
     int r = 0;
@@ -389,12 +394,13 @@ segment_rows_kernel(const GreedyClass* __restrict__ cls, const unsigned char* __
                     const unsigned char* __restrict__ saved, const int* __restrict__ rows_sel,
                     int max_picks, const int* __restrict__ picks, const int* __restrict__ npicks,
                     const int* __restrict__ seg_base, const int* __restrict__ seg_off,
-                    int* __restrict__ seg_rows) {
+                    int* __restrict__ seg_rows, const int* __restrict__ rows_base) {
   const int q = blockIdx.x, ci = blockIdx.y;
   if (q > npicks[ci]) return;
   const GreedyClass e = cls[ci];
   const int n = e.n;
-  const int* src = rows_sel + e.row_off;
+  // rows_base: device offset of the first selected class in the row list (device-sized build)
+  const int* src = rows_sel + (rows_base ? *rows_base : 0) + e.row_off;
   int* dst = seg_rows + seg_off[seg_base[ci] + q];
   if (q == 0) {
     for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
@@ -433,7 +439,8 @@ int launch_greedy_segments(const GreedyClass* cls_dev, int n_classes, int max_n,
                            const unsigned char* saved, const int* rows_sel, int max_picks,
                            int* order_ws, unsigned char* covered_ws, int* seg_sizes,
                            int* seg_base, int* picks, int* npicks, int* seg_off, int* seg_rows,
-                           int* seg_label, int* nseg_out, cudaStream_t stream) {
+                           int* seg_label, int* nseg_out, cudaStream_t stream,
+                           const int* rows_base) {
   if (n_classes == 0) return 0;
   ProfScope prof(kProfRepre, stream);
   greedy_cover_kernel<<<n_classes, 256, 0, stream>>>(cls_dev, masks, counts, saved, max_picks,
@@ -445,9 +452,302 @@ int launch_greedy_segments(const GreedyClass* cls_dev, int n_classes, int max_n,
   NSGP_LAUNCHED();
   dim3 grid(max_picks + 1, n_classes);
   segment_rows_kernel<<<grid, 256, 0, stream>>>(cls_dev, masks, saved, rows_sel, max_picks, picks,
-                                                npicks, seg_base, seg_off, seg_rows);
+                                                npicks, seg_base, seg_off, seg_rows, rows_base);
   NSGP_LAUNCHED();
   (void)max_n;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Device-sized prototype build (repre_build_prototypes): nothing on the host ever learns a
+// class size, so the build is a fixed sequence of launches with no read-back in the middle.
+// ---------------------------------------------------------------------------
+// Stable class index in ONE launch (a single CTA of 32 warps): warp w owns classes w, w+32,
+// ...; it scans the labels 32 at a time - a ballot gives the class's rows of the chunk in
+// ascending order - once to count, once (after the offsets are known) to compact.
+constexpr int kCiTile = 8192;                 // labels per tile: 8 chunks of 32 per warp
+constexpr int kCiMaxC = 256;                  // classes of the single-launch index
+__global__ void __launch_bounds__(1024)
+class_index_fused_kernel(const long long* __restrict__ labels, int M, int C,
+                         int* __restrict__ counts, int* __restrict__ offsets,
+                         int* __restrict__ rows) {
+  // Warp w owns the labels [256 w, 256 w + 256) of every tile of 8192, in order.  For a chunk
+  // of 32 labels __match_any_sync gives every lane the lanes holding the same class: its rank
+  // among them is its position inside the chunk, the group's lowest lane adds the group size
+  // to the (warp, class) counter.  A scan over the 32 warps per class turns the counters
+  // into write positions, so rows of one class come out in ascending order (stable).
+  extern __shared__ int ci_smem[];            // [C] running position, [32][C] per-warp counts
+  int* s_run = ci_smem;
+  int* s_wc = ci_smem + C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  for (int c = threadIdx.x; c < C; c += 1024) s_run[c] = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int t0 = 0; t0 < M; t0 += kCiTile) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * C; i += 1024) s_wc[i] = 0;
+      __syncthreads();
+      int lab[8], rank[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {           // all 8 loads of the lane in flight together
+        const int i = t0 + warp * 256 + k * 32 + lane;
+        const long long l = i < M ? labels[i] : -1;
+        lab[k] = (l >= 0 && l < C) ? (int)l : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned grp = __match_any_sync(0xffffffffu, lab[k]);
+        rank[k] = 0;
+        if (lab[k] >= 0) {
+          rank[k] = s_wc[warp * C + lab[k]] + __popc(grp & lt);
+          __syncwarp(grp);
+          if ((grp & lt) == 0) s_wc[warp * C + lab[k]] += __popc(grp);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      // per class: exclusive scan of the warps' counts on top of the running position
+      for (int c = threadIdx.x; c < C; c += 1024) {
+        int run = s_run[c];
+        for (int w = 0; w < 32; ++w) {
+          const int n = s_wc[w * C + c];
+          s_wc[w * C + c] = run;
+          run += n;
+        }
+        s_run[c] = run;
+      }
+      __syncthreads();
+      if (pass == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (lab[k] >= 0)
+            rows[s_wc[warp * C + lab[k]] + rank[k]] = t0 + warp * 256 + k * 32 + lane;
+      }
+    }
+    if (pass == 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int off = 0;
+        for (int c = 0; c < C; ++c) {
+          const int n = s_run[c];
+          counts[c] = n; offsets[c] = off; s_run[c] = off;      // pass 1 starts at the offset
+          off += n;
+        }
+        offsets[C] = off;
+      }
+    }
+  }
+}
+
+int launch_class_index_fused(const long long* labels, int M, int C, int* counts, int* offsets,
+                             int* rows, cudaStream_t stream) {
+  if (C > kCiMaxC) return launch_class_index(labels, M, C, counts, offsets, rows, stream);
+  ProfScope prof(kProfRepre, stream);
+  const size_t smem = (size_t)(33 * C) * sizeof(int);
+  class_index_fused_kernel<<<1, 1024, smem, stream>>>(labels, M, C, counts, offsets, rows);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// Plan of one build, computed on the device from the class offsets: per-class extents for the
+// threshold / greedy kernels, the tile pairs of the ONE Gram over all foreground rows (sorted
+// by class: only tiles that contain a same-class pair are contracted), its work items and the
+// row bounds of the Gram problem.
+//   hdr[0] = n_fg, [1] = n_pairs, [2] = n_items, [3] = error (1: a class has no rows,
+//   2: a replayed mask has the wrong length), [4] = K splits
+__global__ void __launch_bounds__(256)
+repre_plan_kernel(const int* __restrict__ offsets, int class_first, int n_classes, int ld_s,
+                  const int* __restrict__ n_saved, const int* __restrict__ saved_len, int nkb,
+                  int max_items, ClassExtent* __restrict__ ext, GreedyClass* __restrict__ cls,
+                  int2* __restrict__ pairs, tc::TcItem* __restrict__ items,
+                  tc::TcProblem* __restrict__ prob, int* __restrict__ hdr) {
+  __shared__ int s_npairs, s_splits;
+  extern __shared__ int plan_smem[];          // [n_classes + 1] offsets, [n] n_saved, [n] saved_len
+  int* s_o = plan_smem;
+  int* s_ns = plan_smem + n_classes + 1;
+  int* s_sl = s_ns + n_classes;
+  // one parallel read of everything the (sequential) plan needs
+  for (int k = threadIdx.x; k <= n_classes; k += blockDim.x) s_o[k] = offsets[class_first + k];
+  for (int k = threadIdx.x; k < n_classes; k += blockDim.x) {
+    s_ns[k] = n_saved ? n_saved[k] : 0;
+    s_sl[k] = saved_len ? saved_len[k] : 0;
+  }
+  __syncthreads();
+  const int base = s_o[0];
+  if (threadIdx.x == 0) {
+    int err = 0;
+    long long moff = 0, soff = 0;
+    for (int k = 0; k < n_classes; ++k) {
+      const int a = s_o[k] - base, b = s_o[k + 1] - base;
+      const int n = b - a;
+      if (n == 0) err = 1;
+      const int ns = s_ns[k];
+      if (ns > 0 && s_sl[k] != n) err = 2;
+      ext[k] = ClassExtent{(long long)a * ld_s + a, moff, a, n, ld_s, 0};
+      cls[k] = GreedyClass{moff, soff, a, n, ns, class_first + k};
+      moff += (long long)n * n;
+      soff += (long long)ns * n;
+    }
+    const int n_fg = s_o[n_classes] - base;
+    // tile pairs (rb <= cb) that hold a pair of rows of one class; classes are contiguous
+    // and ascending, so cb_max(rb) is non-decreasing and comes from the classes touching rb
+    int np = 0;
+    const int tiles = (n_fg + 127) >> 7;
+    int k = 0;
+    for (int rb = 0; rb < tiles; ++rb) {
+      int cb_max = rb;
+      // classes intersecting tile rb: advance k to the first class that ends after the tile start
+      while (k < n_classes && s_o[k + 1] - base <= rb * 128) ++k;
+      for (int q = k; q < n_classes && s_o[q] - base < (rb + 1) * 128; ++q) {
+        const int last = (s_o[q + 1] - base - 1) >> 7;
+        if (s_o[q + 1] > s_o[q] && last > cb_max) cb_max = last;
+      }
+      for (int cb = rb; cb <= cb_max; ++cb) pairs[np++] = make_int2(rb, cb);
+    }
+    // K splits: the fp32 accumulation chain allows 64 K blocks; more splits when there are
+    // few tile pairs, so that every SM gets a couple of items
+    int splits = (nkb + 63) / 64;
+    const int want = np > 0 ? (2 * 148 + np - 1) / np : 1;
+    if (want > splits) splits = want;
+    if (splits > nkb / 4) splits = nkb / 4 > 0 ? nkb / 4 : 1;
+    while (np * splits > max_items && splits > 1) --splits;
+    s_npairs = np;
+    s_splits = splits;
+    hdr[0] = n_fg; hdr[1] = np; hdr[2] = np * splits; hdr[3] = err; hdr[4] = splits;
+    prob->p.A.rows = n_fg;
+    prob->p.B.rows = n_fg;
+    prob->p.n_cols = n_fg;
+  }
+  __syncthreads();
+  const int np = s_npairs, splits = s_splits;
+  for (int i = threadIdx.x; i < np * splits; i += blockDim.x) {
+    const int sp = i / np, pr = i - sp * np;            // K-range-major: one K range of all
+    const int2 t = pairs[pr];                           // tiles is in flight together
+    const int kb0 = (int)((long long)nkb * sp / splits);
+    const int kb1 = (int)((long long)nkb * (sp + 1) / splits);
+    items[i] = tc::TcItem{0, t.x, t.y, kb0, kb1, 0, 0, 0};
+  }
+}
+
+// zero the Gram tiles the plan selected (the buffer is sized for the worst case; only the
+// needed 128 x 128 tiles are touched)
+__global__ void __launch_bounds__(256)
+repre_clear_tiles_kernel(const int2* __restrict__ pairs, const int* __restrict__ hdr,
+                         float* __restrict__ S, int ld_s) {
+  const int np = hdr[1], n_fg = hdr[0];
+  for (int p = blockIdx.x; p < np; p += gridDim.x) {
+    const int2 t = pairs[p];
+    for (int e = threadIdx.x; e < 128 * 32; e += 256) {
+      const int r = t.x * 128 + (e >> 5), c = t.y * 128 + (e & 31) * 4;
+      if (r < n_fg && c < ld_s)
+        *reinterpret_cast<float4*>(S + (long long)r * ld_s + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// L2-normalise + tf32 split of the foreground rows, count read on the device
+__global__ void __launch_bounds__(256)
+normalize_split_dev_kernel(const float* __restrict__ F, int D, const int* __restrict__ rows,
+                           const int* __restrict__ offsets, int class_first,
+                           const int* __restrict__ hdr, float* __restrict__ hi,
+                           float* __restrict__ lo) {
+  const int i = blockIdx.x;
+  if (i >= hdr[0]) return;
+  const float4* src =
+      reinterpret_cast<const float4*>(F + (long long)rows[offsets[class_first] + i] * D);
+  const int n4 = D >> 2;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < n4; j += 256) {
+    float4 v = __ldg(src + j);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float red[8];
+  __shared__ float norm_s;
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    norm_s = sqrtf(t);
+  }
+  __syncthreads();
+  const float nrm = norm_s;
+  float4* dh = reinterpret_cast<float4*>(hi + (long long)i * D);
+  float4* dl = reinterpret_cast<float4*>(lo + (long long)i * D);
+  for (int j = threadIdx.x; j < n4; j += 256) {
+    float4 v = __ldg(src + j), h, l;
+    tf32_split(v.x / nrm, h.x, l.x);
+    tf32_split(v.y / nrm, h.y, l.y);
+    tf32_split(v.z / nrm, h.z, l.z);
+    tf32_split(v.w / nrm, h.w, l.w);
+    dh[j] = h;
+    dl[j] = l;
+  }
+}
+
+// threshold + neighbour count, one warp per foreground row; the row's class comes from a
+// binary search over the extents the plan wrote
+__global__ void __launch_bounds__(256)
+threshold_count_dev_kernel(const float* __restrict__ S_all, const ClassExtent* __restrict__ ext,
+                           int n_classes, const int* __restrict__ hdr, float thresh,
+                           unsigned char* __restrict__ mask_all, int* __restrict__ counts_all) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= hdr[0]) return;
+  int lo = 0, hi = n_classes;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (ext[mid].row_off <= i) lo = mid; else hi = mid;
+  }
+  const ClassExtent e = ext[lo];
+  const int li = i - e.row_off;
+  const float* S = S_all + e.s_off;
+  unsigned char* mask = mask_all + e.mask_off;
+  int cnt = 0;
+  for (int j = lane; j < e.n; j += 32) {
+    const float v = (li <= j) ? S[(long long)li * e.ld + j] : S[(long long)j * e.ld + li];
+    const bool m = v >= thresh;
+    mask[(long long)li * e.n + j] = m ? 1 : 0;
+    cnt += m;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts_all[i] = cnt;
+}
+
+int launch_repre_plan(const int* offsets, int class_first, int n_classes, int ld_s,
+                      const int* n_saved_dev, const int* saved_len_dev, int nkb, int max_items,
+                      ClassExtent* ext, GreedyClass* cls, void* pairs, void* items, void* prob,
+                      int* hdr, cudaStream_t stream) {
+  ProfScope prof(kProfRepre, stream);
+  repre_plan_kernel<<<1, 256, (3 * n_classes + 1) * sizeof(int), stream>>>(offsets, class_first, n_classes, ld_s, n_saved_dev,
+                                           saved_len_dev, nkb, max_items, ext, cls,
+                                           reinterpret_cast<int2*>(pairs),
+                                           reinterpret_cast<tc::TcItem*>(items),
+                                           reinterpret_cast<tc::TcProblem*>(prob), hdr);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int launch_repre_prepare(const float* F, int D, int M, const int* rows, const int* offsets,
+                         int class_first, const int* hdr, float* hi, float* lo,
+                         const void* pairs, float* S, int ld_s, cudaStream_t stream) {
+  ProfScope prof(kProfRepre, stream);
+  repre_clear_tiles_kernel<<<148 * 2, 256, 0, stream>>>(reinterpret_cast<const int2*>(pairs), hdr,
+                                                        S, ld_s);
+  NSGP_LAUNCHED();
+  normalize_split_dev_kernel<<<M, 256, 0, stream>>>(F, D, rows, offsets, class_first, hdr, hi, lo);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+int launch_threshold_count_dev(const float* S, const ClassExtent* ext, int n_classes, int M,
+                               const int* hdr, float thresh, unsigned char* mask, int* counts,
+                               cudaStream_t stream) {
+  ProfScope prof(kProfRepre, stream);
+  threshold_count_dev_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(S, ext, n_classes, hdr, thresh,
+                                                                 mask, counts);
+  NSGP_LAUNCHED();
   return 0;
 }
 

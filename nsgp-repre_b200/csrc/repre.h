@@ -21,7 +21,8 @@ int launch_greedy_segments(const GreedyClass* cls_dev, int n_classes, int max_n,
                            const unsigned char* saved, const int* rows_sel, int max_picks,
                            int* order_ws, unsigned char* covered_ws, int* seg_sizes,
                            int* seg_base, int* picks, int* npicks, int* seg_off, int* seg_rows,
-                           int* seg_label, int* nseg_out, cudaStream_t s);
+                           int* seg_label, int* nseg_out, cudaStream_t s,
+                           const int* rows_base = nullptr);
 int launch_normalize_split(const float* F, int D, const int* rows, int n, float* hi, float* lo,
                            cudaStream_t s);
 int launch_threshold_count(const float* S, int n, int ld, float thresh, unsigned char* mask,
@@ -35,6 +36,19 @@ struct ClassExtent {          // one class of a batched cosine-count call
 int launch_threshold_count_batched(const float* S_all, const ClassExtent* ext_dev, int n_classes,
                                    int max_n, float thresh, unsigned char* mask_all,
                                    int* counts_all, cudaStream_t s);
+// device-sized build (repre_build_prototypes)
+int launch_class_index_fused(const long long* labels, int M, int C, int* counts, int* offsets,
+                             int* rows, cudaStream_t s);
+int launch_repre_plan(const int* offsets, int class_first, int n_classes, int ld_s,
+                      const int* n_saved_dev, const int* saved_len_dev, int nkb, int max_items,
+                      ClassExtent* ext, GreedyClass* cls, void* pairs, void* items, void* prob,
+                      int* hdr, cudaStream_t s);
+int launch_repre_prepare(const float* F, int D, int M, const int* rows, const int* offsets,
+                         int class_first, const int* hdr, float* hi, float* lo,
+                         const void* pairs, float* S, int ld_s, cudaStream_t s);
+int launch_threshold_count_dev(const float* S, const ClassExtent* ext, int n_classes, int M,
+                               const int* hdr, float thresh, unsigned char* mask, int* counts,
+                               cudaStream_t s);
 int launch_replay_gather(const float* protos, const float* sigma, const long long* idx, int P,
                          int D, unsigned long long seed, float* out, cudaStream_t s);
 int launch_replay_gather_rois(const float* feats, const long long* cls_t, const float* cls_w,

@@ -2,14 +2,14 @@
 ``StandardMultiPrototypeReplayHead`` (mmdet/models/roi_heads/
 standard_roi_replay_head.py:375-501).
 
-Everything runs on the device - per-class segmented means (:412-414), L2-normalise +
-cosine Gram + ``>= 0.6`` + neighbour counts (:417-421), the density ordering and the
-greedy cover (:421-448: one CTA per class; a stable descending rank reproduces the tie
-order of torch's CPU sort), masked means (:443), the device-resident replay gather
-(:458-463).  The host only learns the class sizes (to size buffers and the grouped
-Gram) and, at the end, the number of prototypes; ``save_idx`` (the ``mask.pth``
-payload) is fetched when it is asked for.  With the SIMT bring-up engine the ordering
-and the cover run on the host with ``torch.sort`` like the reference.
+Everything runs on the device - the stable class index (the boolean-mask gather of :412),
+per-class segmented means (:412-414), L2-normalise + cosine Gram + ``>= 0.6`` + neighbour
+counts (:417-421), the density ordering and the greedy cover (:421-448: one CTA per class; a
+stable descending rank reproduces the tie order of torch's CPU sort), masked means (:443),
+the device-resident replay gather (:458-463).  The build is a FIXED sequence of launches
+sized from the number of rows M: no class size is read back in the middle; the host reads a
+few bytes once at the end (number of prototypes, status) and ``save_idx`` (the ``mask.pth``
+payload) only when it is asked for.
 """
 from __future__ import annotations
 
@@ -52,6 +52,8 @@ class MultiPrototypeReplay:
         self.sigma = None
         self._out = None
         self._ws = None
+        self._bufs = None
+        self._segments = None
 
     # ------------------------------------------------------------------ build
     @torch.no_grad()
@@ -74,98 +76,106 @@ class MultiPrototypeReplay:
             self.save_idx = save_idx
             return self
 
-        # stable class index over [0, C)
+        if M == 0:
+            raise IndexError("class %d has no stored RoI feature "
+                             "(index 0 is out of bounds for dimension 0 with size 0)"
+                             % previous_cls[0])
+        # stable class index over [0, C): one launch
         C = max(previous_cls) + 1
         counts = torch.empty(C, dtype=torch.int32, device=dev)
         offsets = torch.empty(C + 1, dtype=torch.int32, device=dev)
         rows = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
         check(lib.repre_class_index(ptr(labels), M, C, ptr(counts), ptr(offsets), ptr(rows),
                                     stream), "repre_class_index")
-        h_off = offsets.cpu().tolist()
+        consecutive = all(b == a + 1 for a, b in zip(previous_cls, previous_cls[1:]))
+        if not consecutive:
+            # the reference always passes range(...); an arbitrary class list is built class
+            # run by class run and concatenated
+            parts, start = [], 0
+            for i in range(1, len(previous_cls) + 1):
+                if i == len(previous_cls) or previous_cls[i] != previous_cls[i - 1] + 1:
+                    parts.append(previous_cls[start:i])
+                    start = i
+            subs = [MultiPrototypeReplay(self.max_proto, self.thresh).build(
+                feats, labels, p, saved_masks) for p in parts]
+            self.bbox_featss = torch.cat([m.bbox_featss for m in subs])
+            self.tmp_label = torch.cat([m.tmp_label for m in subs])
+            merged = list(save_idx)
+            for m in subs:
+                for c, masks in enumerate(m.save_idx):
+                    if c >= len(merged):
+                        merged.append(masks)
+                    elif masks and not merged[c]:
+                        merged[c] = masks
+            self.save_idx = merged
+            self._segments, self._feats = None, feats
+            return self
+        return self._build_device(feats, M, D, counts, offsets, rows, previous_cls, save_idx,
+                                  stream)
 
-        sizes = []
-        for c in previous_cls:
-            n = h_off[c + 1] - h_off[c]
-            if n == 0:
-                # the reference dies in sim_sum[-0//3] (:422); keep that contract
-                raise IndexError("class %d has no stored RoI feature "
-                                 "(index 0 is out of bounds for dimension 0 with size 0)" % c)
-            sizes.append(n)
-        return self._build_device(feats, rows, h_off, previous_cls, sizes, save_idx, stream)
-
-    def _build_device(self, feats, rows, h_off, previous_cls, sizes, saved_masks, stream):
-        """tcgen05 engine: Gram, ordering, cover, segment table and means without leaving
-        the device; one small D2H at the end for the number of prototypes."""
+    def _build_device(self, feats, M, D, counts, offsets, rows, previous_cls, saved_masks,
+                      stream):
+        """Everything after the class index as ONE C-ABI call (``repre_build_prototypes``): a
+        fixed sequence of launches sized from M - no class size is read back; the host reads
+        4 bytes at the end (the number of prototypes) and the masks lazily."""
         import ctypes
         dev = feats.device
-        M, D = feats.shape
-        ncls = len(sizes)
+        ncls = len(previous_cls)
+        c0 = previous_cls[0]
         mp = self.max_proto - 1
-        sizes_arr = (ctypes.c_int32 * ncls)(*sizes)
-        ids_arr = (ctypes.c_int32 * ncls)(*previous_cls)
-        n_tot = sum(sizes)
-        mask_bytes = sum(n * n for n in sizes)
-        need = int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D)) + \
-            int(lib.repre_greedy_segments_workspace_bytes(sizes_arr, ncls, mp)) + 512
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        ws = self._ws
-        ws2_off = (int(lib.repre_cosine_count_batched_workspace_bytes(sizes_arr, ncls, D)) + 255) \
-            // 256 * 256
-        consecutive = all(b == a + 1 for a, b in zip(previous_cls, previous_cls[1:]))
-        if consecutive:
-            rows_sel = rows[h_off[previous_cls[0]]:h_off[previous_cls[-1] + 1]]
-        else:
-            rows_sel = torch.cat([rows[h_off[c]:h_off[c + 1]] for c in previous_cls])
-        masks = torch.empty(max(mask_bytes, 1), dtype=torch.uint8, device=dev)
-        counts = torch.empty(n_tot, dtype=torch.int32, device=dev)
-        check(lib.repre_cosine_count_batched(
-            ptr(feats), D, ptr(rows_sel), sizes_arr, ncls, float(self.thresh), ptr(masks),
-            ptr(counts), ptr(ws), ws2_off, stream), "repre_cosine_count_batched")
+        need = int(lib.repre_build_prototypes_workspace_bytes(M, D, ncls, mp))
+        key = (M, D, ncls, mp, dev)
+        if self._bufs is None or self._bufs[0] != key:
+            nseg_max = ncls * (mp + 1)
+            self._bufs = (key, dict(
+                ws=torch.empty(need, dtype=torch.uint8, device=dev),
+                masks=torch.empty(M * M, dtype=torch.uint8, device=dev),
+                counts=torch.empty(M, dtype=torch.int32, device=dev),
+                seg_off=torch.empty(nseg_max + 1, dtype=torch.int32, device=dev),
+                seg_rows=torch.empty(M * (mp + 1), dtype=torch.int32, device=dev),
+                seg_label=torch.empty(nseg_max, dtype=torch.int32, device=dev),
+                info=torch.empty(1 + ncls + ncls * mp + 2, dtype=torch.int32, device=dev),
+                out=torch.empty(nseg_max, D, dtype=torch.float32, device=dev)))
+        b = self._bufs[1]
         # masks replayed from mask.pth (:425-433): one H2D of the packed bytes
-        saved_dev, n_saved_arr = None, None
-        saved_lists = []
-        for ci, c in enumerate(previous_cls):
-            lst = list(saved_masks[c]) if c < len(saved_masks) else []
-            saved_lists.append(lst)
+        saved_dev, n_saved_arr, len_arr = None, None, None
+        saved_lists = [list(saved_masks[c]) if c < len(saved_masks) else [] for c in previous_cls]
         if any(saved_lists):
             n_saved = [min(len(l), mp) for l in saved_lists]
+            lens = [int(l[0].numel()) if l else 0 for l in saved_lists]
             chunks = []
-            for l, k, n in zip(saved_lists, n_saved, sizes):
+            for l, k, n in zip(saved_lists, n_saved, lens):
                 for m in l[:k]:
-                    m = m.cpu().to(torch.uint8)
                     if m.numel() != n:
-                        raise IndexError("replayed mask has %d entries, the class has %d rows "
-                                         "(The shape of the mask does not match the tensor)" %
-                                         (m.numel(), n))
-                    chunks.append(m)
+                        raise IndexError("replayed masks of one class differ in length")
+                    chunks.append(m.cpu().to(torch.uint8).reshape(-1))
             if chunks:
                 saved_dev = torch.cat(chunks).to(dev)
                 n_saved_arr = (ctypes.c_int32 * ncls)(*n_saved)
-        nseg_max = ncls * (mp + 1)
-        seg = torch.empty(2 * nseg_max + 1 + n_tot * (mp + 1) + 1 + ncls + ncls * mp,
-                          dtype=torch.int32, device=dev)
-        seg_off = seg[:nseg_max + 1]
-        seg_label = seg[nseg_max + 1:2 * nseg_max + 1]
-        seg_rows = seg[2 * nseg_max + 1:2 * nseg_max + 1 + n_tot * (mp + 1)]
-        info = seg[2 * nseg_max + 1 + n_tot * (mp + 1):]
-        check(lib.repre_greedy_segments(
-            ptr(masks), ptr(counts), ptr(rows_sel), sizes_arr, ids_arr, ncls, mp,
-            ptr(saved_dev), n_saved_arr, ptr(seg_off), ptr(seg_rows), ptr(seg_label), ptr(info),
-            ws.data_ptr() + ws2_off, ws.numel() - ws2_off, stream), "repre_greedy_segments")
-        out = torch.empty(nseg_max, D, dtype=torch.float32, device=dev)
-        max_rows = max(sizes)
-        check(lib.repre_segment_mean_dev(ptr(feats), D, ptr(seg_off), ptr(seg_rows), nseg_max,
-                                         ptr(info), int(max_rows), ptr(out), stream),
-              "repre_segment_mean_dev")
-        h_info = info.cpu().tolist()                                 # the one late sync
-        nseg = h_info[0]
-        self.bbox_featss = out[:nseg]
-        self.tmp_label = seg_label[:nseg].to(torch.int64)
-        self._segments = (seg_off, seg_rows, max_rows)
+                len_arr = (ctypes.c_int32 * ncls)(*lens)
+        check(lib.repre_build_prototypes(
+            ptr(feats), D, M, ptr(rows), ptr(offsets), c0, ncls, float(self.thresh), mp,
+            ptr(saved_dev), n_saved_arr, len_arr, ptr(b["masks"]), ptr(b["counts"]),
+            ptr(b["seg_off"]), ptr(b["seg_rows"]), ptr(b["seg_label"]), ptr(b["info"]),
+            ptr(b["out"]), ptr(b["ws"]), b["ws"].numel(), stream), "repre_build_prototypes")
+        h_info = b["info"].cpu().tolist()                             # the one (late) sync
+        nseg, status = h_info[0], h_info[1 + ncls + ncls * mp]
+        if status == 1:
+            # the reference dies in sim_sum[-0//3] (:422); keep that contract
+            h_cnt = counts.cpu().tolist()
+            empty = [c for c in previous_cls if h_cnt[c] == 0]
+            raise IndexError("class %d has no stored RoI feature "
+                             "(index 0 is out of bounds for dimension 0 with size 0)" % empty[0])
+        if status == 2:
+            raise IndexError("a replayed mask does not have one entry per row of its class "
+                             "(The shape of the mask does not match the tensor)")
+        self.bbox_featss = b["out"][:nseg]
+        self.tmp_label = b["seg_label"][:nseg].to(torch.int64)
+        self._segments = (b["seg_off"], b["seg_rows"], M)
         self._feats = feats
-        self._lazy_masks = (masks, sizes, list(previous_cls), h_info[1:1 + ncls],
-                            h_info[1 + ncls:], saved_lists, list(saved_masks), mp)
+        self._lazy_masks = (b["masks"], counts, list(previous_cls), h_info[1:1 + ncls],
+                            h_info[1 + ncls:1 + ncls + ncls * mp], saved_lists,
+                            list(saved_masks), mp)
         self._save_idx = None
         return self
 
@@ -174,7 +184,9 @@ class MultiPrototypeReplay:
         """``mask.pth`` payload (:450-452): list[class] of list of bool masks over the
         class's rows; built from the device picks on first access."""
         if self._save_idx is None and self._lazy_masks is not None:
-            masks, sizes, classes, npicks, picks, saved_lists, save_idx, mp = self._lazy_masks
+            masks, counts, classes, npicks, picks, saved_lists, save_idx, mp = self._lazy_masks
+            h_cnt = counts.cpu().tolist()
+            sizes = [h_cnt[c] for c in classes]
             moff = 0
             for ci, (c, n) in enumerate(zip(classes, sizes)):
                 tmp = list(saved_lists[ci])
