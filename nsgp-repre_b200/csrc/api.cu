@@ -221,7 +221,7 @@ static int cov_layers_group_build(const ConvGeom* geoms, float* const* stages, f
     sg.off_probs += off;
     sg.off_items += off;
     gi->sub[2] = sg;
-    gi->bytes = sg.off_items + (size_t)sg.n_items * 32;
+    gi->bytes = sg.off_items + (size_t)sg.n_items * 32 + 64;     // + the scheduler's counters
   }
   return 0;
 }

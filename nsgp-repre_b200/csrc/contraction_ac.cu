@@ -90,7 +90,7 @@ __device__ unsigned long long g_ac_counters[160 * 8];
 __global__ void __launch_bounds__(kThreadsAc, 1)
 autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict__ items,
                    int n_items, int dbg, int sa_n, unsigned long long* tl,
-                   int wide_n, int tmem_a) {
+                   int wide_n, int tmem_a, int* __restrict__ sched) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -102,7 +102,14 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   uint64_t* b_empty = b_full + SB;
   uint64_t* tmem_full = b_empty + SB;
   uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  // dynamic work distribution: warp 0 draws item indices from a global ticket counter (the
+  // list is sorted by descending cost, so this is longest-processing-time-first) and hands
+  // them to the other six warps through a 4-deep ring
+  constexpr int kSched = 4;
+  uint64_t* sched_full = tmem_empty + 1;
+  uint64_t* sched_empty = sched_full + kSched;
+  int* sched_item = reinterpret_cast<int*>(sched_empty + kSched);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(sched_item + kSched);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +125,7 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 4);
+    for (int s = 0; s < kSched; ++s) { mbar_init(&sched_full[s], 1); mbar_init(&sched_empty[s], 6); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -131,6 +139,32 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  uint32_t sched_cnt = 0;
+  // warp 0: draw the next item (-1: list exhausted) and publish it
+  auto sched_draw = [&]() -> int {
+    const uint32_t s = sched_cnt % kSched, par = (sched_cnt / kSched) & 1;
+    mbar_wait_warp(&sched_empty[s], par ^ 1, lane);
+    int idx = 0;
+    if (lane == 0) {
+      idx = atomicAdd(sched, 1);
+      if (idx >= n_items) idx = -1;
+      sched_item[s] = idx;
+      mbar_arrive(&sched_full[s]);
+    }
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    ++sched_cnt;
+    return idx;
+  };
+  // the other warps: take the next published item
+  auto sched_take = [&]() -> int {
+    const uint32_t s = sched_cnt % kSched, par = (sched_cnt / kSched) & 1;
+    mbar_wait_warp(&sched_full[s], par, lane);
+    const int idx = *reinterpret_cast<volatile int*>(&sched_item[s]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sched_empty[s]);
+    ++sched_cnt;
+    return idx;
+  };
 
   if (warp == 0 || warp == 6) {
     // ============================ TMA producers ============================
@@ -138,7 +172,9 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
     // allows (one warp for both made every A load wait behind the next B slot)
     const bool is_b = warp == 0;
     uint32_t cnt = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+    for (;;) {
+      const int idx = is_b ? sched_draw() : sched_take();
+      if (idx < 0) break;
       const AcItem it = items[idx];
       const AcProblem& p = probs[it.prob];
       int sa, sb, dx, dy0;
@@ -186,7 +222,9 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     uint32_t a_cnt = 0, b_cnt = 0, n_done = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_done) {
+    for (;; ++n_done) {
+      const int idx = sched_take();
+      if (idx < 0) break;
       const AcItem it = items[idx];
       const AcProblem& p = probs[it.prob];
       int sa, sb, dx, dy0;
@@ -275,7 +313,9 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
     // ============================ epilogue ============================
     const int quad = warp & 3;
     uint32_t n_done = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n_done) {
+    for (;; ++n_done) {
+      const int idx = sched_take();
+      if (idx < 0) break;
       const AcItem it = items[idx];
       const AcProblem& p = probs[it.prob];
       int sa, sb, dx, dy0;
@@ -323,6 +363,11 @@ autocorr_tc_kernel(const AcProblem* __restrict__ probs, const AcItem* __restrict
   tc_fence_before();
   __syncthreads();
   tl_end(tl);
+  // the last CTA to leave rewinds the ticket counter for the next launch of this table
+  if (threadIdx.x == 0 && atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+    atomicExch(sched, 0);
+    atomicExch(sched + 1, 0);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -436,7 +481,7 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
   sg->n_items = (int)keys.size();
   sg->off_probs = 0;
   sg->off_items = (size_t)n * sizeof(AcProblem);
-  const size_t need = sg->off_items + keys.size() * sizeof(AcItem);
+  const size_t need = sg->off_items + keys.size() * sizeof(AcItem) + 64;   // + ticket, done
   NSGP_REQUIRE(need <= table_bytes, "autocorr table too small (%zu < %zu)", table_bytes, need);
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
                "autocorr table must be 64-byte aligned");
@@ -447,6 +492,8 @@ int autocorr_table_build(const ConvGeom* geoms, const float* const* stages, floa
                                     cudaMemcpyHostToDevice, stream));
     NSGP_CHECK_CUDA(cudaMemcpyAsync((char*)table_dev + sg->off_items, hi.data(),
                                     hi.size() * sizeof(AcItem), cudaMemcpyHostToDevice, stream));
+    NSGP_CHECK_CUDA(cudaMemsetAsync((char*)table_dev + sg->off_items + hi.size() * sizeof(AcItem),
+                                    0, 64, stream));
   }
   return 0;
 }
@@ -493,8 +540,10 @@ int autocorr_launch(const void* table_dev, const SubGroup& sg, cudaStream_t stre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  int* sched = reinterpret_cast<int*>(const_cast<char*>((const char*)table_dev) + sg.off_items +
+                                      (size_t)sg.n_items * sizeof(AcItem));
   NSGP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, autocorr_tc_kernel, probs, items, sg.n_items, dbg, sa_n,
-                                     timeline_slot(10), wide_n, tmem_a));
+                                     timeline_slot(10), wide_n, tmem_a, sched));
   NSGP_LAUNCHED();
   return 0;
 }
