@@ -844,7 +844,8 @@ def main():
             "cpu_baseline": cpu_baseline,
             "per_rank_ms_per_step": [m / args.steps for m in per_rank_ms],
             "host_ms_per_step": host_ms, "host_ms_per_phase": host_phase,
-            "stage_sms": int(pkg.CovarianceHooks.stage_sms),
+            "stage_sms": (hooks._sets[0].auto_sms[1] if hooks._sets[0].auto_sms else None)
+            if pkg.CovarianceHooks.stage_sms == "auto" else int(pkg.CovarianceHooks.stage_sms),
             "phase_ms": {"covariance_61_layers": cov_ms, "sgdnscl_step_projection": sgd_ms,
                          "repre_build_gather": repre_ms, "allreduce_covariance_once": allreduce_ms,
                          "allreduce_bytes": sum(b.numel() * 4 for b in hooks.reduce_buffers()),

@@ -57,6 +57,7 @@ class _JobSet:
         self.stage_table = None
         self.stage_group = None
         self.rev = 0            # bumped whenever the job list changes (tables are rebuilt)
+        self.auto_sms = None    # ((rev, B), SMs of the staging half) chosen by _auto_stage_sms
         self.xs_arr = None      # reusable ctypes pointer table of the staging launch
 
 
@@ -71,9 +72,16 @@ class CovarianceHooks:
 
     DEFAULT_IGNORE = ["roi_head.bbox_head.fc_cls", "roi_head.bbox_head.fc_reg", "teacher"]
 
-    # SMs the HBM-bound staging of forward i gets while the tensor-bound contraction of forward
-    # i-1 runs on the others (mode="deferred", nsgp_cov_pipeline_launch); 0 = no partitioning
-    stage_sms = 72
+    # SMs the HBM-bound staging of forward i gets while the sliding-window contraction of forward
+    # i-1 runs on the others (mode="deferred", nsgp_cov_pipeline_launch): an integer, 0 = no
+    # partitioning, "auto" = balanced per job set from the measured scaling of the two kernels
+    stage_sms = "auto"
+    # measured on B200 (profiles/pipeline_r02.txt): slowdown of the first staging phase when it
+    # runs on S of the 148 SMs next to the sliding-window kernel, and that kernel's slowdown
+    # beyond the SM ratio from the staging traffic
+    _STAGE_SCALING = ((40, 2.09), (48, 1.75), (56, 1.48), (64, 1.37), (72, 1.30), (80, 1.23),
+                      (90, 1.17), (104, 1.10), (120, 1.04))
+    _AC_CONTENTION = 1.14
 
     def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
                  mode="deferred", ring=3):
@@ -362,8 +370,41 @@ class CovarianceHooks:
             ptr(prev.table) if have_prev else None,
             ctypes.byref(prev.group) if have_prev else None,
             ptr(js.stage_table), ctypes.byref(js.stage_group), xs,
-            int(self.stage_sms), side.cuda_stream), "nsgp_cov_pipeline_launch")
+            self._auto_stage_sms(js, B) if self.stage_sms == "auto" else int(self.stage_sms),
+            side.cuda_stream), "nsgp_cov_pipeline_launch")
         self._inflight = js
+
+    def _auto_stage_sms(self, js, B):
+        """Partition that balances the two concurrent kernels of the pipelined pass: staging
+        time ~ bytes moved / 5.5 TB/s (x the measured slowdown on S SMs), sliding-window
+        time ~ issued tf32 FLOPs / 660 TFLOP/s (x 148 / (148 - S) x contention)."""
+        if js.auto_sms is not None and js.auto_sms[0] == (js.rev, B):
+            return js.auto_sms[1]
+        read = write = ac_flops = 0.0
+        for i, x in enumerate(js.xs):
+            key, (Cin, H, W, kh, kw, sh, sw, ph, pw), ws, la, alias = js.jobs[i]
+            autocorr = la.layout.kind == 1
+            if x is not None:
+                read += 4.0 * B * Cin * H * W
+                write += (6.6 if autocorr else 2.0) * 4.0 * Cin * H * W
+            if autocorr:
+                # 13 displacement blocks on / above the diagonal of the channel-tile grid, 12
+                # below; the last tile column issues round_up(C mod 128, 16) columns
+                t = -(-Cin // 128)
+                last = -(-(Cin - (t - 1) * 128) // 16) * 16
+                nsum = sum((13 if rb <= cb else 12) * (128 if cb < t - 1 else last)
+                           for rb in range(t) for cb in range(t))
+                ac_flops += 3 * 2.0 * 128 * nsum * 32 * H * -(-W // 32)
+        t_stage = (read + write) / 5.5e12
+        t_ac = ac_flops / 680e12
+        best, best_t = 0, t_stage + t_ac                 # no partition: back to back
+        if t_ac > 0 and t_stage > 0:
+            for sms, slow in self._STAGE_SCALING:
+                t = max(t_stage * slow, t_ac * 148.0 / (148 - sms) * self._AC_CONTENTION)
+                if t < best_t:
+                    best, best_t = sms, t
+        js.auto_sms = ((js.rev, B), best)
+        return best
 
     def _launch_inflight(self, side):
         """Contract the set that is staged but not yet contracted (no staging to pair with)."""
