@@ -460,6 +460,11 @@ int nsgp_debug_tma_probe(const float* base, long long pitch_elems, int K, int ro
                          int depth, unsigned long long* out_dev /* device */, int n_ctas,
                          void* stream);
 
+/* bring-up: the same with one 3-D tensor-map box (256 floats x box_rows x B images) per stage */
+int nsgp_debug_tma3d_probe(const float* base, long long img_elems, int B, int box_rows,
+                           int boxes_per_cta, int depth, unsigned long long* out_dev, int n_ctas,
+                           void* stream);
+
 /* bring-up: every CTA streams bytes_per_cta contiguous bytes of src into shared memory with
  * `depth` cp.async.bulk chunks of `chunk` bytes in flight; out_dev: n_ctas u64 cycle counts */
 int nsgp_debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,

@@ -170,6 +170,8 @@ BRINGUP_SIGNATURES = {
     "nsgp_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p]),
     "nsgp_debug_tma_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
                                      c_int, c_void_p]),
+    "nsgp_debug_tma3d_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_int, c_void_p]),
     "nsgp_debug_bulk_probe": (c_int, [c_void_p, C.c_longlong, c_int, c_int, c_void_p, c_int,
                                       c_void_p]),
     "nsgp_debug_timeline_read": (c_int, [C.POINTER(C.c_ulonglong), C.POINTER(c_int), c_int]),

@@ -1240,6 +1240,14 @@ int nsgp_debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, vo
   return debug_occupy(threads, smem, cycles, n_ctas, (cudaStream_t)stream_);
 }
 
+int nsgp_debug_tma3d_probe(const float* base, long long img_elems, int B, int box_rows,
+                           int boxes_per_cta, int depth, unsigned long long* out_dev, int n_ctas,
+                           void* stream_) {
+  NSGP_REQUIRE(base && out_dev && n_ctas > 0, "tma3d_probe: bad arguments");
+  return debug_tma3d_probe(base, img_elems, B, box_rows, boxes_per_cta, depth, out_dev, n_ctas,
+                           (cudaStream_t)stream_);
+}
+
 int nsgp_debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
                           unsigned long long* out_dev, int n_ctas, void* stream_) {
   NSGP_REQUIRE(src && out_dev && n_ctas > 0, "bulk_probe: bad arguments");

@@ -161,6 +161,9 @@ int debug_read_counters(unsigned long long* out, int n);
 int debug_tma_probe(const float* base, long long pitch_elems, int K, int rows, int iters,
                     int depth, unsigned long long* out_dev, int n_ctas, cudaStream_t stream);
 int debug_occupy(int threads, size_t smem, long long cycles, int n_ctas, cudaStream_t stream);
+int debug_tma3d_probe(const float* base, long long img_elems, int B, int box_rows,
+                      int boxes_per_cta, int depth, unsigned long long* out_dev, int n_ctas,
+                      cudaStream_t stream);
 int debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
                      unsigned long long* out_dev, int n_ctas, cudaStream_t stream);
 int debug_mma_rate(int mode, int iters, unsigned long long* out_dev, int n_ctas,

@@ -191,6 +191,77 @@ bulk_probe_kernel(const uint8_t* __restrict__ src, long long bytes_per_cta, int 
   }
 }
 
+// The same with ONE 3-D tensor-map box per stage: (256 floats, rows_per_box rows, B images)
+// - the shape a batch-mean staging kernel needs (B images' chunks in one request).
+__global__ void __launch_bounds__(64, 1)
+tma3d_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_cta, int box_rows,
+                   int box_bytes, int depth, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full[16], empty[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (warp == 0) {
+    uint32_t st = 0, ph = 0;
+    for (int it = 0; it < boxes_per_cta; ++it) {
+      mbar_wait_warp(&empty[st], ph ^ 1, lane);
+      mbar_expect_tx_elect(&full[st], (uint32_t)box_bytes);
+      const int row = (blockIdx.x * boxes_per_cta + it) * box_rows;
+      if (lane == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_raw + (size_t)st * box_bytes)),
+            "l"(reinterpret_cast<uint64_t>(&map)), "r"(smem_u32(&full[st])), "r"(0), "r"(row),
+            "r"(0)
+            : "memory");
+      __syncwarp();
+      if (++st == (uint32_t)depth) { st = 0; ph ^= 1; }
+    }
+  } else {
+    uint32_t st = 0, ph = 0;
+    for (int it = 0; it < boxes_per_cta; ++it) {
+      mbar_wait_warp(&full[st], ph, lane);
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == (uint32_t)depth) { st = 0; ph ^= 1; }
+    }
+    if (lane == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+}
+
+int debug_tma3d_probe(const float* base, long long img_elems, int B, int box_rows,
+                      int boxes_per_cta, int depth, unsigned long long* out_dev, int n_ctas,
+                      cudaStream_t stream) {
+  typedef CUresult (*Enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                          CUtensorMapFloatOOBfill);
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  NSGP_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  const int box_bytes = 256 * 4 * box_rows * B;
+  NSGP_REQUIRE(fp && depth >= 1 && depth <= 16 && (size_t)box_bytes * depth <= 220 * 1024 &&
+                   img_elems % 256 == 0, "tma3d_probe: bad arguments");
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {256, (cuuint64_t)(img_elems / 256), (cuuint64_t)B};
+  cuuint64_t gstr[2] = {1024, (cuuint64_t)img_elems * 4};
+  cuuint32_t box[3] = {256, (cuuint32_t)box_rows, (cuuint32_t)B};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((Enc)fp)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSGP_REQUIRE(r == CUDA_SUCCESS, "tma3d_probe: encode failed (%d)", (int)r);
+  NSGP_CHECK_CUDA(cudaFuncSetAttribute(tma3d_probe_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  tma3d_probe_kernel<<<n_ctas, 64, (size_t)box_bytes * depth + 1024, stream>>>(
+      map, boxes_per_cta, box_rows, box_bytes, depth, out_dev);
+  NSGP_LAUNCHED();
+  return 0;
+}
+
 int debug_bulk_probe(const void* src, long long bytes_per_cta, int chunk, int depth,
                      unsigned long long* out_dev, int n_ctas, cudaStream_t stream) {
   NSGP_REQUIRE(depth >= 1 && depth <= 16 && chunk % 16 == 0 && (size_t)chunk * depth <= 220 * 1024,
