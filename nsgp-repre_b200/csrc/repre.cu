@@ -607,7 +607,7 @@ repre_plan_kernel(const int* __restrict__ offsets, int class_first, int n_classe
     // K splits: the fp32 accumulation chain allows 64 K blocks; more splits when there are
     // few tile pairs, so that every SM gets a couple of items
     int splits = (nkb + 63) / 64;
-    const int want = np > 0 ? (2 * 148 + np - 1) / np : 1;
+    const int want = np > 0 ? (2 * 148) / np : 1;      // at most two full waves of items
     if (want > splits) splits = want;
     if (splits > nkb / 4) splits = nkb / 4 > 0 ? nkb / 4 : 1;
     while (np * splits > max_items && splits > 1) --splits;

@@ -1,7 +1,9 @@
-"""torch.distributed plumbing (one process per GPU, NCCL over NVLink; gloo on CPU
-for the tests).  The only collective on this path is the SUM all-reduce of the
-covariance accumulators (nsrunner_roi_replay.py:746-749) - see
-``CovarianceHooks.all_reduce``; RePRE class sums are additive the same way."""
+"""torch.distributed plumbing (one process per GPU, NCCL over NVLink; gloo on CPU for the
+tests): process-group bring-up from the torchrun environment, the round-robin batch shard of
+the covariance accumulation, and the layer-sharded computation the projector build uses
+(``SGDNSCL.get_eigens``).  The collective of the accumulation itself - one SUM all-reduce of
+the flat accumulator arena (nsrunner_roi_replay.py:746-749) - is ``CovarianceHooks.all_reduce``;
+the class-sharded prototype build is ``prototypes.build_prototypes_sharded``."""
 from __future__ import annotations
 
 import os
@@ -29,27 +31,6 @@ def shard_batches(n_batches: int, rank: int, world: int):
     """Batch indices of this rank: r, r+W, ... (DefaultSampler-style round robin,
     SURVEY.md 8e)."""
     return list(range(rank, n_batches, world))
-
-
-def all_reduce_sum_(tensors, group=None):
-    """In-place SUM all-reduce of a list of tensors through ONE flat buffer."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return tensors
-    flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
-    for t in tensors:
-        t.copy_(flat[off:off + t.numel()].view_as(t))
-        off += t.numel()
-    return tensors
-
-
-def max_over_ranks(value: float, device) -> float:
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return value
-    t = torch.tensor([value], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
 
 
 def shard_by_cost(costs, world: int):

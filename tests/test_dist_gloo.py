@@ -39,10 +39,6 @@ def _worker(rank, world, port, ret):
     total = sum(O.cov_conv2d(b, (3, 3), (1, 1), (1, 1)) for b in batches)
     ok = torch.allclose(hooks._layers["conv.weight"].acc.view(36, 36), total, rtol=1e-5, atol=1e-4)
     ok &= bool((hooks._layers["other.weight"].acc == 3.0).all())
-    t = [torch.ones(3) * (rank + 1), torch.ones(2, 2) * 10 * (rank + 1)]
-    D.all_reduce_sum_(t)
-    ok &= bool((t[0] == 3).all() and (t[1] == 30).all())
-    ok &= D.max_over_ranks(float(rank), "cpu") == 1.0
     # variable-length gather (nsrunner_roi_replay.py:73-105): rank r holds r+2 rows
     from nsgp_repre_b200.rois import all_gather_different_shape, RoIHarvest
     mine_t = torch.arange((rank + 2) * 3, dtype=torch.float32).view(rank + 2, 3) + 100 * rank
