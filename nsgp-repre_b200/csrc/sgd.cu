@@ -24,27 +24,57 @@ sgd_prologue_kernel(const SgdTensorDev* __restrict__ tensors,
   const SgdTensorDev t = tensors[lo];
   const long long beg = (long long)(chunk - chunk_start[lo]) * kChunk;
   const long long end = min(t.numel, beg + kChunk);
+  // one element of the update (SGD_NSCL.py:399-411); returns -lr * (momentum buffer | grad)
+  auto update = [&](float w, float& g, float& b) -> float {
+    if (wd != 0.f) g = g + wd * w;                       // side effect kept: p.grad is modified
+    float src = g;
+    if (momentum != 0.f) {
+      b = t.first ? (b + g) : (b * momentum + one_minus_damp * g);
+      if (nesterov) { g = g + momentum * b; src = g; } else { src = b; }
+    }
+    return -(lr * src);
+  };
+  // 128-bit path: every pointer 16-byte aligned, the chunk a whole number of float4s and the
+  // staged rows contiguous (pitch == d)
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.w) | reinterpret_cast<uintptr_t>(t.g) |
+                     reinterpret_cast<uintptr_t>(t.buf) | reinterpret_cast<uintptr_t>(t.u_hi) |
+                     reinterpret_cast<uintptr_t>(t.u_lo)) & 15) == 0 &&
+                   (t.numel & 3) == 0 && (t.u_hi == nullptr || t.ldu == t.d);
+  if (vec) {
+    for (long long i = beg + threadIdx.x * 4; i < end; i += 256 * 4) {
+      float4 w = *reinterpret_cast<const float4*>(t.w + i);
+      float4 g = *reinterpret_cast<const float4*>(t.g + i);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (momentum != 0.f) b = *reinterpret_cast<const float4*>(t.buf + i);
+      float4 u;
+      u.x = update(w.x, g.x, b.x); u.y = update(w.y, g.y, b.y);
+      u.z = update(w.z, g.z, b.z); u.w = update(w.w, g.w, b.w);
+      if (wd != 0.f || (momentum != 0.f && nesterov)) *reinterpret_cast<float4*>(t.g + i) = g;
+      if (momentum != 0.f) *reinterpret_cast<float4*>(t.buf + i) = b;
+      if (t.u_hi) {
+        float4 h, l;
+        tf32_split(u.x, h.x, l.x); tf32_split(u.y, h.y, l.y);
+        tf32_split(u.z, h.z, l.z); tf32_split(u.w, h.w, l.w);
+        *reinterpret_cast<float4*>(t.u_hi + i) = h;
+        *reinterpret_cast<float4*>(t.u_lo + i) = l;
+        if (t.apply != 0.f) {
+          w.x += t.apply * u.x; w.y += t.apply * u.y; w.z += t.apply * u.z; w.w += t.apply * u.w;
+          *reinterpret_cast<float4*>(t.w + i) = w;
+        }
+      } else {
+        w.x += u.x; w.y += u.y; w.z += u.z; w.w += u.w;
+        *reinterpret_cast<float4*>(t.w + i) = w;
+      }
+    }
+    return;
+  }
   for (long long i = beg + threadIdx.x; i < end; i += 256) {
     float w = t.w[i];
     float g = t.g[i];
-    if (wd != 0.f) {
-      g = g + wd * w;
-      t.g[i] = g;                       // side effect kept: p.grad is modified
-    }
-    float src = g;
-    if (momentum != 0.f) {
-      float b = t.buf[i];
-      b = t.first ? (b + g) : (b * momentum + one_minus_damp * g);
-      t.buf[i] = b;
-      if (nesterov) {
-        g = g + momentum * b;
-        t.g[i] = g;
-        src = g;
-      } else {
-        src = b;
-      }
-    }
-    float upd = -(lr * src);
+    float b = momentum != 0.f ? t.buf[i] : 0.f;
+    const float upd = update(w, g, b);
+    if (wd != 0.f || (momentum != 0.f && nesterov)) t.g[i] = g;
+    if (momentum != 0.f) t.buf[i] = b;
     if (t.u_hi) {
       float h, l;
       tf32_split(upd, h, l);

@@ -220,3 +220,33 @@ def test_bench_workload_matches_survey_appendix_a():
     assert abs(sum(r["cov_flops"] for r in small) / 1e9 - 1074.995) < 0.01
     feats, lab = bench.synthetic_rois(8, 7)
     assert feats.shape == (4096, 12544) and int((lab < 19).sum()) == 1024
+
+
+def test_auto_stage_partition_balances_with_batch_size():
+    """CovarianceHooks.stage_sms = "auto": the SMs given to the staging half of the pipelined
+    covariance pass grow with the batch size (more bytes to average per contracted FLOP) and
+    the choice is cached per job set."""
+    import types
+    import bench
+    from nsgp_repre_b200 import covariance as cv
+    layers = bench.trace_layers(800, 1344, bench.load_standin())
+    picks = {}
+    for B in (2, 8, 16):
+        js = cv._JobSet()
+        for r in layers:
+            la = types.SimpleNamespace(layout=types.SimpleNamespace(
+                kind=1 if (r["k"] == 3 and r["s"] == 1 and r["Cin"] % 8 == 0) else 0))
+            js.jobs.append([r["name"], (r["Cin"], r["H"], r["W"], r["k"], r["k"], r["s"], r["s"],
+                                        r["p"], r["p"]), None, la, None])
+            js.xs.append(object())
+        hooks = cv.CovarianceHooks(torch.nn.Identity())
+        picks[B] = hooks._auto_stage_sms(js, B)
+        assert js.auto_sms == ((js.rev, B), picks[B])
+    assert 0 < picks[2] < picks[8] < picks[16] <= 120
+    assert picks[8] in (64, 72)                      # measured optimum at configs[1]
+    # nothing to overlap (no sliding-window layers): no partition
+    js = cv._JobSet()
+    la = types.SimpleNamespace(layout=types.SimpleNamespace(kind=0))
+    js.jobs.append(["a", (64, 8, 8, 1, 1, 1, 1, 0, 0), None, la, None])
+    js.xs.append(object())
+    assert cv.CovarianceHooks(torch.nn.Identity())._auto_stage_sms(js, 8) == 0
