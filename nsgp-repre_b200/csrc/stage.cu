@@ -48,13 +48,27 @@ stage_conv_body_t(const float* __restrict__ x, float* __restrict__ stage, const 
   const float fb = (float)B;
   const int HWout = g.Hout * g.Wout;
   if (end > total) end = total;
-  for (I idx = (I)first; idx < (I)end; idx += (I)step) {
-    const int x4 = (int)(idx % W4);
-    I rest = idx / W4;
-    const int r = (int)(rest % g.Hs);
+  // (x4, r, c, copy) of the thread's first index by division, then advanced by `step` as a
+  // mixed-radix number: the gather routines are instruction-bound and the divisions were most
+  // of their instructions
+  int x4 = 0, r = 0, c = 0, copy = 0;
+  if ((I)first < (I)end) {
+    x4 = (int)((I)first % W4);
+    I rest = (I)first / W4;
+    r = (int)(rest % g.Hs);
     rest /= g.Hs;
-    const int c = (int)(rest % g.Cs);
-    const int copy = (int)(rest / g.Cs);
+    c = (int)(rest % g.Cs);
+    copy = (int)(rest / g.Cs);
+  }
+  const int dx = (int)(step % W4);
+  const long long srest = step / W4;
+  const int dr = (int)(srest % g.Hs);
+  const long long srest2 = srest / g.Hs;
+  const int dc = (int)(srest2 % g.Cs), dcopy = (int)(srest2 / g.Cs);
+  for (I idx = (I)first; idx < (I)end; idx += (I)step,
+         x4 += dx, r += dr + (x4 >= W4), x4 -= (x4 >= W4) ? W4 : 0,
+         c += dc + (r >= g.Hs), r -= (r >= g.Hs) ? g.Hs : 0,
+         copy += dcopy + (c >= g.Cs), c -= (c >= g.Cs) ? g.Cs : 0) {
     int p = 0, j = 0, y = 0;
     bool row_ok = true;
     if (g.mode != kModeFlat) {
@@ -541,9 +555,15 @@ stage_conv_explicit_body_t(const float* __restrict__ x, float* __restrict__ stag
   const int W4 = g.Ws >> 2;
   const long long total = (long long)g.Cs * W4;
   if (end > total) end = total;
-  for (I idx = (I)first; idx < (I)end; idx += (I)step) {
-    const int row = (int)(idx / W4);
-    const int k4 = (int)(idx - (I)row * W4);
+  // (row, k4) of the thread's first index by division, then advanced by `step`
+  int row = 0, k4 = 0;
+  if ((I)first < (I)end) {
+    row = (int)((I)first / W4);
+    k4 = (int)((I)first - (I)row * W4);
+  }
+  const int drow = (int)(step / W4), dk4 = (int)(step - (long long)drow * W4);
+  for (I idx = (I)first; idx < (I)end; idx += (I)step,
+         k4 += dk4, row += drow + (k4 >= W4), k4 -= (k4 >= W4) ? W4 : 0) {
     const int c = row / taps, t = row - c * taps;
     const int i = t / g.kw, j = t - i * g.kw;
     const bool row_ok = row < d;
