@@ -339,14 +339,19 @@ int repre_greedy_segments(const uint8_t* masks, const int32_t* counts, const int
  * seg_label, protos (n_classes*(max_picks+1), D),
  * info = [n_segments | picks per class (n_classes) | picks (n_classes*max_picks) | status |
  *         n_foreground]; status 1: a class has no rows (the reference raises IndexError at
- *         :422), 2: a replayed mask does not match its class's row count. */
+ *         :422), 2: a replayed mask does not match its class's row count.
+ * flags & 1: the Gram problem (tensor maps over this workspace) is still in the workspace from
+ * an earlier call with the same F-independent arguments (M, D, workspace) - the call is then
+ * launches and device-to-device copies only, i.e. capturable into a CUDA graph; needs
+ * saved == NULL. */
 size_t repre_build_prototypes_workspace_bytes(int M, int D, int n_classes, int max_picks);
 int repre_build_prototypes(const float* F, int D, int M, const int32_t* rows,
                            const int32_t* offsets, int class_first, int n_classes, float thresh,
                            int max_picks, const uint8_t* saved, const int32_t* n_saved /* host */,
                            const int32_t* saved_len /* host */, uint8_t* masks, int32_t* counts,
                            int32_t* seg_off, int32_t* seg_rows, int32_t* seg_label, int32_t* info,
-                           float* protos, void* workspace, size_t workspace_bytes, void* stream);
+                           float* protos, void* workspace, size_t workspace_bytes, int flags,
+                           void* stream);
 
 /* repre_segment_mean over at most max_segments segments, the live count read on the device */
 int repre_segment_mean_dev(const float* F, int D, const int32_t* seg_offsets, const int32_t* rows,

@@ -131,7 +131,7 @@ SIGNATURES = {
                                        c_float, c_int, c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_size_t, c_void_p]),
+                                       c_size_t, c_int, c_void_p]),
     "repre_segment_mean_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                        c_int, c_void_p, c_void_p]),
     "repre_replay_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -227,7 +227,12 @@ def require_cuda(t, name="tensor"):
 PROFILE_KINDS = {"gram": 0, "gemm": 1, "stage": 2, "sgd": 3, "repre": 4}
 
 
+PROFILE_ON = False
+
+
 def profile_enable(on: bool) -> None:
+    global PROFILE_ON
+    PROFILE_ON = bool(on)
     lib.nsgp_profile_enable(1 if on else 0)
 
 

@@ -1055,8 +1055,12 @@ int repre_build_prototypes(const float* F, int D, int M, const int32_t* rows,
                            int max_picks, const uint8_t* saved, const int32_t* n_saved,
                            const int32_t* saved_len, uint8_t* masks, int32_t* counts,
                            int32_t* seg_off, int32_t* seg_rows, int32_t* seg_label, int32_t* info,
-                           float* protos, void* workspace, size_t workspace_bytes, void* stream_) {
+                           float* protos, void* workspace, size_t workspace_bytes, int flags,
+                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool tables_resident = (flags & 1) != 0;
+  NSGP_REQUIRE(!(tables_resident && saved), "build_prototypes: replayed masks are uploaded per "
+               "call (flags & 1 needs saved == NULL)");
   NSGP_REQUIRE(F && rows && offsets && masks && counts && seg_off && seg_rows && seg_label &&
                    info && protos && workspace,
                "build_prototypes: null pointer");
@@ -1096,11 +1100,14 @@ int repre_build_prototypes(const float* F, int D, int M, const int32_t* rows,
   a.alpha = 1.f;
   a.epi = kEpiGramAtomic;
   a.splits = 1;
-  std::vector<char> prob_host(contraction_problem_bytes());
-  int rc = contraction_build_problem(a, prob_host.data());
-  if (rc) return rc;
-  NSGP_CHECK_CUDA(cudaMemcpyAsync(ws + L.off_prob, prob_host.data(), prob_host.size(),
-                                  cudaMemcpyHostToDevice, stream));
+  int rc = 0;
+  if (!tables_resident) {
+    std::vector<char> prob_host(contraction_problem_bytes());
+    rc = contraction_build_problem(a, prob_host.data());
+    if (rc) return rc;
+    NSGP_CHECK_CUDA(cudaMemcpyAsync(ws + L.off_prob, prob_host.data(), prob_host.size(),
+                                    cudaMemcpyHostToDevice, stream));
+  }
   const int nkb = ceil_div(D, 32);
   rc = launch_repre_plan(offsets, class_first, n_classes, L.ld_s, nsaved_dev, savedlen_dev, nkb,
                          L.max_items, ext, cls, ws + L.off_pairs, ws + L.off_items,

@@ -51,6 +51,34 @@ def test_prototypes_at_baseline_configs(pkg, config):
     assert torch.equal(mp.staged().cpu(), mp.bbox_featss.cpu())
 
 
+def test_prototype_build_graph_replay_tracks_the_buffers(pkg):
+    """A build repeated on the same input buffers replays a CUDA graph of its launch sequence
+    from the third run on: the replay must read the buffers' CURRENT content."""
+    feats, lab = synth.proto_features(seed=8, classes=4, per_class=45, D=12544, bg=20)
+    f_d, l_d = feats.cuda(), lab.cuda()
+    mp = pkg.MultiPrototypeReplay(10)
+    want_p, want_l, want_m = O.build_prototypes(feats, lab, range(4), 10)
+    for run in range(4):
+        mp.build(f_d, l_d, range(4))
+        assert (mp._graph is not None) == (run >= 1)
+        assert torch.equal(mp.tmp_label.cpu(), want_l)
+        assert rel_fro(mp.bbox_featss, want_p) < 1e-5
+    _same_masks(mp.save_idx, want_m)
+    # new content in the same buffers (other features, other labels): the graph follows
+    feats2, lab2 = synth.proto_features(seed=9, classes=4, per_class=45, D=12544, bg=20)
+    f_d.copy_(feats2)
+    l_d.copy_(lab2)
+    want_p2, want_l2, want_m2 = O.build_prototypes(feats2, lab2, range(4), 10)
+    mp.build(f_d, l_d, range(4))
+    assert torch.equal(mp.tmp_label.cpu(), want_l2)
+    assert rel_fro(mp.bbox_featss, want_p2) < 1e-5
+    _same_masks(mp.save_idx, want_m2)
+    # an empty class is reported from a replayed build too (status word of the plan)
+    l_d.copy_(torch.where(lab2 == 2, torch.full_like(lab2, 4), lab2))
+    with pytest.raises(IndexError):
+        mp.build(f_d, l_d, range(4))
+
+
 # ------------------------------------------------------------------ configs[3]: 4-task chain
 def test_four_task_chain_covariance_projector_and_masks(pkg, tmp_path):
     """VOC 5+5 multi-step: three task boundaries of cal_fea_in -> save -> (next task)
