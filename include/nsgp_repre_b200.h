@@ -218,12 +218,15 @@ typedef struct {
   int n_jobs, B;
   int n_items[2];
   size_t off_jobs, off_items[2], off_xs, bytes;
+  int n_items_tma, pad;            /* items of the TMA-fed staging kernel (heavy routines) */
+  size_t off_items_tma, off_maps;  /* ... and one 3-D tensor map per job, re-encoded per launch */
 } nsgp_stage_group_t;
 size_t nsgp_cov_stage_group_bytes(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B);
 int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B,
                                void* table_dev /* 64-byte aligned */, size_t table_bytes,
                                nsgp_stage_group_t* out /* host */, void* stream);
 int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg /* host */,
+                                const nsgp_cov_job_t* jobs /* host: as given to the build */,
                                 const void* const* xs /* host */, void* stream);
 
 /* Pipelined covariance pass (a1 + a2): the tensor-bound contraction of the PREVIOUS forward
@@ -236,6 +239,7 @@ int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg /*
  * workspace sets. */
 int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_group,
                              void* stage_table, const nsgp_stage_group_t* sg,
+                             const nsgp_cov_job_t* stage_jobs /* host: as given to the build */,
                              const void* const* xs /* host */, int stage_sms, void* stream);
 
 /* ------------------------------------------------------------------------- *

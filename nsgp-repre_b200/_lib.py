@@ -52,7 +52,9 @@ class SgdPlan(C.Structure):
 
 class StageGroup(C.Structure):
     _fields_ = [("n_jobs", c_int), ("B", c_int), ("n_items", c_int * 2), ("off_jobs", c_size_t),
-                ("off_items", c_size_t * 2), ("off_xs", c_size_t), ("bytes", c_size_t)]
+                ("off_items", c_size_t * 2), ("off_xs", c_size_t), ("bytes", c_size_t),
+                ("n_items_tma", c_int), ("pad", c_int), ("off_items_tma", c_size_t),
+                ("off_maps", c_size_t)]
 
 
 class EwcTensor(C.Structure):
@@ -102,12 +104,12 @@ SIGNATURES = {
     "nsgp_cov_stage_group_bytes": (c_size_t, [C.POINTER(CovJob), c_int, c_int]),
     "nsgp_cov_stage_group_build": (c_int, [C.POINTER(CovJob), c_int, c_int, c_void_p, c_size_t,
                                            C.POINTER(StageGroup), c_void_p]),
-    "nsgp_cov_stage_group_launch": (c_int, [c_void_p, C.POINTER(StageGroup),
+    "nsgp_cov_stage_group_launch": (c_int, [c_void_p, C.POINTER(StageGroup), C.POINTER(CovJob),
                                             C.POINTER(c_void_p), c_void_p]),
     "nsgp_group_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p]),
     "nsgp_cov_pipeline_launch": (c_int, [c_void_p, C.POINTER(Group), c_void_p,
-                                         C.POINTER(StageGroup), C.POINTER(c_void_p), c_int,
-                                         c_void_p]),
+                                         C.POINTER(StageGroup), C.POINTER(CovJob),
+                                         C.POINTER(c_void_p), c_int, c_void_p]),
     "repre_class_index": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
     "repre_segment_mean": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -59,6 +59,7 @@ class _JobSet:
         self.rev = 0            # bumped whenever the job list changes (tables are rebuilt)
         self.auto_sms = None    # ((rev, B), SMs of the staging half) chosen by _auto_stage_sms
         self.xs_arr = None      # reusable ctypes pointer table of the staging launch
+        self.stage_jobs = None  # the CovJob array the staging table was built from
 
 
 class CovarianceHooks:
@@ -359,6 +360,7 @@ class CovarianceHooks:
                                                  side.cuda_stream),
                   "nsgp_cov_stage_group_build")
             js.stage_sig = sig
+            js.stage_jobs = arr                   # kept: the per-launch tensor maps need them
             js.xs_arr = (ctypes.c_void_p * n)()
         xs = js.xs_arr
         for k, i in enumerate(uniq):
@@ -369,7 +371,7 @@ class CovarianceHooks:
         check(lib.nsgp_cov_pipeline_launch(
             ptr(prev.table) if have_prev else None,
             ctypes.byref(prev.group) if have_prev else None,
-            ptr(js.stage_table), ctypes.byref(js.stage_group), xs,
+            ptr(js.stage_table), ctypes.byref(js.stage_group), js.stage_jobs, xs,
             self._auto_stage_sms(js, B) if self.stage_sms == "auto" else int(self.stage_sms),
             side.cuda_stream), "nsgp_cov_pipeline_launch")
         self._inflight = js
@@ -411,7 +413,7 @@ class CovarianceHooks:
         prev, self._inflight = self._inflight, None
         if prev is not None:
             check(lib.nsgp_cov_pipeline_launch(ptr(prev.table), ctypes.byref(prev.group), None,
-                                               None, None, 0, side.cuda_stream),
+                                               None, None, None, 0, side.cuda_stream),
                   "nsgp_cov_pipeline_launch")
 
     def consumed_event(self):

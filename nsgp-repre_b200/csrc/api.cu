@@ -704,22 +704,11 @@ int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs, int n_jobs, int B, vo
   out->off_jobs = gi.off_jobs;
   out->off_items[0] = gi.off_items[0]; out->off_items[1] = gi.off_items[1];
   out->off_xs = gi.off_xs; out->bytes = gi.bytes;
+  out->n_items_tma = gi.n_items_tma; out->pad = 0; out->off_items_tma = gi.off_items_tma;
+  out->off_maps = gi.off_maps;
   return 0;
 }
 
-int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg,
-                                const void* const* xs, void* stream_) {
-  NSGP_REQUIRE(table_dev && sg && xs, "cov_stage_group_launch: null pointer");
-  StageGroupInfo gi{};
-  gi.n_jobs = sg->n_jobs; gi.B = sg->B;
-  gi.n_items[0] = sg->n_items[0]; gi.n_items[1] = sg->n_items[1];
-  gi.off_jobs = sg->off_jobs;
-  gi.off_items[0] = sg->off_items[0]; gi.off_items[1] = sg->off_items[1];
-  gi.off_xs = sg->off_xs; gi.bytes = sg->bytes;
-  return stage_group_launch(table_dev, gi, xs, (cudaStream_t)stream_);
-}
-
-// ---- pipelined covariance pass: contraction of forward i-1 || staging of forward i ----
 static StageGroupInfo stage_from_abi(const nsgp_stage_group_t* sg) {
   StageGroupInfo gi{};
   gi.n_jobs = sg->n_jobs; gi.B = sg->B;
@@ -727,15 +716,41 @@ static StageGroupInfo stage_from_abi(const nsgp_stage_group_t* sg) {
   gi.off_jobs = sg->off_jobs;
   gi.off_items[0] = sg->off_items[0]; gi.off_items[1] = sg->off_items[1];
   gi.off_xs = sg->off_xs; gi.bytes = sg->bytes;
+  gi.n_items_tma = sg->n_items_tma; gi.off_items_tma = sg->off_items_tma;
+  gi.off_maps = sg->off_maps;
   return gi;
 }
 
+// geometries of the jobs a staging table was built for (the TMA kernel's tensor maps are
+// re-encoded per launch from them and the current input pointers)
+static int stage_job_geoms(const nsgp_cov_job_t* jobs, int n, std::vector<ConvGeom>* geoms) {
+  geoms->resize(n);
+  for (int i = 0; i < n; ++i)
+    NSGP_REQUIRE(make_conv_geom(jobs[i].Cin, jobs[i].H, jobs[i].W, jobs[i].kh, jobs[i].kw,
+                                jobs[i].sh, jobs[i].sw, jobs[i].ph, jobs[i].pw,
+                                &(*geoms)[i]) == 0, "stage group: invalid conv geometry");
+  return 0;
+}
+
+int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg,
+                                const nsgp_cov_job_t* jobs, const void* const* xs,
+                                void* stream_) {
+  NSGP_REQUIRE(table_dev && sg && xs && jobs, "cov_stage_group_launch: null pointer");
+  std::vector<ConvGeom> geoms;
+  int rc = stage_job_geoms(jobs, sg->n_jobs, &geoms);
+  if (rc) return rc;
+  return stage_group_launch(table_dev, stage_from_abi(sg), xs, (cudaStream_t)stream_,
+                            geoms.data());
+}
+
+// ---- pipelined covariance pass: contraction of forward i-1 || staging of forward i ----
 int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_group,
                              void* stage_table, const nsgp_stage_group_t* sg,
-                             const void* const* xs, int stage_sms, void* stream_) {
+                             const nsgp_cov_job_t* stage_jobs, const void* const* xs,
+                             int stage_sms, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool have_prev = prev_table && prev_group;
-  const bool have_stage = stage_table && sg && xs;
+  const bool have_stage = stage_table && sg && xs && stage_jobs;
   NSGP_REQUIRE(have_prev || have_stage, "cov_pipeline_launch: nothing to launch");
   StageGroupInfo si{};
   int rc = 0;
@@ -743,22 +758,28 @@ int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_gr
     si = stage_from_abi(sg);
     // the pointer table travels BEFORE the kernels: a copy between two kernels would break
     // their programmatic pairing
-    rc = stage_group_upload(stage_table, si, xs, stream);
+    std::vector<ConvGeom> geoms;
+    rc = stage_job_geoms(stage_jobs, si.n_jobs, &geoms);
+    if (rc) return rc;
+    rc = stage_group_upload(stage_table, si, xs, stream, geoms.data());
     if (rc) return rc;
   }
   const int sms = tc::sm_count();
   const bool overlap = have_prev && have_stage && stage_sms > 0 && stage_sms <= sms - 16 &&
-                       si.n_items[0] > 0;
+                       (si.n_items[0] > 0 || si.n_items_tma > 0);
   if (!overlap) {
     if (have_prev) {
       rc = group_launch(prev_table, group_from_abi(*prev_group), stream);
       if (rc) return rc;
     }
-    if (have_stage)
+    if (have_stage) {
+      rc = stage_group_launch_tma(stage_table, si, 0, 0, stream);
+      if (rc) return rc;
       for (int ph = 0; ph < 2; ++ph) {
         rc = stage_group_launch_phase(stage_table, si, ph, 0, 0, stream);
         if (rc) return rc;
       }
+    }
     return 0;
   }
   // Partitioned: the sliding-window kernel (MMA-issue bound, barely affected by HBM traffic
@@ -772,14 +793,22 @@ int nsgp_cov_pipeline_launch(const void* prev_table, const nsgp_group_t* prev_gr
   const bool have_ac = gi.sub[2].n_items > 0, have_gen = gi.sub[0].n_items > 0;
   NSGP_REQUIRE(gi.sub[1].n_items == 0 && gi.sub[3].n_items == 0,
                "cov_pipeline_launch: bring-up sub-tables are not pipelined");
+  // the staging half: the TMA kernel when the table has TMA items (the heavy routines), else
+  // the register kernel's phase 0; whatever is left of phase 0 follows as an ordinary launch
+  const bool tma = si.n_items_tma > 0;
   if (have_ac) {
     rc = group_launch_sub(prev_table, gi, 2, ctas, 0, stream);
     if (rc) return rc;
-    rc = stage_group_launch_phase(stage_table, si, 0, 1, stage_sms, stream);
+    rc = tma ? stage_group_launch_tma(stage_table, si, 1, stage_sms, stream)
+             : stage_group_launch_phase(stage_table, si, 0, 1, stage_sms, stream);
+    if (rc) return rc;
+    if (tma) rc = stage_group_launch_phase(stage_table, si, 0, 0, 0, stream);
     if (rc) return rc;
     if (have_gen) rc = group_launch_sub(prev_table, gi, 0, 0, 0, stream);
   } else {
     if (have_gen) rc = group_launch_sub(prev_table, gi, 0, 0, 0, stream);
+    if (rc) return rc;
+    rc = stage_group_launch_tma(stage_table, si, 0, 0, stream);
     if (rc) return rc;
     rc = stage_group_launch_phase(stage_table, si, 0, 0, 0, stream);
   }

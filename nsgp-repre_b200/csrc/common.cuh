@@ -203,6 +203,10 @@ static inline const char* nsgp_env(const char*) { return nullptr; }
 #endif
 
 namespace tc { int sm_count(); }
+// 3-D fp32 tensor map (x: 256 floats, y: rows of 1 KB, z: images `img_elems` apart), box
+// (256, box_rows, B), no swizzle: the batch-mean staging kernel's view of a layer input
+int encode_batch_rows_map(CUtensorMap* dst, const float* base, long long img_elems, int B,
+                          int box_rows);
 
 // number of 32-wide K blocks of an operand
 static inline int k_blocks(const Operand& o) { return ceil_div(o.K, 32); }

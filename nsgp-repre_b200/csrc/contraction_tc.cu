@@ -668,6 +668,23 @@ int chain_limit(const TcParams& p) {
 
 }  // namespace
 
+int encode_batch_rows_map(CUtensorMap* dst, const float* base, long long img_elems, int B,
+                          int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  NSGP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable");
+  NSGP_REQUIRE(img_elems % 256 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+               "batch rows map: input must be 16-byte aligned with a multiple of 256 elements");
+  cuuint64_t gdim[3] = {256, (cuuint64_t)(img_elems / 256), (cuuint64_t)B};
+  cuuint64_t gstr[2] = {1024, (cuuint64_t)img_elems * 4};
+  cuuint32_t box[3] = {256, (cuuint32_t)box_rows, (cuuint32_t)B};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (batch rows) failed (%d)", (int)r);
+  return 0;
+}
+
 namespace tc {
 int sm_count() {
   static int n = 0;

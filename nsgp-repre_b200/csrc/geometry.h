@@ -316,15 +316,21 @@ struct StageGroupInfo {
   int n_jobs, B;
   int n_items[2];
   size_t off_jobs, off_items[2], off_xs, bytes;
+  // TMA-fed phase 0 (stage_tma_kernel): its items and one 3-D tensor map per job (re-encoded
+  // for the current input pointers at every launch)
+  int n_items_tma, pad;
+  size_t off_items_tma, off_maps;
 };
 size_t stage_group_bytes(const ConvGeom* geoms, int n, int B);
 int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
                       int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
                       cudaStream_t stream);
 int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const ConvGeom* geoms = nullptr);
 int stage_group_upload(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const ConvGeom* geoms = nullptr);
+int stage_group_launch_tma(const void* table_dev, const StageGroupInfo& info, int pdl, int sms,
+                           cudaStream_t stream);
 int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, int ph, int pdl,
                              int sms, cudaStream_t stream);
 int launch_cov_finalize_autocorr(const float* acc, float* out, int C, int accumulate,

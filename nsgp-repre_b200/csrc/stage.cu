@@ -2,8 +2,13 @@
 // engines.  All are HBM-bound element-wise/reduction kernels.
 #include <vector>
 
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "geometry.h"
+#include "tc_common.cuh"
 
 namespace nsgp {
 
@@ -798,45 +803,315 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
   tl_end(tl);
 }
 
+// ---------------------------------------------------------------------------
+// TMA-fed phase 0 (batch mean, flat 1x1 staging, vectorised autocorrelation staging).
+// The register routines keep their loads in flight in registers - ~128 KB per SM at most,
+// fine when all 148 SMs stage, not when the staging only gets a slice of the GPU next to the
+// sliding-window contraction.  Here ONE 3-D tensor-map box (256 floats x rows x B images,
+// <= 32 KB) brings the same chunk of all B images into shared memory and seven of them are
+// in flight per SM (scripts/tma3d_probe.py: the loads alone reach 149 GB/s per SM).
+//   warp 0        producer: cp.async.bulk.tensor.3d into a 7-stage ring, mbarrier complete_tx
+//   warps 1..16   two consumer groups of 8 warps; group g takes every other chunk: batch mean
+//                 out of shared memory, tf32 split, layout stores
+// Index space = float4s of the per-image tensor (every routine's input is contiguous).
+// Autocorrelation layout: the two column-shifted copies need the NEXT float4's first two
+// means; the means are written back over image 0 of the stage, so inside a stage they come
+// from shared memory; at a stage end the owner writes only the words it knows and the first
+// thread of the next stage (maybe in another CTA) writes the rest - disjoint words, no
+// ordering needed.  Padding of the tiled layout (rows H, H+1, columns >= W, channels >= C)
+// is zeroed once at table build.
+// ---------------------------------------------------------------------------
+constexpr int kTmaStages = 7;
+constexpr int kTmaGroupThreads = 256;
+constexpr int kTmaThreads = 32 + 2 * kTmaGroupThreads;
+constexpr int kTmaStageBytes = 32768;
+// rows of 1 KB per box (power of two): B * rows KB <= 32 KB per stage, <= 1024 float4s of
+// means per stage
+static inline int tma_box_rows(int B) {
+  if (B < 1 || B > 32) return 0;
+  int r = 1;
+  while (r * 2 * B <= 32 && r < 16) r *= 2;
+  return r;
+}
+static inline size_t stage_tma_smem_bytes() {
+  return (size_t)kTmaStages * kTmaStageBytes + 128 /* alignment slack */;
+}
+
+__device__ __forceinline__ void split_store1(float* hi, float* lo, float v) {
+  float h, l;
+  tf32_split(v, h, l);
+  *hi = h;
+  *lo = l;
+}
+__device__ __forceinline__ void store_hl4(float* p, long long hl, const float* h, const float* l,
+                                          int i) {
+  *reinterpret_cast<float4*>(p) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+  *reinterpret_cast<float4*>(p + hl) = make_float4(l[i], l[i + 1], l[i + 2], l[i + 3]);
+}
+// (c, r, x) += (dc, dr, dx) as a mixed-radix number with radices (-, R, X)
+__device__ __forceinline__ void radix_add(int& c, int& r, int& x, int dc, int dr, int dx, int R,
+                                          int X) {
+  x += dx;
+  const int cx = x >= X;
+  x -= cx ? X : 0;
+  r += dr + cx;
+  const int cr = r >= R;
+  r -= cr ? R : 0;
+  c += dc + cr;
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restrict__ items,
+                 int n_items, const CUtensorMap* __restrict__ maps, int B, int rows,
+                 unsigned long long* tl) {
+  using namespace tc;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ __align__(128) uint8_t tma_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tma_smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tl_begin(tl);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaGroupThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int E4 = rows * 64;                        // float4s of one image per stage
+  const uint32_t stage_tx = (uint32_t)B * rows * 1024u;
+  if (warp == 0) {
+    // ============================ producer ============================
+    uint32_t st = 0, ph = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const StageItem it = items[w];
+      const CUtensorMap* map = &maps[it.job];
+      for (long long q0 = it.lo; q0 < it.hi; q0 += E4) {
+        mbar_wait_warp(&empty[st], ph ^ 1, lane);
+        mbar_expect_tx_elect(&full[st], stage_tx);
+        if (lane == 0)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+              "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem + st * kTmaStageBytes)),
+              "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(&full[st])), "r"(0),
+              "r"((int)(q0 >> 6)), "r"(0)
+              : "memory");
+        __syncwarp();
+        if (++st == kTmaStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ============================ consumers ============================
+    const int gid = (threadIdx.x - 32) / kTmaGroupThreads;
+    const int tid = (threadIdx.x - 32) % kTmaGroupThreads;
+    const float fb = (float)B, inv = 1.f / fb;
+    const bool pow2 = (B & (B - 1)) == 0;          // then x * (1/B) == x / B exactly
+    uint32_t st = 0, ph = 0, n = 0;                // ring slot / phase / chunk number
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const StageItem it = items[w];
+      const StageJobDev& j = jobs[it.job];
+      const int kind = it.kind;
+      const long long hl = j.hl;
+      float* const stage = j.stage;
+      // autocorrelation geometry (tiled layout; W % 4 == 0)
+      const int H = j.g.H, W = j.g.W, C = j.g.C;
+      const int W4 = W >> 2, HW4 = H * W4;
+      const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Hs = H + 2;
+      const long long copy_stride = (long long)CB * Hs * NS * 4096;
+      float* const rowbuf = stage + j.rowbuf_off;
+      // coordinates (c, r, x4) of this thread's first float4 of its group's first chunk of
+      // the item, by division; afterwards advanced as a mixed-radix number (the divisions
+      // would be a third of the consumer's instructions)
+      const int k0 = (int)((gid - n) & 1u);        // first chunk of the item that is ours
+      int c0 = 0, r0 = 0, x0 = 0, dcC = 0, drC = 0, dxC = 0, dcU = 0, drU = 0, dxU = 0;
+      if (kind == kStAcVec) {
+        const long long q = it.lo + (long long)k0 * E4 + tid;
+        c0 = (int)(q / HW4);
+        int rem = (int)(q - (long long)c0 * HW4);
+        r0 = rem / W4; x0 = rem - r0 * W4;
+        const int dC = 2 * E4;                     // from one of our chunks to the next
+        dcC = dC / HW4; rem = dC - dcC * HW4; drC = rem / W4; dxC = rem - drC * W4;
+        const int dU = kTmaGroupThreads;           // from one float4 of a chunk to the next
+        dcU = dU / HW4; rem = dU - dcU * HW4; drU = rem / W4; dxU = rem - drU * W4;
+      }
+      for (long long q0 = it.lo; q0 < it.hi; q0 += E4, ++n) {
+        const uint32_t slot = st, par = ph;
+        if (++st == kTmaStages) { st = 0; ph ^= 1; }
+        if ((n & 1u) != (uint32_t)gid) continue;
+        mbar_wait_warp(&full[slot], par, lane);
+        float4* raw = reinterpret_cast<float4*>(smem + slot * kTmaStageBytes);
+        if (kind != kStAcVec) {
+          for (int f = tid; f < E4; f += kTmaGroupThreads) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int b = 0; b < B; ++b) {
+              const float4 v = raw[b * E4 + f];
+              s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            }
+            if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
+            else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
+            const long long q = q0 + f;
+            if (q >= it.hi) continue;
+            if (kind == kStMean) *reinterpret_cast<float4*>(j.mean + q * 4) = s4;
+            else split_store4(stage + q * 4, stage + q * 4 + hl, s4.x, s4.y, s4.z, s4.w);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+          continue;
+        }
+        // ---- autocorrelation layout: means over image 0 of the stage, then the stores
+        for (int f = tid; f < E4; f += kTmaGroupThreads) {
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+          for (int b = 0; b < B; ++b) {
+            const float4 v = raw[b * E4 + f];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+          }
+          if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
+          else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
+          raw[f] = s4;
+        }
+        if (gid == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        int c = c0, r = r0, x4 = x0;
+        for (int f = tid; f < E4; f += kTmaGroupThreads, radix_add(c, r, x4, dcU, drU, dxU, H, W4)) {
+          if (q0 + f >= it.hi) break;
+          const float4 mm = raw[f];
+          const bool next_data = x4 + 1 < W4;
+          const bool in_stage = f + 1 < E4;          // the next float4's means are in `raw`
+          float2 nx = make_float2(0.f, 0.f);
+          if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(raw + f + 1);
+          const bool defer = next_data && !in_stage;
+          float h[6], l[6];
+          tf32_split(mm.x, h[0], l[0]); tf32_split(mm.y, h[1], l[1]);
+          tf32_split(mm.z, h[2], l[2]); tf32_split(mm.w, h[3], l[3]);
+          tf32_split(nx.x, h[4], l[4]); tf32_split(nx.y, h[5], l[5]);
+          float* o0 = stage + ((long long)(((c >> 7) * Hs + r) * NS + (x4 >> 3)) * 4096 +
+                               (c & 127) * 32 + (x4 & 7) * 4);
+          float* o1 = o0 + copy_stride;
+          float* o2 = o1 + copy_stride;
+          store_hl4(o0, hl, h, l, 0);
+          if (!defer) {
+            store_hl4(o1, hl, h, l, 1);
+            store_hl4(o2, hl, h, l, 2);
+          } else {
+            o1[0] = h[1]; o1[1] = h[2]; o1[2] = h[3];
+            o1[hl] = l[1]; o1[hl + 1] = l[2]; o1[hl + 2] = l[3];
+            o2[0] = h[2]; o2[1] = h[3];
+            o2[hl] = l[2]; o2[hl + 1] = l[3];
+          }
+          // the previous float4 of this row ended a stage: complete its shifted copies
+          const bool fix_prev = f == 0 && x4 > 0;
+          if (fix_prev) {
+            // one float4 to the left inside the same 32-column strip, or the last one of the
+            // previous strip
+            const long long back = (x4 & 7) ? 4 : 4096 - 28;
+            float* p1 = o1 - back;
+            float* p2 = o2 - back;
+            p1[3] = h[0]; p1[hl + 3] = l[0];
+            p2[2] = h[0]; p2[hl + 2] = l[0];
+            p2[3] = h[1]; p2[hl + 3] = l[1];
+          }
+          if (r == 0 || r == H - 1) {
+            // edge rows of the three copies, plain layout (pitch W)
+            const long long cs = (long long)C * W;
+            for (int e = 0; e < 2; ++e) {
+              if (r != (e == 0 ? H - 1 : 0)) continue;
+              float* qb = rowbuf + ((long long)(e * 3) * C + c) * W + x4 * 4;
+              store_hl4(qb, hl, h, l, 0);
+              if (!defer) {
+                store_hl4(qb + cs, hl, h, l, 1);
+                store_hl4(qb + 2 * cs, hl, h, l, 2);
+              } else {
+                float* q1 = qb + cs;
+                float* q2 = qb + 2 * cs;
+                q1[0] = h[1]; q1[1] = h[2]; q1[2] = h[3];
+                q1[hl] = l[1]; q1[hl + 1] = l[2]; q1[hl + 2] = l[3];
+                q2[0] = h[2]; q2[1] = h[3];
+                q2[hl] = l[2]; q2[hl + 1] = l[3];
+              }
+              if (fix_prev) {
+                float* q1 = qb + cs - 4;
+                float* q2 = qb + 2 * cs - 4;
+                q1[3] = h[0]; q1[hl + 3] = l[0];
+                q2[2] = h[0]; q2[hl + 2] = l[0];
+                q2[3] = h[1]; q2[hl + 3] = l[1];
+              }
+            }
+          }
+        }
+        radix_add(c0, r0, x0, dcC, drC, dxC, H, W4);
+        // the means were written through the generic proxy; the next TMA into this slot goes
+        // through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+    }
+  }
+  __syncthreads();
+  tl_end(tl);
+}
+
 // Plans one layer: the same routine choice as launch_stage_conv (x assumed 16-byte aligned;
-// the caller checks).  Appends to items[phase] when items != nullptr, always counts.
+// the caller checks).  Appends to items[list] when items != nullptr, always counts.
+// lists: [0] phase 0, register kernel; [1] phase 1 (after the batch means; also the light
+// phase-0 routines when the TMA kernel takes the heavy ones); [2] phase 0, TMA kernel
+static bool stage_tma_enabled(int B) {
+  static const bool off = [] {
+    const char* e = nsgp_env("NSGP_STAGE_TMA");     // bring-up switch
+    return e && e[0] == '0';
+  }();
+  return !off && tma_box_rows(B) > 0;
+}
+
 static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
-                           std::vector<StageItem>* items /* [2] or null */, size_t* counts) {
+                           std::vector<StageItem>* items /* [3] or null */, size_t* counts) {
   const long long img = (long long)g.C * g.H * g.W;
   const bool aligned = img % 4 == 0;
-  auto add = [&](int phase, int kind, int from_mean, long long total, long long chunk) {
+  const bool tma = stage_tma_enabled(B);
+  const bool tma_job = tma && img % 256 == 0 && !g.ftiled;
+  auto add = [&](int list, int kind, int from_mean, long long total, long long chunk) {
     for (long long lo = 0; lo < total; lo += chunk) {
-      ++counts[phase];
+      ++counts[list];
       if (items) {
         StageItem it{};
         it.job = job; it.kind = (short)kind; it.from_mean = (short)from_mean;
         it.lo = lo; it.hi = lo + chunk < total ? lo + chunk : total;
-        items[phase].push_back(it);
+        items[list].push_back(it);
       }
     }
   };
   const long long kVec = 2048, kScalar = 8192;
+  const long long kTma = 32LL * 64 * (tma ? tma_box_rows(B) : 1);    // 32 stages per item
+  const int light = tma ? 1 : 0;       // light phase-0 routines ride with phase 1 under TMA
   const bool two_pass_ok = B > 1 && aligned && have_mean;
   if (g.mode == kModeAutocorr) {
     if (aligned && g.W % 4 == 0 && (g.tiled || g.Ws == g.W + 4)) {
-      const long long n = g.tiled ? (long long)ac_cblocks(g) * 128 * g.Hs * (ac_strips(g) * 8)
-                                  : (long long)g.C * g.Hs * (g.Ws / 4);
-      add(0, kStAcVec, 0, round_up(n, 32), kVec);
+      if (tma_job && g.tiled) {
+        add(2, kStAcVec, 0, img / 4, kTma);
+      } else {
+        const long long n = g.tiled ? (long long)ac_cblocks(g) * 128 * g.Hs * (ac_strips(g) * 8)
+                                    : (long long)g.C * g.Hs * (g.Ws / 4);
+        add(0, kStAcVec, 0, round_up(n, 32), kVec);
+      }
     } else {
       const long long n = g.tiled ? 3LL * ac_cblocks(g) * 128 * g.Hs * ac_strips(g) * 32
                                   : (long long)g.C * g.Hs * g.Ws * 3;
       if (two_pass_ok) {
-        add(0, kStMean, 0, img / 4, kVec);
+        if (tma_job) add(2, kStMean, 0, img / 4, kTma); else add(0, kStMean, 0, img / 4, kVec);
         add(1, kStAcScalar, 1, n, kScalar);
       } else {
-        add(0, kStAcScalar, 0, n, kScalar);
+        add(light, kStAcScalar, 0, n, kScalar);
       }
     }
-    add(0, kStAcEdges, 0, 6LL * g.C * ac_col_pitch(g) + 16LL * g.C, kVec);
+    add(light, kStAcEdges, 0, 6LL * g.C * ac_col_pitch(g) + 16LL * g.C, kVec);
     return;
   }
   if (g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && aligned && (g.H * g.W) % 4 == 0) {
-    add(0, kStFlatVec, 0, img / 4, kVec);
+    if (tma_job) add(2, kStFlatVec, 0, img / 4, kTma); else add(0, kStFlatVec, 0, img / 4, kVec);
     return;
   }
   if (g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 &&
@@ -846,31 +1121,42 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
   }
   const bool sparse = g.mode == kModeFlat && g.sh * g.sw > 1;
   const bool two = two_pass_ok && !sparse;
-  if (two) add(0, kStMean, 0, img / 4, kVec);
+  if (two) {
+    if (tma_job) add(2, kStMean, 0, img / 4, kTma); else add(0, kStMean, 0, img / 4, kVec);
+  }
   if (g.mode == kModeExplicit)
-    add(two ? 1 : 0, kStExplicit, two ? 1 : 0, (long long)g.Cs * (g.Ws / 4), kVec);
+    add(two ? 1 : light, kStExplicit, two ? 1 : 0, (long long)g.Cs * (g.Ws / 4), kVec);
   else
-    add(two ? 1 : 0, kStConv, two ? 1 : 0, (long long)g.Cs * g.Hs * g.ncopy * (g.Ws / 4), kVec);
+    add(two ? 1 : light, kStConv, two ? 1 : 0, (long long)g.Cs * g.Hs * g.ncopy * (g.Ws / 4), kVec);
 }
 
 namespace tc { int sm_count(); }
 using tc::sm_count;
 
 size_t stage_group_bytes(const ConvGeom* geoms, int n, int B) {
-  size_t counts[2] = {0, 0};
+  size_t counts[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i) plan_stage_job(geoms[i], i, B, true, nullptr, counts);
-  return (size_t)n * sizeof(StageJobDev) + (counts[0] + counts[1]) * sizeof(StageItem) +
-         (size_t)n * sizeof(void*) + 1024;
+  return (size_t)n * sizeof(StageJobDev) + (counts[0] + counts[1] + counts[2]) * sizeof(StageItem) +
+         (size_t)n * sizeof(void*) + (size_t)n * sizeof(CUtensorMap) + 2048;
 }
+
+// input pointers last uploaded into a staging table (the upload and the tensor-map encodes
+// are skipped when a launch sees the same pointers again)
+static std::mutex g_upload_mu;
+static std::unordered_map<const void*, std::vector<const void*>> g_uploaded;
 
 int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
                       int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
                       cudaStream_t stream) {
-  NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 63) == 0,
-               "stage group table must be 64-byte aligned");
+  NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 127) == 0,
+               "stage group table must be 128-byte aligned");
+  {
+    std::lock_guard<std::mutex> lk(g_upload_mu);
+    g_uploaded.erase(table_dev);
+  }
   std::vector<StageJobDev> jobs(n);
-  std::vector<StageItem> items[2];
-  size_t counts[2] = {0, 0};
+  std::vector<StageItem> items[3];
+  size_t counts[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i) {
     const ConvGeom& g = geoms[i];
     StageJobDev& j = jobs[i];
@@ -885,7 +1171,12 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
       j.cornerbuf_off = ac_cornerbuf_off(g);
       j.Hc = ac_col_pitch(g);
     }
+    const size_t before = items[2].size();
     plan_stage_job(g, i, B, means[i] != nullptr, items, counts);
+    // the TMA autocorrelation routine writes the data words only: the padding of the tiled
+    // layout (rows H, H + 1, columns >= W, channels >= C) is zeroed here, once per table
+    if (items[2].size() > before && items[2][before].kind == kStAcVec)
+      NSGP_CHECK_CUDA(cudaMemsetAsync(stages[i], 0, stage_bytes(g), stream));
   }
   info->n_jobs = n;
   info->B = B;
@@ -896,39 +1187,105 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
     info->off_items[ph] = off;
     off = round_up((long long)(off + items[ph].size() * sizeof(StageItem)), 64);
   }
+  info->n_items_tma = (int)items[2].size();
+  info->pad = 0;
+  info->off_items_tma = off;
+  off = round_up((long long)(off + items[2].size() * sizeof(StageItem)), 64);
   info->off_xs = off;
-  off += (size_t)n * sizeof(void*);
+  off = round_up((long long)(off + (size_t)n * sizeof(void*)), 128);
+  info->off_maps = off;
+  off += (size_t)n * sizeof(CUtensorMap);
   info->bytes = off;
   NSGP_REQUIRE(off <= table_bytes, "stage group table too small (%zu < %zu)", table_bytes, off);
   char* t = (char*)table_dev;
   NSGP_CHECK_CUDA(cudaMemcpyAsync(t, jobs.data(), (size_t)n * sizeof(StageJobDev),
                                   cudaMemcpyHostToDevice, stream));
-  for (int ph = 0; ph < 2; ++ph)
+  for (int ph = 0; ph < 3; ++ph) {
+    const size_t o = ph < 2 ? info->off_items[ph] : info->off_items_tma;
     if (!items[ph].empty())
-      NSGP_CHECK_CUDA(cudaMemcpyAsync(t + info->off_items[ph], items[ph].data(),
+      NSGP_CHECK_CUDA(cudaMemcpyAsync(t + o, items[ph].data(),
                                       items[ph].size() * sizeof(StageItem),
                                       cudaMemcpyHostToDevice, stream));
+  }
   return 0;
 }
 
+// Per launch: the current input pointers and, for the TMA kernel, one 3-D tensor map per job
+// over that input (geoms: the geometries the table was built for; null: no TMA items).
 int stage_group_upload(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const ConvGeom* geoms) {
   if (info.n_jobs == 0) return 0;
   const char* t = (const char*)table_dev;
   for (int i = 0; i < info.n_jobs; ++i)
     NSGP_REQUIRE(xs[i] && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0,
                  "stage group: input %d must be a 16-byte aligned device pointer", i);
+  {
+    std::lock_guard<std::mutex> lk(g_upload_mu);
+    std::vector<const void*>& last = g_uploaded[table_dev];
+    if ((int)last.size() == info.n_jobs && std::equal(last.begin(), last.end(), xs)) return 0;
+    last.assign(xs, xs + info.n_jobs);
+  }
   NSGP_CHECK_CUDA(cudaMemcpyAsync((void*)(t + info.off_xs), xs,
                                   (size_t)info.n_jobs * sizeof(void*), cudaMemcpyHostToDevice,
                                   stream));
+  if (info.n_items_tma > 0) {
+    NSGP_REQUIRE(geoms != nullptr, "stage group: the TMA staging needs the job geometries");
+    std::vector<CUtensorMap> maps(info.n_jobs);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    const int rows = tma_box_rows(info.B);
+    for (int i = 0; i < info.n_jobs; ++i) {
+      const long long img = (long long)geoms[i].C * geoms[i].H * geoms[i].W;
+      if (img % 256 != 0) continue;               // this job has no TMA items
+      int rc = encode_batch_rows_map(&maps[i], (const float*)xs[i], img, info.B, rows);
+      if (rc) return rc;
+    }
+    NSGP_CHECK_CUDA(cudaMemcpyAsync((void*)(t + info.off_maps), maps.data(),
+                                    maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
+                                    stream));
+  }
   return 0;
 }
 
-// One phase of the grouped staging.  sms > 0: the launch is confined to `sms` SMs - every
-// block asks for kStagePartSmem bytes of (unused) dynamic shared memory, which does not fit
-// next to a resident contraction CTA (>= 225 KB), so the blocks only land on the SMs the
-// contraction grid left free; pdl: launched with the programmatic stream-serialization
-// attribute, i.e. it starts while the kernel queued before it is still running.
+// TMA-fed phase 0: one CTA per SM (its 32 KB stages fill the SM's shared memory, so no other
+// block joins it); sms > 0 confines it to that many SMs, pdl as for the other phases
+int stage_group_launch_tma(const void* table_dev, const StageGroupInfo& info, int pdl, int sms,
+                           cudaStream_t stream) {
+  if (info.n_items_tma == 0) return 0;
+  const char* t = (const char*)table_dev;
+  const size_t smem = stage_tma_smem_bytes();
+  static const bool configured = [smem] {
+    return cudaFuncSetAttribute(stage_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem) == cudaSuccess;
+  }();
+  NSGP_REQUIRE(configured, "stage_tma_kernel: %zu bytes of shared memory refused", smem);
+  ProfScope prof(kProfStage, stream);
+  int cap = sms > 0 ? sms : sm_count();
+  int grid = info.n_items_tma < cap ? info.n_items_tma : cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTmaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  NSGP_CHECK_CUDA(cudaLaunchKernelEx(
+      &cfg, stage_tma_kernel, reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
+      reinterpret_cast<const StageItem*>(t + info.off_items_tma), info.n_items_tma,
+      reinterpret_cast<const CUtensorMap*>(t + info.off_maps), info.B, tma_box_rows(info.B),
+      timeline_slot(2)));
+  NSGP_LAUNCHED();
+  return 0;
+}
+
+// One phase of the grouped staging (register kernel).  sms > 0: the launch is confined to
+// `sms` SMs - every block asks for kStagePartSmem bytes of (unused) dynamic shared memory,
+// which does not fit next to a resident contraction CTA (>= 225 KB), so the blocks only land
+// on the SMs the contraction grid left free; pdl: launched with the programmatic
+// stream-serialization attribute, i.e. it starts while the kernel queued before it is still
+// running.
 constexpr int kStagePartBlocksPerSm = 4;              // 256 threads x <= 64 registers
 constexpr size_t kStagePartSmem = 8 * 1024;
 int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, int ph, int pdl,
@@ -972,8 +1329,10 @@ int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, 
 }
 
 int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
-                       cudaStream_t stream) {
-  int rc = stage_group_upload(table_dev, info, xs, stream);
+                       cudaStream_t stream, const ConvGeom* geoms) {
+  int rc = stage_group_upload(table_dev, info, xs, stream, geoms);
+  if (rc) return rc;
+  rc = stage_group_launch_tma(table_dev, info, 0, 0, stream);
   if (rc) return rc;
   for (int ph = 0; ph < 2; ++ph) {
     rc = stage_group_launch_phase(table_dev, info, ph, 0, 0, stream);
