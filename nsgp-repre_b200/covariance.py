@@ -77,12 +77,22 @@ class CovarianceHooks:
     # i-1 runs on the others (mode="deferred", nsgp_cov_pipeline_launch): an integer, 0 = no
     # partitioning, "auto" = balanced per job set from the measured scaling of the two kernels
     stage_sms = "auto"
-    # measured on B200 (profiles/pipeline_r02.txt): slowdown of the first staging phase when it
-    # runs on S of the 148 SMs next to the sliding-window kernel, and that kernel's slowdown
-    # beyond the SM ratio from the staging traffic
-    _STAGE_SCALING = ((40, 2.09), (48, 1.75), (56, 1.48), (64, 1.37), (72, 1.30), (80, 1.23),
-                      (90, 1.17), (104, 1.10), (120, 1.04))
-    _AC_CONTENTION = 1.14
+    # Model of the two concurrent kernels of the pipelined pass, fitted on B200
+    # (profiles/pipeline_r02.txt, TMA-fed staging, B = 2 / 8 / 16 at 800x1344):
+    #   staging on S SMs      t = _STAGE_FLOOR * read + (_STAGE_READ * read + _STAGE_WRITE * write) / S
+    #                         (GB, ms; the second term is the consumer warps' work)
+    #   sliding window kernel t = t_alone * 148 / (148 - S) * (1 + _AC_CONTENTION * S)
+    _STAGE_FLOOR = 0.10          # ms per GB read
+    _STAGE_READ = 2.0            # SM ms per GB read
+    _STAGE_WRITE = 22.7          # SM ms per GB written
+    _AC_CONTENTION = 0.0019
+    # device time (ms) of the caller's own kernels per forward that should find idle SMs
+    # inside the pass (the hot path's own: SGDNSCL.step + the RePRE build, 0.45 ms): both
+    # kernels are persistent, so the caller's kernels only run on the side that finishes
+    # first; a partition that leaves no such window serialises them behind the pass (+0.7 ms
+    # measured).  A caller with much more work than fits (a detector's forward / backward)
+    # makes the penalty the same for every S, i.e. the plain balance point is chosen.
+    main_stream_ms = 0.45
 
     def __init__(self, model: nn.Module, ignore_keys=(), add_default_ignores=True,
                  mode="deferred", ring=3):
@@ -377,9 +387,8 @@ class CovarianceHooks:
         self._inflight = js
 
     def _auto_stage_sms(self, js, B):
-        """Partition that balances the two concurrent kernels of the pipelined pass: staging
-        time ~ bytes moved / 5.5 TB/s (x the measured slowdown on S SMs), sliding-window
-        time ~ issued tf32 FLOPs / 660 TFLOP/s (x 148 / (148 - S) x contention)."""
+        """Partition of the SMs between the two concurrent kernels of the pipelined pass
+        (model: class attributes above); 0 = run them back to back."""
         if js.auto_sms is not None and js.auto_sms[0] == (js.rev, B):
             return js.auto_sms[1]
         read = write = ac_flops = 0.0
@@ -397,12 +406,20 @@ class CovarianceHooks:
                 nsum = sum((13 if rb <= cb else 12) * (128 if cb < t - 1 else last)
                            for rb in range(t) for cb in range(t))
                 ac_flops += 3 * 2.0 * 128 * nsum * 32 * H * -(-W // 32)
-        t_stage = (read + write) / 5.5e12
-        t_ac = ac_flops / 680e12
-        best, best_t = 0, t_stage + t_ac                 # no partition: back to back
-        if t_ac > 0 and t_stage > 0:
-            for sms, slow in self._STAGE_SCALING:
-                t = max(t_stage * slow, t_ac * 148.0 / (148 - sms) * self._AC_CONTENTION)
+        t_ac = ac_flops / 680e9                          # ms, alone on 148 SMs
+        read, write = read / 1e9, write / 1e9
+        floor = self._STAGE_FLOOR * read
+        work = self._STAGE_READ * read + self._STAGE_WRITE * write
+        m = float(self.main_stream_ms)
+        # no partition: back to back, each on the whole GPU (no window for the caller)
+        best, best_t = 0, floor + work / 148.0 + t_ac + min(m, 0.7)
+        if t_ac > 0 and work > 0:
+            for sms in range(24, 124, 4):
+                ts = floor + work / sms
+                ta = t_ac * 148.0 / (148 - sms) * (1.0 + self._AC_CONTENTION * sms)
+                t = max(ts, ta)
+                if m > 0:
+                    t += min(m, 0.7) * max(0.0, 1.0 - abs(ts - ta) / m)
                 if t < best_t:
                     best, best_t = sms, t
         js.auto_sms = ((js.rev, B), best)

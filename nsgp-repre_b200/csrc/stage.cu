@@ -808,33 +808,45 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
 // The register routines keep their loads in flight in registers - ~128 KB per SM at most,
 // fine when all 148 SMs stage, not when the staging only gets a slice of the GPU next to the
 // sliding-window contraction.  Here ONE 3-D tensor-map box (256 floats x rows x B images,
-// <= 32 KB) brings the same chunk of all B images into shared memory and seven of them are
+// <= 32 KB) brings the same chunk of all B images into shared memory and six of them are
 // in flight per SM (scripts/tma3d_probe.py: the loads alone reach 149 GB/s per SM).
-//   warp 0        producer: cp.async.bulk.tensor.3d into a 7-stage ring, mbarrier complete_tx
-//   warps 1..16   two consumer groups of 8 warps; group g takes every other chunk: batch mean
-//                 out of shared memory, tf32 split, layout stores
+//   warp 0        producer: cp.async.bulk.tensor.3d into a 6-stage ring, mbarrier complete_tx
+//   warps 1..16   two consumer groups of 8 warps; group g takes every other chunk (= the ring
+//                 slots of parity g: the stage count is EVEN so that a group sees every lap of
+//                 its slots - a group that skipped a lap of a slot could run two mbarrier
+//                 phases ahead and pass a parity wait early): batch mean out of shared
+//                 memory, tf32 split, layout stores
 // Index space = float4s of the per-image tensor (every routine's input is contiguous).
 // Autocorrelation layout: the two column-shifted copies need the NEXT float4's first two
-// means; the means are written back over image 0 of the stage, so inside a stage they come
-// from shared memory; at a stage end the owner writes only the words it knows and the first
-// thread of the next stage (maybe in another CTA) writes the rest - disjoint words, no
-// ordering needed.  Padding of the tiled layout (rows H, H+1, columns >= W, channels >= C)
-// is zeroed once at table build.
+// means; the means go through a (double-buffered, per group) shared array, so inside a stage
+// they come from there; at a stage end the owner writes only the words it knows and the
+// first thread of the next stage (maybe in another CTA) writes the rest - disjoint words, no
+// ordering needed.  The threads that hold the first / last float4 of an image row also write
+// the edge-column and corner-pixel buffers of the boundary corrections.  Padding of the tiled
+// layout (rows H, H+1, columns >= W, channels >= C) and of those buffers is zeroed once at
+// table build.
 // ---------------------------------------------------------------------------
-constexpr int kTmaStages = 7;
+constexpr int kTmaStages = 6;                      // at most; always an even number
+constexpr int kTmaRingBytes = 192 * 1024;
+constexpr int kTmaMaxRows = 8;                     // <= 512 float4s of means per stage
 constexpr int kTmaGroupThreads = 256;
 constexpr int kTmaThreads = 32 + 2 * kTmaGroupThreads;
-constexpr int kTmaStageBytes = 32768;
-// rows of 1 KB per box (power of two): B * rows KB <= 32 KB per stage, <= 1024 float4s of
-// means per stage
+// rows of 1 KB per box: 8 / 4 rows (all 256 threads of a group busy) while the stage stays
+// <= 32 KB, else as many as fit 48 KB (B = 16: 3 rows, 192 of the 256 threads busy)
 static inline int tma_box_rows(int B) {
   if (B < 1 || B > 32) return 0;
-  int r = 1;
-  while (r * 2 * B <= 32 && r < 16) r *= 2;
-  return r;
+  if (8 * B <= 32) return 8;
+  if (4 * B <= 48) return 4;
+  return 48 / B > 0 ? 48 / B : 1;
 }
+// ring slots: as many stages as fit 192 KB, an even number (<= kTmaStages)
+static inline int tma_ring_stages(int B) {
+  const int n = kTmaRingBytes / (B * tma_box_rows(B) * 1024);
+  return n >= kTmaStages ? kTmaStages : (n & ~1);
+}
+constexpr int kTmaMeanBytes = kTmaMaxRows * 1024;    // one buffer of means
 static inline size_t stage_tma_smem_bytes() {
-  return (size_t)kTmaStages * kTmaStageBytes + 128 /* alignment slack */;
+  return (size_t)kTmaRingBytes + 4 * kTmaMeanBytes + 128 /* alignment slack */;
 }
 
 __device__ __forceinline__ void split_store1(float* hi, float* lo, float v) {
@@ -863,7 +875,7 @@ __device__ __forceinline__ void radix_add(int& c, int& r, int& x, int dc, int dr
 __global__ void __launch_bounds__(kTmaThreads, 1)
 stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restrict__ items,
                  int n_items, const CUtensorMap* __restrict__ maps, int B, int rows,
-                 unsigned long long* tl) {
+                 int n_stages, unsigned long long* tl) {
   using namespace tc;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(128) uint8_t tma_smem_raw[];
@@ -873,7 +885,7 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   tl_begin(tl);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kTmaGroupThreads / 32);
     }
@@ -881,7 +893,7 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
   }
   __syncthreads();
   const int E4 = rows * 64;                        // float4s of one image per stage
-  const uint32_t stage_tx = (uint32_t)B * rows * 1024u;
+  const uint32_t stage_tx = (uint32_t)B * rows * 1024u;      // = bytes of one ring slot
   if (warp == 0) {
     // ============================ producer ============================
     uint32_t st = 0, ph = 0;
@@ -894,12 +906,12 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
         if (lane == 0)
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-              "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem + st * kTmaStageBytes)),
+              "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem + st * stage_tx)),
               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(&full[st])), "r"(0),
               "r"((int)(q0 >> 6)), "r"(0)
               : "memory");
         __syncwarp();
-        if (++st == kTmaStages) { st = 0; ph ^= 1; }
+        if (++st == (uint32_t)n_stages) { st = 0; ph ^= 1; }
       }
     }
   } else {
@@ -909,6 +921,9 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
     const float fb = (float)B, inv = 1.f / fb;
     const bool pow2 = (B & (B - 1)) == 0;          // then x * (1/B) == x / B exactly
     uint32_t st = 0, ph = 0, n = 0;                // ring slot / phase / chunk number
+    float4* const mean_s = reinterpret_cast<float4*>(smem + kTmaRingBytes +
+                                                     gid * 2 * kTmaMeanBytes);
+    int mbuf = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const StageItem it = items[w];
       const StageJobDev& j = jobs[it.job];
@@ -921,6 +936,9 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Hs = H + 2;
       const long long copy_stride = (long long)CB * Hs * NS * 4096;
       float* const rowbuf = stage + j.rowbuf_off;
+      float* const colbuf = stage + j.colbuf_off;
+      float* const cornerbuf = stage + j.cornerbuf_off;
+      const int Hc = j.Hc;
       // coordinates (c, r, x4) of this thread's first float4 of its group's first chunk of
       // the item, by division; afterwards advanced as a mixed-radix number (the divisions
       // would be a third of the consumer's instructions)
@@ -938,10 +956,10 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       }
       for (long long q0 = it.lo; q0 < it.hi; q0 += E4, ++n) {
         const uint32_t slot = st, par = ph;
-        if (++st == kTmaStages) { st = 0; ph ^= 1; }
+        if (++st == (uint32_t)n_stages) { st = 0; ph ^= 1; }
         if ((n & 1u) != (uint32_t)gid) continue;
         mbar_wait_warp(&full[slot], par, lane);
-        float4* raw = reinterpret_cast<float4*>(smem + slot * kTmaStageBytes);
+        const float4* raw = reinterpret_cast<const float4*>(smem + slot * stage_tx);
         if (kind != kStAcVec) {
           for (int f = tid; f < E4; f += kTmaGroupThreads) {
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -961,7 +979,10 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
           if (lane == 0) mbar_arrive(&empty[slot]);
           continue;
         }
-        // ---- autocorrelation layout: means over image 0 of the stage, then the stores
+        // ---- autocorrelation layout: means into shared memory (the raw chunk is then
+        // consumed), then the stores
+        float4* ms = mean_s + mbuf * (kTmaMeanBytes / 16);
+        mbuf ^= 1;
         for (int f = tid; f < E4; f += kTmaGroupThreads) {
           float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -971,18 +992,20 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
           }
           if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
           else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
-          raw[f] = s4;
+          ms[f] = s4;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
         if (gid == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 2, 256;" ::: "memory");
         int c = c0, r = r0, x4 = x0;
         for (int f = tid; f < E4; f += kTmaGroupThreads, radix_add(c, r, x4, dcU, drU, dxU, H, W4)) {
           if (q0 + f >= it.hi) break;
-          const float4 mm = raw[f];
+          const float4 mm = ms[f];
           const bool next_data = x4 + 1 < W4;
-          const bool in_stage = f + 1 < E4;          // the next float4's means are in `raw`
+          const bool in_stage = f + 1 < E4;          // the next float4's means are in `ms`
           float2 nx = make_float2(0.f, 0.f);
-          if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(raw + f + 1);
+          if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(ms + f + 1);
           const bool defer = next_data && !in_stage;
           float h[6], l[6];
           tf32_split(mm.x, h[0], l[0]); tf32_split(mm.y, h[1], l[1]);
@@ -1014,6 +1037,25 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
             p2[2] = h[0]; p2[hl + 2] = l[0];
             p2[3] = h[1]; p2[hl + 3] = l[1];
           }
+          if (x4 == 0 || x4 == W4 - 1) {
+            // edge columns (x = W-1: side 0, x = 0: side 1) of the three row shifts and the
+            // corner pixels (layouts: stage_autocorr_edges_body); their padding is zeroed at
+            // table build like the rest of the workspace
+            for (int side = 0; side < 2; ++side) {
+              if (side == 0 ? x4 != W4 - 1 : x4 != 0) continue;
+              const float vh = side == 0 ? h[3] : h[0], vl = side == 0 ? l[3] : l[0];
+              float* cb = colbuf + ((long long)(side * 3) * C + c) * Hc + r;
+              const long long ss = (long long)C * Hc;
+              cb[0] = vh; cb[hl] = vl;
+              if (r >= 1) { cb[ss - 1] = vh; cb[ss - 1 + hl] = vl; }
+              if (r >= 2) { cb[2 * ss - 2] = vh; cb[2 * ss - 2 + hl] = vl; }
+              if (r == 0 || r == H - 1) {
+                const int q = (r == 0 ? 2 : 0) + side;
+                float* kb = cornerbuf + ((long long)q * C + c) * 4;
+                kb[0] = vh; kb[hl] = vl;
+              }
+            }
+          }
           if (r == 0 || r == H - 1) {
             // edge rows of the three copies, plain layout (pitch W)
             const long long cs = (long long)C * W;
@@ -1043,11 +1085,6 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
           }
         }
         radix_add(c0, r0, x0, dcC, drC, dxC, H, W4);
-        // the means were written through the generic proxy; the next TMA into this slot goes
-        // through the async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
       }
     }
   }
@@ -1064,7 +1101,7 @@ static bool stage_tma_enabled(int B) {
     const char* e = nsgp_env("NSGP_STAGE_TMA");     // bring-up switch
     return e && e[0] == '0';
   }();
-  return !off && tma_box_rows(B) > 0;
+  return !off && tma_box_rows(B) > 0 && tma_ring_stages(B) >= 2;
 }
 
 static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
@@ -1073,7 +1110,12 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
   const bool aligned = img % 4 == 0;
   const bool tma = stage_tma_enabled(B);
   const bool tma_job = tma && img % 256 == 0 && !g.ftiled;
+  static const int skip_kinds = [] {             // bring-up: time the phases without a routine
+    const char* e = nsgp_env("NSGP_STAGE_SKIP");
+    return e ? atoi(e) : 0;
+  }();
   auto add = [&](int list, int kind, int from_mean, long long total, long long chunk) {
+    if (skip_kinds >> kind & 1) return;
     for (long long lo = 0; lo < total; lo += chunk) {
       ++counts[list];
       if (items) {
@@ -1091,7 +1133,8 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
   if (g.mode == kModeAutocorr) {
     if (aligned && g.W % 4 == 0 && (g.tiled || g.Ws == g.W + 4)) {
       if (tma_job && g.tiled) {
-        add(2, kStAcVec, 0, img / 4, kTma);
+        add(2, kStAcVec, 0, img / 4, kTma);      // writes the edge columns and corners too
+        return;
       } else {
         const long long n = g.tiled ? (long long)ac_cblocks(g) * 128 * g.Hs * (ac_strips(g) * 8)
                                     : (long long)g.C * g.Hs * (g.Ws / 4);
@@ -1275,7 +1318,7 @@ int stage_group_launch_tma(const void* table_dev, const StageGroupInfo& info, in
       &cfg, stage_tma_kernel, reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
       reinterpret_cast<const StageItem*>(t + info.off_items_tma), info.n_items_tma,
       reinterpret_cast<const CUtensorMap*>(t + info.off_maps), info.B, tma_box_rows(info.B),
-      timeline_slot(2)));
+      tma_ring_stages(info.B), timeline_slot(2)));
   NSGP_LAUNCHED();
   return 0;
 }

@@ -230,8 +230,7 @@ def test_auto_stage_partition_balances_with_batch_size():
     import bench
     from nsgp_repre_b200 import covariance as cv
     layers = bench.trace_layers(800, 1344, bench.load_standin())
-    picks = {}
-    for B in (2, 8, 16):
+    def pick(B, main_ms):
         js = cv._JobSet()
         for r in layers:
             la = types.SimpleNamespace(layout=types.SimpleNamespace(
@@ -240,10 +239,18 @@ def test_auto_stage_partition_balances_with_batch_size():
                                         r["p"], r["p"]), None, la, None])
             js.xs.append(object())
         hooks = cv.CovarianceHooks(torch.nn.Identity())
-        picks[B] = hooks._auto_stage_sms(js, B)
-        assert js.auto_sms == ((js.rev, B), picks[B])
-    assert 0 < picks[2] < picks[8] < picks[16] <= 120
-    assert picks[8] in (64, 72)                      # measured optimum at configs[1]
+        hooks.main_stream_ms = main_ms
+        got = hooks._auto_stage_sms(js, B)
+        assert js.auto_sms == ((js.rev, B), got)
+        return got
+    # plain balance of the two kernels: more SMs for the staging as the batch grows
+    balanced = {B: pick(B, 0.0) for B in (2, 8, 16)}
+    assert 0 < balanced[2] < balanced[8] < balanced[16] <= 120
+    # a caller whose own work is far more than fits a window gets the same balance point
+    assert pick(8, 50.0) == balanced[8]
+    # the hot path's own 0.45 ms: the partition is moved off balance so that one side ends
+    # >= 0.45 ms early (measured optimum at configs[1]: 48 or 64 SMs, not 56)
+    assert pick(8, 0.45) != balanced[8] and 40 <= pick(8, 0.45) <= 72
     # nothing to overlap (no sliding-window layers): no partition
     js = cv._JobSet()
     la = types.SimpleNamespace(layout=types.SimpleNamespace(kind=0))
