@@ -696,7 +696,8 @@ def main():
     # the HBM-bound half: grouped staging (batch mean + tf32 split + layout).  Algorithmic
     # bytes = one read of every layer input; what it writes is this implementation's own
     # traffic and shows up in `traffic` only.
-    roofline_staging = {"kernel": "stage_group_kernel (layer inputs -> staged operands)",
+    roofline_staging = {"kernel": "stage_tma_kernel (TMA-fed batch mean + tf32 split + layout) + "
+                                  "stage_group_kernel (gathers from the means)",
                         "bound": "hbm", "achieved": input_bytes / (stage_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s",
                         "frac": input_bytes / (stage_ms * 1e-3) / 1e9 / hbm_peak,

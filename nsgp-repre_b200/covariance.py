@@ -79,12 +79,13 @@ class CovarianceHooks:
     stage_sms = "auto"
     # Model of the two concurrent kernels of the pipelined pass, fitted on B200
     # (profiles/pipeline_r02.txt, TMA-fed staging, B = 2 / 8 / 16 at 800x1344):
-    #   staging on S SMs      t = _STAGE_FLOOR * read + (_STAGE_READ * read + _STAGE_WRITE * write) / S
-    #                         (GB, ms; the second term is the consumer warps' work)
+    #   staging on S SMs      t = _STAGE_FLOOR[0] + _STAGE_FLOOR[1] * read
+    #                             + (_STAGE_READ * read + _STAGE_WRITE * write) / S
+    #                         (GB, ms; from ~56 SMs on the phase is HBM-bound at configs[1])
     #   sliding window kernel t = t_alone * 148 / (148 - S) * (1 + _AC_CONTENTION * S)
-    _STAGE_FLOOR = 0.10          # ms per GB read
-    _STAGE_READ = 2.0            # SM ms per GB read
-    _STAGE_WRITE = 22.7          # SM ms per GB written
+    _STAGE_FLOOR = (0.15, 0.07)  # ms, ms per GB read
+    _STAGE_READ = 4.5            # SM ms per GB read
+    _STAGE_WRITE = 15.8          # SM ms per GB written
     _AC_CONTENTION = 0.0019
     # device time (ms) of the caller's own kernels per forward that should find idle SMs
     # inside the pass (the hot path's own: SGDNSCL.step + the RePRE build, 0.45 ms): both
@@ -408,7 +409,7 @@ class CovarianceHooks:
                 ac_flops += 3 * 2.0 * 128 * nsum * 32 * H * -(-W // 32)
         t_ac = ac_flops / 680e9                          # ms, alone on 148 SMs
         read, write = read / 1e9, write / 1e9
-        floor = self._STAGE_FLOOR * read
+        floor = self._STAGE_FLOOR[0] + self._STAGE_FLOOR[1] * read
         work = self._STAGE_READ * read + self._STAGE_WRITE * write
         m = float(self.main_stream_ms)
         # no partition: back to back, each on the whole GPU (no window for the caller)

@@ -811,11 +811,14 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
 // <= 32 KB) brings the same chunk of all B images into shared memory and six of them are
 // in flight per SM (scripts/tma3d_probe.py: the loads alone reach 149 GB/s per SM).
 //   warp 0        producer: cp.async.bulk.tensor.3d into a 6-stage ring, mbarrier complete_tx
-//   warps 1..16   two consumer groups of 8 warps; group g takes every other chunk (= the ring
-//                 slots of parity g: the stage count is EVEN so that a group sees every lap of
-//                 its slots - a group that skipped a lap of a slot could run two mbarrier
-//                 phases ahead and pass a parity wait early): batch mean out of shared
-//                 memory, tf32 split, layout stores
+//   warps 1..16   kTmaGroups consumer groups; group g takes the chunks g, g + G, ... of the
+//                 CTA's chunk sequence: batch mean out of shared memory, tf32 split, layout
+//                 stores.  A group does not see every lap of a ring slot, so before the
+//                 parity wait on full[slot] it checks on empty[slot] that the slot's previous
+//                 lap was consumed - otherwise it could be two mbarrier phases ahead and pass
+//                 the parity wait early (measured: "unspecified launch failure").  Two groups
+//                 of 8 warps and four of 4 perform alike (profiles/pipeline_r02.txt): next to
+//                 the sliding-window kernel the phase is HBM-bound from ~56 SMs on.
 // Index space = float4s of the per-image tensor (every routine's input is contiguous).
 // Autocorrelation layout: the two column-shifted copies need the NEXT float4's first two
 // means; the means go through a (double-buffered, per group) shared array, so inside a stage
@@ -826,12 +829,13 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
 // layout (rows H, H+1, columns >= W, channels >= C) and of those buffers is zeroed once at
 // table build.
 // ---------------------------------------------------------------------------
-constexpr int kTmaStages = 6;                      // at most; always an even number
+constexpr int kTmaStages = 12;                     // at most
 constexpr int kTmaRingBytes = 192 * 1024;
 constexpr int kTmaMaxRows = 8;                     // <= 512 float4s of means per stage
+constexpr int kTmaGroups = 2;
 constexpr int kTmaGroupThreads = 256;
-constexpr int kTmaThreads = 32 + 2 * kTmaGroupThreads;
-// rows of 1 KB per box: 8 / 4 rows (all 256 threads of a group busy) while the stage stays
+constexpr int kTmaThreads = 32 + kTmaGroups * kTmaGroupThreads;
+// rows of 1 KB per box: 8 / 4 rows (every thread of a group busy) while the stage stays
 // <= 32 KB, else as many as fit 48 KB (B = 16: 3 rows, 192 of the 256 threads busy)
 static inline int tma_box_rows(int B) {
   if (B < 1 || B > 32) return 0;
@@ -839,21 +843,25 @@ static inline int tma_box_rows(int B) {
   if (4 * B <= 48) return 4;
   return 48 / B > 0 ? 48 / B : 1;
 }
-// ring slots: as many stages as fit 192 KB, an even number (<= kTmaStages)
+// ring slots: as many stages as fit 192 KB (<= kTmaStages)
 static inline int tma_ring_stages(int B) {
   const int n = kTmaRingBytes / (B * tma_box_rows(B) * 1024);
-  return n >= kTmaStages ? kTmaStages : (n & ~1);
+  return n >= kTmaStages ? kTmaStages : n;
 }
 constexpr int kTmaMeanBytes = kTmaMaxRows * 1024;    // one buffer of means
 static inline size_t stage_tma_smem_bytes() {
-  return (size_t)kTmaRingBytes + 4 * kTmaMeanBytes + 128 /* alignment slack */;
+  return (size_t)kTmaRingBytes + 2 * kTmaGroups * kTmaMeanBytes + 128 /* alignment slack */;
 }
 
-__device__ __forceinline__ void split_store1(float* hi, float* lo, float v) {
-  float h, l;
-  tf32_split(v, h, l);
-  *hi = h;
-  *lo = l;
+// cvt.rna.tf32.f32 is lowered to integer add + mask + an inf / NaN guard on sm_100a; the
+// staging consumers are instruction-bound, so they use the two instructions without the guard
+// (finite inputs: bit-identical; an inf stays inf, a NaN stays non-finite)
+__device__ __forceinline__ float tf32_rna_finite(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void tf32_split_finite(float x, float& hi, float& lo) {
+  hi = tf32_rna_finite(x);
+  lo = tf32_rna_finite(x - hi);
 }
 __device__ __forceinline__ void store_hl4(float* p, long long hl, const float* h, const float* l,
                                           int i) {
@@ -872,17 +880,22 @@ __device__ __forceinline__ void radix_add(int& c, int& r, int& x, int dc, int dr
   c += dc + cr;
 }
 
+// KB / KROWS > 0: batch size and box rows known at compile time (the loads get immediate
+// offsets and the batch loop is unrolled); 0: run-time values
+template <int KB, int KROWS>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restrict__ items,
-                 int n_items, const CUtensorMap* __restrict__ maps, int B, int rows,
+                 int n_items, const CUtensorMap* __restrict__ maps, int B_rt, int rows_rt,
                  int n_stages, unsigned long long* tl) {
   using namespace tc;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(128) uint8_t tma_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(tma_smem_raw) + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start of the ring (pointer arithmetic on the shared array itself, so
+  // that the accesses stay LDS / STS instead of generic loads)
+  uint8_t* const smem = tma_smem_raw + ((128u - (smem_u32(tma_smem_raw) & 127u)) & 127u);
   __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = KB > 0 ? KB : B_rt, rows = KROWS > 0 ? KROWS : rows_rt;
   tl_begin(tl);
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -920,17 +933,78 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
     const int tid = (threadIdx.x - 32) % kTmaGroupThreads;
     const float fb = (float)B, inv = 1.f / fb;
     const bool pow2 = (B & (B - 1)) == 0;          // then x * (1/B) == x / B exactly
-    uint32_t st = 0, ph = 0, n = 0;                // ring slot / phase / chunk number
+    // ring slot / lap of the group's next chunk (chunk gid of the CTA's chunk sequence)
+    uint32_t st = gid % n_stages, lap = gid / n_stages;
+    uint32_t n = 0;                                // chunks of the CTA before the current item
+    auto wait_chunk = [&]() {
+      if (lap > 0) mbar_wait_warp(&empty[st], (lap - 1) & 1, lane);   // previous lap consumed
+      mbar_wait_warp(&full[st], lap & 1, lane);
+    };
+    auto next_chunk = [&]() {
+      st += kTmaGroups;
+      while (st >= (uint32_t)n_stages) { st -= n_stages; ++lap; }
+    };
     float4* const mean_s = reinterpret_cast<float4*>(smem + kTmaRingBytes +
                                                      gid * 2 * kTmaMeanBytes);
     int mbuf = 0;
+    // batch mean of float4 f of the chunk in `raw`
+    auto mean4 = [&](const float4* raw, int f) {
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (KB > 0) {
+#pragma unroll
+        for (int b = 0; b < (KB > 0 ? KB : 1); ++b) {
+          const float4 v = raw[b * E4 + f];
+          s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+      } else {
+        const float4* p = raw + f;
+#pragma unroll 4
+        for (int b = 0; b < B; ++b, p += E4) {
+          const float4 v = *p;
+          s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+      }
+      if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
+      else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
+      return s4;
+    };
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const StageItem it = items[w];
       const StageJobDev& j = jobs[it.job];
       const int kind = it.kind;
       const long long hl = j.hl;
       float* const stage = j.stage;
-      // autocorrelation geometry (tiled layout; W % 4 == 0)
+      const int n_chunks = (int)((it.hi - it.lo + E4 - 1) / E4);
+      static_assert((kTmaGroups & (kTmaGroups - 1)) == 0 && kTmaGroups <= 4, "2 or 4 groups");
+      const int k0 = (int)((gid - n) & (kTmaGroups - 1));   // first chunk of the item that is ours
+      n += n_chunks;
+      if (kind != kStAcVec) {
+        float* const dst = kind == kStMean ? j.mean : stage;
+        for (int k = k0; k < n_chunks; k += kTmaGroups) {
+          const long long q0 = it.lo + (long long)k * E4;
+          wait_chunk();
+          const float4* raw = reinterpret_cast<const float4*>(smem + st * stage_tx);
+          for (int f = tid; f < E4; f += kTmaGroupThreads) {
+            const float4 m = mean4(raw, f);
+            const long long q = q0 + f;
+            if (q >= it.hi) continue;
+            if (kind == kStMean) {
+              *reinterpret_cast<float4*>(dst + q * 4) = m;
+            } else {
+              float4 h, l;
+              tf32_split_finite(m.x, h.x, l.x); tf32_split_finite(m.y, h.y, l.y);
+              tf32_split_finite(m.z, h.z, l.z); tf32_split_finite(m.w, h.w, l.w);
+              *reinterpret_cast<float4*>(dst + q * 4) = h;
+              *reinterpret_cast<float4*>(dst + q * 4 + hl) = l;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          next_chunk();
+        }
+        continue;
+      }
+      // ---- autocorrelation layout (tiled; W % 4 == 0)
       const int H = j.g.H, W = j.g.W, C = j.g.C;
       const int W4 = W >> 2, HW4 = H * W4;
       const int CB = (C + 127) >> 7, NS = (W + 31) >> 5, Hs = H + 2;
@@ -939,65 +1013,37 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       float* const colbuf = stage + j.colbuf_off;
       float* const cornerbuf = stage + j.cornerbuf_off;
       const int Hc = j.Hc;
-      // coordinates (c, r, x4) of this thread's first float4 of its group's first chunk of
+      // coordinates (c, r, x4) of this thread's first float4 of the group's first chunk of
       // the item, by division; afterwards advanced as a mixed-radix number (the divisions
       // would be a third of the consumer's instructions)
-      const int k0 = (int)((gid - n) & 1u);        // first chunk of the item that is ours
-      int c0 = 0, r0 = 0, x0 = 0, dcC = 0, drC = 0, dxC = 0, dcU = 0, drU = 0, dxU = 0;
-      if (kind == kStAcVec) {
+      int c0, r0, x0, dcC, drC, dxC, dcU, drU, dxU;
+      {
         const long long q = it.lo + (long long)k0 * E4 + tid;
         c0 = (int)(q / HW4);
         int rem = (int)(q - (long long)c0 * HW4);
         r0 = rem / W4; x0 = rem - r0 * W4;
-        const int dC = 2 * E4;                     // from one of our chunks to the next
+        const int dC = kTmaGroups * E4;            // from one of our chunks to the next
         dcC = dC / HW4; rem = dC - dcC * HW4; drC = rem / W4; dxC = rem - drC * W4;
         const int dU = kTmaGroupThreads;           // from one float4 of a chunk to the next
         dcU = dU / HW4; rem = dU - dcU * HW4; drU = rem / W4; dxU = rem - drU * W4;
       }
-      for (long long q0 = it.lo; q0 < it.hi; q0 += E4, ++n) {
-        const uint32_t slot = st, par = ph;
-        if (++st == (uint32_t)n_stages) { st = 0; ph ^= 1; }
-        if ((n & 1u) != (uint32_t)gid) continue;
-        mbar_wait_warp(&full[slot], par, lane);
-        const float4* raw = reinterpret_cast<const float4*>(smem + slot * stage_tx);
-        if (kind != kStAcVec) {
-          for (int f = tid; f < E4; f += kTmaGroupThreads) {
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-            for (int b = 0; b < B; ++b) {
-              const float4 v = raw[b * E4 + f];
-              s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
-            }
-            if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
-            else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
-            const long long q = q0 + f;
-            if (q >= it.hi) continue;
-            if (kind == kStMean) *reinterpret_cast<float4*>(j.mean + q * 4) = s4;
-            else split_store4(stage + q * 4, stage + q * 4 + hl, s4.x, s4.y, s4.z, s4.w);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[slot]);
-          continue;
-        }
-        // ---- autocorrelation layout: means into shared memory (the raw chunk is then
-        // consumed), then the stores
+      for (int k = k0; k < n_chunks; k += kTmaGroups) {
+        const long long q0 = it.lo + (long long)k * E4;
+        wait_chunk();
+        const float4* raw = reinterpret_cast<const float4*>(smem + st * stage_tx);
+        // means into shared memory (the raw chunk is then consumed), then the stores
         float4* ms = mean_s + mbuf * (kTmaMeanBytes / 16);
         mbuf ^= 1;
-        for (int f = tid; f < E4; f += kTmaGroupThreads) {
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-          for (int b = 0; b < B; ++b) {
-            const float4 v = raw[b * E4 + f];
-            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
-          }
-          if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
-          else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
-          ms[f] = s4;
-        }
+        for (int f = tid; f < E4; f += kTmaGroupThreads) ms[f] = mean4(raw, f);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
-        if (gid == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (lane == 0) mbar_arrive(&empty[st]);
+        next_chunk();
+        switch (gid) {                               // the group's own named barrier
+          case 0: asm volatile("bar.sync 1, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+          case 1: asm volatile("bar.sync 2, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+          case 2: asm volatile("bar.sync 3, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+          default: asm volatile("bar.sync 4, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+        }
         int c = c0, r = r0, x4 = x0;
         for (int f = tid; f < E4; f += kTmaGroupThreads, radix_add(c, r, x4, dcU, drU, dxU, H, W4)) {
           if (q0 + f >= it.hi) break;
@@ -1008,9 +1054,9 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
           if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(ms + f + 1);
           const bool defer = next_data && !in_stage;
           float h[6], l[6];
-          tf32_split(mm.x, h[0], l[0]); tf32_split(mm.y, h[1], l[1]);
-          tf32_split(mm.z, h[2], l[2]); tf32_split(mm.w, h[3], l[3]);
-          tf32_split(nx.x, h[4], l[4]); tf32_split(nx.y, h[5], l[5]);
+          tf32_split_finite(mm.x, h[0], l[0]); tf32_split_finite(mm.y, h[1], l[1]);
+          tf32_split_finite(mm.z, h[2], l[2]); tf32_split_finite(mm.w, h[3], l[3]);
+          tf32_split_finite(nx.x, h[4], l[4]); tf32_split_finite(nx.y, h[5], l[5]);
           float* o0 = stage + ((long long)(((c >> 7) * Hs + r) * NS + (x4 >> 3)) * 4096 +
                                (c & 127) * 32 + (x4 & 7) * 4);
           float* o1 = o0 + copy_stride;
@@ -1037,26 +1083,29 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
             p2[2] = h[0]; p2[hl + 2] = l[0];
             p2[3] = h[1]; p2[hl + 3] = l[1];
           }
-          if (x4 == 0 || x4 == W4 - 1) {
+          const bool first_x = x4 == 0, last_x = x4 == W4 - 1;
+          const bool edge_row = r == 0 || r == H - 1;
+          if (!(first_x || last_x || edge_row)) continue;
+          if (first_x || last_x) {
             // edge columns (x = W-1: side 0, x = 0: side 1) of the three row shifts and the
             // corner pixels (layouts: stage_autocorr_edges_body); their padding is zeroed at
             // table build like the rest of the workspace
             for (int side = 0; side < 2; ++side) {
-              if (side == 0 ? x4 != W4 - 1 : x4 != 0) continue;
+              if (side == 0 ? !last_x : !first_x) continue;
               const float vh = side == 0 ? h[3] : h[0], vl = side == 0 ? l[3] : l[0];
               float* cb = colbuf + ((long long)(side * 3) * C + c) * Hc + r;
               const long long ss = (long long)C * Hc;
               cb[0] = vh; cb[hl] = vl;
               if (r >= 1) { cb[ss - 1] = vh; cb[ss - 1 + hl] = vl; }
               if (r >= 2) { cb[2 * ss - 2] = vh; cb[2 * ss - 2 + hl] = vl; }
-              if (r == 0 || r == H - 1) {
+              if (edge_row) {
                 const int q = (r == 0 ? 2 : 0) + side;
                 float* kb = cornerbuf + ((long long)q * C + c) * 4;
                 kb[0] = vh; kb[hl] = vl;
               }
             }
           }
-          if (r == 0 || r == H - 1) {
+          if (edge_row) {
             // edge rows of the three copies, plain layout (pitch W)
             const long long cs = (long long)C * W;
             for (int e = 0; e < 2; ++e) {
@@ -1101,7 +1150,7 @@ static bool stage_tma_enabled(int B) {
     const char* e = nsgp_env("NSGP_STAGE_TMA");     // bring-up switch
     return e && e[0] == '0';
   }();
-  return !off && tma_box_rows(B) > 0 && tma_ring_stages(B) >= 2;
+  return !off && tma_box_rows(B) > 0 && tma_ring_stages(B) >= kTmaGroups;
 }
 
 static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
@@ -1296,9 +1345,23 @@ int stage_group_launch_tma(const void* table_dev, const StageGroupInfo& info, in
   if (info.n_items_tma == 0) return 0;
   const char* t = (const char*)table_dev;
   const size_t smem = stage_tma_smem_bytes();
+  const int B = info.B, rows = tma_box_rows(B);
+  using Kernel = void (*)(const StageJobDev*, const StageItem*, int, const CUtensorMap*, int, int,
+                          int, unsigned long long*);
+  Kernel kernel = stage_tma_kernel<0, 0>;
+  if (B == 8 && rows == 4) kernel = stage_tma_kernel<8, 4>;
+  else if (B == 16 && rows == 3) kernel = stage_tma_kernel<16, 3>;
+  else if (B == 4 && rows == 8) kernel = stage_tma_kernel<4, 8>;
+  else if (B == 2 && rows == 8) kernel = stage_tma_kernel<2, 8>;
+  else if (B == 1 && rows == 8) kernel = stage_tma_kernel<1, 8>;
   static const bool configured = [smem] {
-    return cudaFuncSetAttribute(stage_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem) == cudaSuccess;
+    bool ok = true;
+    for (Kernel k : {(Kernel)stage_tma_kernel<0, 0>, (Kernel)stage_tma_kernel<8, 4>,
+                     (Kernel)stage_tma_kernel<16, 3>, (Kernel)stage_tma_kernel<4, 8>,
+                     (Kernel)stage_tma_kernel<2, 8>, (Kernel)stage_tma_kernel<1, 8>})
+      ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem) == cudaSuccess;
+    return ok;
   }();
   NSGP_REQUIRE(configured, "stage_tma_kernel: %zu bytes of shared memory refused", smem);
   ProfScope prof(kProfStage, stream);
@@ -1315,10 +1378,10 @@ int stage_group_launch_tma(const void* table_dev, const StageGroupInfo& info, in
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   NSGP_CHECK_CUDA(cudaLaunchKernelEx(
-      &cfg, stage_tma_kernel, reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
+      &cfg, kernel, reinterpret_cast<const StageJobDev*>(t + info.off_jobs),
       reinterpret_cast<const StageItem*>(t + info.off_items_tma), info.n_items_tma,
-      reinterpret_cast<const CUtensorMap*>(t + info.off_maps), info.B, tma_box_rows(info.B),
-      tma_ring_stages(info.B), timeline_slot(2)));
+      reinterpret_cast<const CUtensorMap*>(t + info.off_maps), B, rows,
+      tma_ring_stages(B), timeline_slot(2)));
   NSGP_LAUNCHED();
   return 0;
 }

@@ -47,10 +47,16 @@ def biggest(pred, n):
     return c[:n]
 
 
+# phase 0 = the TMA-fed kernel (stage_tma_kernel) when the capture has it, else the largest
+# stage_group_kernel launch; phase 1 = the largest stage_group_kernel launch that is not phase 0
+tma = biggest(lambda k: "stage_tma_kernel" in k, 1)
 stage = biggest(lambda k: "stage_group_kernel" in k, 4)
-# phase 0 and phase 1 alternate: take the largest phase-0 and the largest phase-1 launch
-ph0 = stage[0]
-ph1 = next((r for r in stage if gb(r) < 0.5 * gb(ph0)), None)
+if tma:
+    ph0 = tma[0]
+    ph1 = stage[0] if stage else None
+else:
+    ph0 = stage[0]
+    ph1 = next((r for r in stage if gb(r) < 0.5 * gb(ph0)), None)
 gen = biggest(lambda k: "contraction_tc_kernel" in k, 1)[0]
 ac = biggest(lambda k: "autocorr_tc_kernel" in k, 1)[0]
 traffic = {
