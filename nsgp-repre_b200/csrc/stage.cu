@@ -1407,12 +1407,13 @@ int stage_group_launch_phase(const void* table_dev, const StageGroupInfo& info, 
   (void)carve_once;
   const char* t = (const char*)table_dev;
   ProfScope prof(kProfStage, stream);
-  // blocks per SM: few enough that the persistent contraction CTA (224 threads, ~16 K
-  // registers) of the previous forward always finds room next to them
+  // blocks per SM: 4 x 256 threads x 64 registers fill the register file (the gather
+  // routines are latency-bound: phase 1 0.58 -> 0.53 ms from 3 to 4 blocks; issuing the loads
+  // of two positions per iteration was measured too: spills, 0.58 ms)
   static const int per_sm = [] {
     const char* e = nsgp_env("NSGP_STAGE_BLOCKS_PER_SM");
-    const int v = e ? atoi(e) : 3;
-    return v > 0 && v <= 8 ? v : 3;
+    const int v = e ? atoi(e) : 4;
+    return v > 0 && v <= 8 ? v : 4;
   }();
   int cap = sms > 0 ? sms * kStagePartBlocksPerSm : sm_count() * per_sm;
   int grid = info.n_items[ph] < cap ? info.n_items[ph] : cap;

@@ -185,6 +185,58 @@ def test_covariance_full_size_full_matrix(pkg, name, Cin, H, W, k, s, p, B):
     assert worst < 1e-4, worst
 
 
+# ------------------------------------------------------------------ TMA-fed staging, any batch
+class _FourLayouts(torch.nn.Module):
+    """One forward hooks the four staging routines the TMA kernel feeds: sliding-window 3x3
+    (tile-major copies + edge rows / columns / corners), flat 1x1, and the batch mean of the
+    gather layouts (3x3 stride 2, 7x7 stem)."""
+    def __init__(self):
+        super().__init__()
+        self.stem = torch.nn.Conv2d(4, 8, 7, stride=2, padding=3, bias=False)
+        self.c3 = torch.nn.Conv2d(64, 8, 3, padding=1, bias=False)
+        self.c1 = torch.nn.Conv2d(64, 8, 1, bias=False)
+        self.s2 = torch.nn.Conv2d(64, 8, 3, stride=2, padding=1, bias=False)
+        self.d2 = torch.nn.Conv2d(64, 8, 1, stride=2, bias=False)
+
+    def forward(self, img, x):
+        return self.stem(img), self.c3(x), self.c1(x), self.s2(x), self.d2(x)
+
+
+@pytest.mark.parametrize("stage_sms", ["auto", 40])
+@pytest.mark.parametrize("B", [1, 2, 3, 5, 8, 12, 16, 24, 32, 33])
+def test_covariance_every_batch_size_through_the_staging_ring(pkg, B, stage_sms):
+    """The TMA-fed staging kernel changes its box (rows per stage), ring depth and template
+    instance with the batch size (1-32; 33 falls back to the register kernel); every variant
+    against the oracle, pipelined over three forwards with and without a forced partition.
+    Extents: image sizes that are multiples of 256 floats, W = 20 (five float4s per row, so
+    chunks end inside rows and the stage-end fix-ups of the shifted copies run)."""
+    g = torch.Generator(device="cuda").manual_seed(100 + B)
+    img = torch.relu(torch.randn(B, 4, 32, 64, device="cuda", generator=g))
+    x = torch.relu(torch.randn(B, 64, 16, 20, device="cuda", generator=g))
+    model = _FourLayouts().cuda()
+    old = pkg.CovarianceHooks.stage_sms
+    pkg.CovarianceHooks.stage_sms = stage_sms
+    try:
+        hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+        with torch.no_grad():
+            for _ in range(3):
+                model(img, x)
+        hooks.remove()
+        fea = hooks.fea_in
+    finally:
+        pkg.CovarianceHooks.stage_sms = old
+    want = {"stem": O.cov_conv2d(img.double(), (7, 7), (2, 2), (3, 3)),
+            "c3": O.cov_conv2d(x.double(), (3, 3), (1, 1), (1, 1)),
+            "c1": O.cov_conv2d(x.double(), (1, 1), (1, 1), (0, 0)),
+            "s2": O.cov_conv2d(x.double(), (3, 3), (2, 2), (1, 1)),
+            "d2": O.cov_conv2d(x.double(), (1, 1), (2, 2), (0, 0))}
+    for k, w in want.items():
+        got = fea[k + ".weight"].double()
+        assert got.shape == w.shape
+        worst = float((got - 3.0 * w).abs().max() / (3.0 * w).abs().max())
+        assert worst < 1e-4, (k, B, worst)
+
+
 # ------------------------------------------------------------------ one key, several extents
 def test_covariance_shared_module_five_levels_one_key(pkg):
     """rpn_head.rpn_conv / rpn_cls are applied to the five FPN levels: five hook calls at
