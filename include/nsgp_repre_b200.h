@@ -222,8 +222,14 @@ typedef struct {
   size_t off_items_tma, off_maps;  /* ... and one 3-D tensor map per job, re-encoded per launch */
 } nsgp_stage_group_t;
 size_t nsgp_cov_stage_group_bytes(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B);
+/* same_input (host, n_jobs entries, or NULL): same_input[i] = k >= 0 promises that job i is
+ * given the SAME tensor as job k at every launch of this table (else -1).  Used for a 1x1
+ * stride-2 conv next to a 1x1 stride-1 conv on one tensor (ResNet: layerN.0.downsample.0 /
+ * layerN.0.conv1): its staged operand is written along with the other's, the input is read
+ * once. */
 int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs /* host */, int n_jobs, int B,
-                               void* table_dev /* 64-byte aligned */, size_t table_bytes,
+                               const int* same_input /* host or NULL */,
+                               void* table_dev /* 128-byte aligned */, size_t table_bytes,
                                nsgp_stage_group_t* out /* host */, void* stream);
 int nsgp_cov_stage_group_launch(void* table_dev, const nsgp_stage_group_t* sg /* host */,
                                 const nsgp_cov_job_t* jobs /* host: as given to the build */,

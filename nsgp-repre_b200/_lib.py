@@ -102,7 +102,8 @@ SIGNATURES = {
     "nsgp_cov_group_build": (c_int, [C.POINTER(CovJob), c_int, c_void_p, c_size_t,
                                      C.POINTER(Group), c_void_p]),
     "nsgp_cov_stage_group_bytes": (c_size_t, [C.POINTER(CovJob), c_int, c_int]),
-    "nsgp_cov_stage_group_build": (c_int, [C.POINTER(CovJob), c_int, c_int, c_void_p, c_size_t,
+    "nsgp_cov_stage_group_build": (c_int, [C.POINTER(CovJob), c_int, c_int, C.POINTER(c_int),
+                                           c_void_p, c_size_t,
                                            C.POINTER(StageGroup), c_void_p]),
     "nsgp_cov_stage_group_launch": (c_int, [c_void_p, C.POINTER(StageGroup), C.POINTER(CovJob),
                                             C.POINTER(c_void_p), c_void_p]),

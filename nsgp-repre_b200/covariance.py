@@ -347,7 +347,20 @@ class CovarianceHooks:
             self._inflight = js
             return
         B = Bs.pop()
-        sig = (js.rev, B)
+        # jobs that read one tensor with different geometries (layerN.0.conv1 and
+        # layerN.0.downsample.0 of a ResNet): the library stages a 1x1 stride-2 operand along
+        # with the 1x1 stride-1 one.  Part of the table's signature: the promise is checked
+        # against the tensors of every forward.
+        source = {}                                  # tensor -> its 1x1 stride-1 reader
+        for k, i in enumerate(uniq):
+            if js.jobs[i][1][3:] == (1, 1, 1, 1, 0, 0):
+                source.setdefault((js.xs[i].data_ptr(), tuple(js.xs[i].shape)), k)
+        same = []
+        for k, i in enumerate(uniq):
+            src = source.get((js.xs[i].data_ptr(), tuple(js.xs[i].shape)), -1)
+            same.append(src if src != k else -1)
+        same = tuple(same)
+        sig = (js.rev, B, same)
         if js.stage_sig != sig:
             n = len(uniq)
             arr = (CovJob * n)()
@@ -365,7 +378,8 @@ class CovarianceHooks:
                     js.stage_table.device != dev:
                 js.stage_table = torch.empty(need, dtype=torch.uint8, device=dev)
             js.stage_group = StageGroup()
-            check(lib.nsgp_cov_stage_group_build(arr, n, B, ptr(js.stage_table),
+            same_arr = (ctypes.c_int * n)(*same)
+            check(lib.nsgp_cov_stage_group_build(arr, n, B, same_arr, ptr(js.stage_table),
                                                  js.stage_table.numel(),
                                                  ctypes.byref(js.stage_group),
                                                  side.cuda_stream),

@@ -686,8 +686,9 @@ size_t nsgp_cov_stage_group_bytes(const nsgp_cov_job_t* jobs, int n_jobs, int B)
   return stage_group_bytes(geoms.data(), n_jobs, B) + 256;
 }
 
-int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs, int n_jobs, int B, void* table_dev,
-                               size_t table_bytes, nsgp_stage_group_t* out, void* stream_) {
+int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs, int n_jobs, int B,
+                               const int* same_input, void* table_dev, size_t table_bytes,
+                               nsgp_stage_group_t* out, void* stream_) {
   NSGP_REQUIRE(jobs && table_dev && out && n_jobs > 0 && B > 0,
                "cov_stage_group_build: bad arguments");
   std::vector<ConvGeom> geoms;
@@ -696,8 +697,8 @@ int nsgp_cov_stage_group_build(const nsgp_cov_job_t* jobs, int n_jobs, int B, vo
   if (rc) return rc;
   for (int i = 0; i < n_jobs; ++i) means.push_back(job_mean_scratch(jobs[i], geoms[i], stages[i]));
   StageGroupInfo gi{};
-  rc = stage_group_build(geoms.data(), stages.data(), means.data(), n_jobs, B, table_dev,
-                         table_bytes, &gi, (cudaStream_t)stream_);
+  rc = stage_group_build(geoms.data(), stages.data(), means.data(), n_jobs, B, same_input,
+                         table_dev, table_bytes, &gi, (cudaStream_t)stream_);
   if (rc) return rc;
   out->n_jobs = gi.n_jobs; out->B = gi.B;
   out->n_items[0] = gi.n_items[0]; out->n_items[1] = gi.n_items[1];

@@ -296,7 +296,8 @@ static inline size_t mean_scratch_elems(const ConvGeom& g) {
 }
 // grouped staging (stage.cu): all layer inputs of a forward in one or two launches
 enum StageKind : int {
-  kStFlatVec = 0, kStAcVec, kStAcEdges, kStMean, kStConv, kStExplicit, kStAcScalar, kSt3x3Vec
+  kStFlatVec = 0, kStAcVec, kStAcEdges, kStMean, kStConv, kStExplicit, kStAcScalar, kSt3x3Vec,
+  kStFlatSub     // kStFlatVec that also writes the stride-2 subsample of a 1x1 s2 job on the same input
 };
 struct alignas(16) StageJobDev {
   ConvGeom g;
@@ -305,6 +306,11 @@ struct alignas(16) StageJobDev {
   long long hl;
   long long rowbuf_off, colbuf_off, cornerbuf_off;
   int Hc, pad;
+  // kStFlatSub: staged operand of the 1x1 stride-2 job that reads the same tensor (row pitch
+  // sub_pitch, sub_wout = W / 2 output columns per output row)
+  float* sub_stage;
+  long long sub_hl;
+  int sub_pitch, sub_wout;
 };
 struct alignas(16) StageItem {
   int job;
@@ -322,9 +328,11 @@ struct StageGroupInfo {
   size_t off_items_tma, off_maps;
 };
 size_t stage_group_bytes(const ConvGeom* geoms, int n, int B);
+// same_input (n entries or null): same_input[i] = k >= 0 when job i is given the same tensor as
+// job k at every launch
 int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
-                      int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
-                      cudaStream_t stream);
+                      int B, const int* same_input, void* table_dev, size_t table_bytes,
+                      StageGroupInfo* info, cudaStream_t stream);
 int stage_group_launch(const void* table_dev, const StageGroupInfo& info, const void* const* xs,
                        cudaStream_t stream, const ConvGeom* geoms = nullptr);
 int stage_group_upload(const void* table_dev, const StageGroupInfo& info, const void* const* xs,

@@ -978,6 +978,52 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       static_assert((kTmaGroups & (kTmaGroups - 1)) == 0 && kTmaGroups <= 4, "2 or 4 groups");
       const int k0 = (int)((gid - n) & (kTmaGroups - 1));   // first chunk of the item that is ours
       n += n_chunks;
+      if (kind == kStFlatSub) {
+        // flat 1x1 staging + the stride-2 subsample for the 1x1 s2 job on the same tensor:
+        // even rows, elements .x / .z of every float4 (W % 4 == 0)
+        const int H = j.g.H, W4 = j.g.W >> 2, HW4 = H * W4;
+        float* const sub = j.sub_stage;
+        const long long sub_hl = j.sub_hl;
+        const int sub_pitch = j.sub_pitch, sub_wout = j.sub_wout;
+        int c0, r0, x0, dcC, drC, dxC, dcU, drU, dxU;
+        {
+          const long long q = it.lo + (long long)k0 * E4 + tid;
+          c0 = (int)(q / HW4);
+          int rem = (int)(q - (long long)c0 * HW4);
+          r0 = rem / W4; x0 = rem - r0 * W4;
+          const int dC = kTmaGroups * E4;
+          dcC = dC / HW4; rem = dC - dcC * HW4; drC = rem / W4; dxC = rem - drC * W4;
+          const int dU = kTmaGroupThreads;
+          dcU = dU / HW4; rem = dU - dcU * HW4; drU = rem / W4; dxU = rem - drU * W4;
+        }
+        for (int k = k0; k < n_chunks; k += kTmaGroups) {
+          const long long q0 = it.lo + (long long)k * E4;
+          wait_chunk();
+          const float4* raw = reinterpret_cast<const float4*>(smem + st * stage_tx);
+          int c = c0, r = r0, x4 = x0;
+          for (int f = tid; f < E4;
+               f += kTmaGroupThreads, radix_add(c, r, x4, dcU, drU, dxU, H, W4)) {
+            const float4 m = mean4(raw, f);
+            const long long q = q0 + f;
+            if (q >= it.hi) continue;
+            float4 h, l;
+            tf32_split_finite(m.x, h.x, l.x); tf32_split_finite(m.y, h.y, l.y);
+            tf32_split_finite(m.z, h.z, l.z); tf32_split_finite(m.w, h.w, l.w);
+            *reinterpret_cast<float4*>(stage + q * 4) = h;
+            *reinterpret_cast<float4*>(stage + q * 4 + hl) = l;
+            if ((r & 1) == 0) {
+              float* o = sub + (long long)c * sub_pitch + (r >> 1) * sub_wout + 2 * x4;
+              *reinterpret_cast<float2*>(o) = make_float2(h.x, h.z);
+              *reinterpret_cast<float2*>(o + sub_hl) = make_float2(l.x, l.z);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          next_chunk();
+          radix_add(c0, r0, x0, dcC, drC, dxC, H, W4);
+        }
+        continue;
+      }
       if (kind != kStAcVec) {
         float* const dst = kind == kStMean ? j.mean : stage;
         for (int k = k0; k < n_chunks; k += kTmaGroups) {
@@ -1153,8 +1199,13 @@ static bool stage_tma_enabled(int B) {
   return !off && tma_box_rows(B) > 0 && tma_ring_stages(B) >= kTmaGroups;
 }
 
+// role: 0 = plain; 1 = this flat 1x1 job also writes the stride-2 subsample of a sibling job
+// (kStFlatSub); 2 = this job is that sibling (no items of its own)
+static bool stage_sub_pair_ok(const ConvGeom& sub, const ConvGeom& full, int B);
 static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
-                           std::vector<StageItem>* items /* [3] or null */, size_t* counts) {
+                           std::vector<StageItem>* items /* [3] or null */, size_t* counts,
+                           int role = 0) {
+  if (role == 2) return;
   const long long img = (long long)g.C * g.H * g.W;
   const bool aligned = img % 4 == 0;
   const bool tma = stage_tma_enabled(B);
@@ -1203,7 +1254,8 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
     return;
   }
   if (g.mode == kModeFlat && g.sh == 1 && g.sw == 1 && aligned && (g.H * g.W) % 4 == 0) {
-    if (tma_job) add(2, kStFlatVec, 0, img / 4, kTma); else add(0, kStFlatVec, 0, img / 4, kVec);
+    if (tma_job) add(2, role == 1 ? kStFlatSub : kStFlatVec, 0, img / 4, kTma);
+    else add(0, kStFlatVec, 0, img / 4, kVec);
     return;
   }
   if (g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 &&
@@ -1225,6 +1277,17 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
 namespace tc { int sm_count(); }
 using tc::sm_count;
 
+// a 1x1 stride-2 conv (`sub`) and a 1x1 stride-1 conv (`full`) on the same tensor: the staged
+// operand of the first is every other row / column of the staged operand of the second, so
+// the TMA consumer that stages `full` writes it along (no second read of the input)
+static bool stage_sub_pair_ok(const ConvGeom& sub, const ConvGeom& full, int B) {
+  const long long img = (long long)full.C * full.H * full.W;
+  return stage_tma_enabled(B) && img % 256 == 0 && full.W % 4 == 0 && !full.ftiled &&
+         !sub.ftiled && full.mode == kModeFlat && sub.mode == kModeFlat && full.sh == 1 &&
+         full.sw == 1 && sub.sh == 2 && sub.sw == 2 && sub.C == full.C && sub.H == full.H &&
+         sub.W == full.W && sub.Wout * 2 == full.W;
+}
+
 size_t stage_group_bytes(const ConvGeom* geoms, int n, int B) {
   size_t counts[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i) plan_stage_job(geoms[i], i, B, true, nullptr, counts);
@@ -1238,8 +1301,8 @@ static std::mutex g_upload_mu;
 static std::unordered_map<const void*, std::vector<const void*>> g_uploaded;
 
 int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const* means, int n,
-                      int B, void* table_dev, size_t table_bytes, StageGroupInfo* info,
-                      cudaStream_t stream) {
+                      int B, const int* same_input, void* table_dev, size_t table_bytes,
+                      StageGroupInfo* info, cudaStream_t stream) {
   NSGP_REQUIRE((reinterpret_cast<uintptr_t>(table_dev) & 127) == 0,
                "stage group table must be 128-byte aligned");
   {
@@ -1249,6 +1312,13 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
   std::vector<StageJobDev> jobs(n);
   std::vector<StageItem> items[3];
   size_t counts[3] = {0, 0, 0};
+  // pairs (1x1 s2 job, 1x1 s1 job on the same tensor): role[i] = 2, role[k] = 1, sub_of[k] = i
+  std::vector<int> role(n, 0), sub_of(n, -1);
+  for (int i = 0; i < n && same_input; ++i) {
+    const int k = same_input[i];
+    if (k < 0 || k >= n || k == i || role[i] || role[k]) continue;
+    if (stage_sub_pair_ok(geoms[i], geoms[k], B)) { role[i] = 2; role[k] = 1; sub_of[k] = i; }
+  }
   for (int i = 0; i < n; ++i) {
     const ConvGeom& g = geoms[i];
     StageJobDev& j = jobs[i];
@@ -1263,8 +1333,17 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
       j.cornerbuf_off = ac_cornerbuf_off(g);
       j.Hc = ac_col_pitch(g);
     }
+    if (role[i] == 1) {
+      const ConvGeom& sg = geoms[sub_of[i]];
+      j.sub_stage = stages[sub_of[i]];
+      j.sub_hl = stage_hl_stride(sg);
+      j.sub_pitch = sg.Ws;
+      j.sub_wout = sg.Wout;
+      // the zero tail of the rows (Hout * Wout .. Ws) is written here, once per table
+      NSGP_CHECK_CUDA(cudaMemsetAsync(stages[sub_of[i]], 0, stage_bytes(sg), stream));
+    }
     const size_t before = items[2].size();
-    plan_stage_job(g, i, B, means[i] != nullptr, items, counts);
+    plan_stage_job(g, i, B, means[i] != nullptr, items, counts, role[i]);
     // the TMA autocorrelation routine writes the data words only: the padding of the tiled
     // layout (rows H, H + 1, columns >= W, channels >= C) is zeroed here, once per table
     if (items[2].size() > before && items[2][before].kind == kStAcVec)
