@@ -297,7 +297,8 @@ static inline size_t mean_scratch_elems(const ConvGeom& g) {
 // grouped staging (stage.cu): all layer inputs of a forward in one or two launches
 enum StageKind : int {
   kStFlatVec = 0, kStAcVec, kStAcEdges, kStMean, kStConv, kStExplicit, kStAcScalar, kSt3x3Vec,
-  kStFlatSub     // kStFlatVec that also writes the stride-2 subsample of a 1x1 s2 job on the same input
+  kStFlatSub,    // kStFlatVec that also writes the stride-2 subsample of a 1x1 s2 job on the same input
+  kStS2x3        // 3x3 stride-2 pad-1 tap copies straight from the input (TMA kernel only)
 };
 struct alignas(16) StageJobDev {
   ConvGeom g;

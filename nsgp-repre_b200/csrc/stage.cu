@@ -1024,6 +1024,56 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
         }
         continue;
       }
+      if (kind == kStS2x3) {
+        // 3x3 stride-2 pad-1: copy(p, jj)[c][r][x] = m[c][2(r-1) + py_p][2x - 1 + jj] with
+        // py = (1, 0): input row y lands in row phase p = 1 - (y & 1) at r = (y >> 1) + 1, its
+        // even columns in tap column 1, its odd columns in tap columns 0 (one to the right)
+        // and 2; every input element is read once, halo / padding words stay zero
+        const int H = j.g.H, W4 = j.g.W >> 2, HW4 = H * W4;
+        const int Hs = j.g.Hs, Ws = j.g.Ws, Wout = j.g.Wout, Cs = j.g.Cs;
+        const long long plane = (long long)Cs * Hs * Ws;     // one copy
+        int c0, r0, x0, dcC, drC, dxC, dcU, drU, dxU;
+        {
+          const long long q = it.lo + (long long)k0 * E4 + tid;
+          c0 = (int)(q / HW4);
+          int rem = (int)(q - (long long)c0 * HW4);
+          r0 = rem / W4; x0 = rem - r0 * W4;
+          const int dC = kTmaGroups * E4;
+          dcC = dC / HW4; rem = dC - dcC * HW4; drC = rem / W4; dxC = rem - drC * W4;
+          const int dU = kTmaGroupThreads;
+          dcU = dU / HW4; rem = dU - dcU * HW4; drU = rem / W4; dxU = rem - drU * W4;
+        }
+        for (int k = k0; k < n_chunks; k += kTmaGroups) {
+          const long long q0 = it.lo + (long long)k * E4;
+          wait_chunk();
+          const float4* raw = reinterpret_cast<const float4*>(smem + st * stage_tx);
+          int c = c0, y = r0, x4 = x0;
+          for (int f = tid; f < E4;
+               f += kTmaGroupThreads, radix_add(c, y, x4, dcU, drU, dxU, H, W4)) {
+            const float4 m = mean4(raw, f);
+            if (q0 + f >= it.hi) continue;
+            float4 h, l;
+            tf32_split_finite(m.x, h.x, l.x); tf32_split_finite(m.y, h.y, l.y);
+            tf32_split_finite(m.z, h.z, l.z); tf32_split_finite(m.w, h.w, l.w);
+            const int p = 1 - (y & 1);
+            float* o = stage + (long long)(p * 3) * plane +
+                       ((long long)c * Hs + (y >> 1) + 1) * Ws + 2 * x4;
+            float* o1 = o + plane;                   // tap column 1: even input columns
+            float* o2 = o1 + plane;                  // tap column 2: odd input columns
+            *reinterpret_cast<float2*>(o1) = make_float2(h.x, h.z);
+            *reinterpret_cast<float2*>(o1 + hl) = make_float2(l.x, l.z);
+            *reinterpret_cast<float2*>(o2) = make_float2(h.y, h.w);
+            *reinterpret_cast<float2*>(o2 + hl) = make_float2(l.y, l.w);
+            o[1] = h.y; o[1 + hl] = l.y;             // tap column 0: x = (xx + 1) / 2
+            if (2 * x4 + 2 < Wout) { o[2] = h.w; o[2 + hl] = l.w; }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          next_chunk();
+          radix_add(c0, r0, x0, dcC, drC, dxC, H, W4);
+        }
+        continue;
+      }
       if (kind != kStAcVec) {
         float* const dst = kind == kStMean ? j.mean : stage;
         for (int k = k0; k < n_chunks; k += kTmaGroups) {
@@ -1263,6 +1313,12 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
     add(0, kSt3x3Vec, 0, round_up((long long)g.C * g.Hs * (g.W / 4), 32), kVec);
     return;
   }
+  if (tma_job && g.mode == kModeImplicit && g.kh == 3 && g.kw == 3 && g.sh == 2 && g.sw == 2 &&
+      g.ph == 1 && g.pw == 1 && g.W % 4 == 0 && g.nrowphase == 2 && g.rowphase_py[0] == 1 &&
+      g.rowphase_py[1] == 0 && g.Ht == 1) {
+    add(2, kStS2x3, 0, img / 4, kTma);              // no batch-mean pass, no gather
+    return;
+  }
   const bool sparse = g.mode == kModeFlat && g.sh * g.sw > 1;
   const bool two = two_pass_ok && !sparse;
   if (two) {
@@ -1344,9 +1400,11 @@ int stage_group_build(const ConvGeom* geoms, float* const* stages, float* const*
     }
     const size_t before = items[2].size();
     plan_stage_job(g, i, B, means[i] != nullptr, items, counts, role[i]);
-    // the TMA autocorrelation routine writes the data words only: the padding of the tiled
-    // layout (rows H, H + 1, columns >= W, channels >= C) is zeroed here, once per table
-    if (items[2].size() > before && items[2][before].kind == kStAcVec)
+    // the TMA autocorrelation / stride-2 routines write the data words only: the padding of
+    // the layouts (halo rows, columns past the row end, channels >= C) is zeroed here, once
+    // per table
+    if (items[2].size() > before &&
+        (items[2][before].kind == kStAcVec || items[2][before].kind == kStS2x3))
       NSGP_CHECK_CUDA(cudaMemsetAsync(stages[i], 0, stage_bytes(g), stream));
   }
   info->n_jobs = n;
