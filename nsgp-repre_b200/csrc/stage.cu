@@ -605,6 +605,52 @@ stage_conv_explicit_body_t(const float* __restrict__ x, float* __restrict__ stag
   }
 }
 
+// One im2col row per work item (the grouped kernel's items never cross a row; Wout % 4 == 0,
+// plain layout): the (c, i, j) decode is paid once per item, (oy, ox) advance incrementally
+// and the four columns of a float4 share their input row - the general routine above spends
+// most of its instructions on three divisions and four bounds checks per float4.
+__device__ __forceinline__ void
+stage_conv_explicit_row_body(const float* __restrict__ x, float* __restrict__ stage,
+                             const ConvGeom& g, int B, long long hl_stride, long long first,
+                             int tid, int step, long long end) {
+  const int W4 = g.Ws >> 2;
+  const int row = (int)(first / W4);
+  const int k4_lo = (int)(first - (long long)row * W4), k4_hi = (int)(end - (long long)row * W4);
+  const int taps = g.kh * g.kw;
+  const int c = row / taps, t = row - c * taps;
+  const int i = t / g.kw, jj = t - i * g.kw;
+  const bool row_ok = row < g.C * taps;
+  const long long img = (long long)g.C * g.H * g.W;
+  const float fb = (float)B;
+  int k4 = k4_lo + tid;
+  int oy = (k4 * 4) / g.Wout, ox = k4 * 4 - oy * g.Wout;
+  const int d_oy = (step * 4) / g.Wout, d_ox = step * 4 - d_oy * g.Wout;
+  float* out = stage + (long long)row * g.Ws;
+  const float* plane = x + (long long)c * g.H * g.W;
+  for (; k4 < k4_hi; k4 += step) {
+    const int y = oy * g.sh - g.ph + i;
+    const int xx0 = ox * g.sw - g.pw + jj;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row_ok && y >= 0 && y < g.H) {
+      const float* src = plane + (long long)y * g.W + xx0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int xx = xx0 + e * g.sw;
+        if (xx >= 0 && xx < g.W) {
+          float acc = 0.f;
+          for (int b = 0; b < B; ++b) acc += __ldg(src + e * g.sw + (long long)b * img);
+          v[e] = acc / fb;
+        }
+      }
+    }
+    float* o = out + k4 * 4;
+    split_store4(o, o + hl_stride, v[0], v[1], v[2], v[3]);
+    ox += d_ox;
+    oy += d_oy + (ox >= g.Wout);
+    ox -= (ox >= g.Wout) ? g.Wout : 0;
+  }
+}
+
 __device__ __forceinline__ void
 stage_conv_explicit_body(const float* __restrict__ x, float* __restrict__ stage,
                          const ConvGeom& g, int B, long long hl_stride, long long first,
@@ -787,7 +833,11 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
         stage_conv_body(x, j.stage, g, Bx, j.hl, first, step, end);
         break;
       case kStExplicit:
-        stage_conv_explicit_body(x, j.stage, g, Bx, j.hl, first, step, end);
+        if (g.Wout % 4 == 0 && !g.ftiled)           // items are row-aligned (plan_stage_job)
+          stage_conv_explicit_row_body(x, j.stage, g, Bx, j.hl, it.lo, threadIdx.x, blockDim.x,
+                                       end);
+        else
+          stage_conv_explicit_body(x, j.stage, g, Bx, j.hl, first, step, end);
         break;
       case kStAcScalar:
         stage_autocorr_body(x, j.stage, g.C, g.H, g.W, g.Hs, g.Ws, Bx, j.hl, g.tiled,
@@ -1324,9 +1374,21 @@ static void plan_stage_job(const ConvGeom& g, int job, int B, bool have_mean,
   if (two) {
     if (tma_job) add(2, kStMean, 0, img / 4, kTma); else add(0, kStMean, 0, img / 4, kVec);
   }
-  if (g.mode == kModeExplicit)
-    add(two ? 1 : light, kStExplicit, two ? 1 : 0, (long long)g.Cs * (g.Ws / 4), kVec);
-  else
+  if (g.mode == kModeExplicit) {
+    // one item never crosses an im2col row (stage_conv_explicit_row_body)
+    const long long w4 = g.Ws / 4;
+    for (int row = 0; row < g.Cs; ++row)
+      for (long long lo = 0; lo < w4; lo += kVec) {
+        ++counts[two ? 1 : light];
+        if (items && !(skip_kinds >> kStExplicit & 1)) {
+          StageItem it{};
+          it.job = job; it.kind = (short)kStExplicit; it.from_mean = (short)(two ? 1 : 0);
+          it.lo = row * w4 + lo;
+          it.hi = row * w4 + (lo + kVec < w4 ? lo + kVec : w4);
+          items[two ? 1 : light].push_back(it);
+        }
+      }
+  } else
     add(two ? 1 : light, kStConv, two ? 1 : 0, (long long)g.Cs * g.Hs * g.ncopy * (g.Ws / 4), kVec);
 }
 
