@@ -351,15 +351,8 @@ class CovarianceHooks:
         # layerN.0.downsample.0 of a ResNet): the library stages a 1x1 stride-2 operand along
         # with the 1x1 stride-1 one.  Part of the table's signature: the promise is checked
         # against the tensors of every forward.
-        source = {}                                  # tensor -> its 1x1 stride-1 reader
-        for k, i in enumerate(uniq):
-            if js.jobs[i][1][3:] == (1, 1, 1, 1, 0, 0):
-                source.setdefault((js.xs[i].data_ptr(), tuple(js.xs[i].shape)), k)
-        same = []
-        for k, i in enumerate(uniq):
-            src = source.get((js.xs[i].data_ptr(), tuple(js.xs[i].shape)), -1)
-            same.append(src if src != k else -1)
-        same = tuple(same)
+        same = self._same_input_links([js.jobs[i][1] for i in uniq],
+                                      [(js.xs[i].data_ptr(), tuple(js.xs[i].shape)) for i in uniq])
         sig = (js.rev, B, same)
         if js.stage_sig != sig:
             n = len(uniq)
@@ -400,6 +393,18 @@ class CovarianceHooks:
             self._auto_stage_sms(js, B) if self.stage_sms == "auto" else int(self.stage_sms),
             side.cuda_stream), "nsgp_cov_pipeline_launch")
         self._inflight = js
+
+    @staticmethod
+    def _same_input_links(geoms, idents):
+        """``same_input`` of ``nsgp_cov_stage_group_build``: for every staged job the index of
+        the 1x1 stride-1 job that reads the same tensor (``idents``: one hashable per job,
+        equal for equal tensors), -1 when there is none or the job is that reader itself."""
+        source = {}
+        for k, (geom, ident) in enumerate(zip(geoms, idents)):
+            if tuple(geom[3:]) == (1, 1, 1, 1, 0, 0):
+                source.setdefault(ident, k)
+        return tuple(-1 if source.get(ident, k) == k else source[ident]
+                     for k, ident in enumerate(idents))
 
     def _auto_stage_sms(self, js, B):
         """Partition of the SMs between the two concurrent kernels of the pipelined pass

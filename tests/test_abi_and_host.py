@@ -257,3 +257,20 @@ def test_auto_stage_partition_balances_with_batch_size():
     js.jobs.append(["a", (64, 8, 8, 1, 1, 1, 1, 0, 0), None, la, None])
     js.xs.append(object())
     assert cv.CovarianceHooks(torch.nn.Identity())._auto_stage_sms(js, 8) == 0
+
+
+def test_same_input_links_pair_a_tensor_with_its_1x1_reader():
+    """CovarianceHooks._same_input_links (host half of `same_input`): jobs that read the
+    tensor of a 1x1 stride-1 job point at it, whatever the hook order; the reader itself and
+    jobs on other tensors get -1; with two 1x1 readers the first one is the source."""
+    from nsgp_repre_b200.covariance import CovarianceHooks
+    s1 = (256, 200, 336, 1, 1, 1, 1, 0, 0)          # layer2.0.conv1
+    s2 = (256, 200, 336, 1, 1, 2, 2, 0, 0)          # layer2.0.downsample.0
+    c3 = (256, 200, 336, 3, 3, 1, 1, 1, 1)
+    other = (64, 200, 336, 1, 1, 1, 1, 0, 0)
+    link = CovarianceHooks._same_input_links
+    assert link([s1, s2, other], ["x", "x", "y"]) == (-1, 0, -1)
+    assert link([s2, c3, s1], ["x", "x", "x"]) == (2, 2, -1)          # reader hooked last
+    assert link([s2, other], ["x", "x2"]) == (-1, -1)                  # no 1x1 reader of x
+    assert link([s1, s1, s2], ["x", "x", "x"]) == (-1, 0, 0)
+    assert link([], []) == ()
