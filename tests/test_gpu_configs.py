@@ -237,6 +237,42 @@ def test_covariance_every_batch_size_through_the_staging_ring(pkg, B, stage_sms)
         assert worst < 1e-4, (k, B, worst)
 
 
+def test_covariance_pipeline_many_forwards_fresh_inputs(pkg):
+    """30 forwards with NEW activations each (new addresses: the tensor maps are re-encoded,
+    the two workspace sets alternate, the contraction of forward i-1 runs beside the staging
+    of forward i on a forced partition) accumulate to the sum of the oracle's per-forward
+    covariances."""
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(7)
+    model = _FourLayouts().cuda()
+    old = pkg.CovarianceHooks.stage_sms
+    pkg.CovarianceHooks.stage_sms = 48
+    want = {}
+    keep = []
+    try:
+        hooks = pkg.CovarianceHooks(model, add_default_ignores=False).register()
+        with torch.no_grad():
+            for it in range(30):
+                img = torch.relu(torch.randn(B, 4, 32, 64, device="cuda", generator=g))
+                x = torch.relu(torch.randn(B, 64, 16, 20, device="cuda", generator=g))
+                if it % 3 == 0:
+                    keep.append((img, x))            # vary the allocator's reuse pattern
+                model(img, x)
+                for k, (t, ks, st, pd) in {"stem": (img, 7, 2, 3), "c3": (x, 3, 1, 1),
+                                           "c1": (x, 1, 1, 0), "s2": (x, 3, 2, 1),
+                                           "d2": (x, 1, 2, 0)}.items():
+                    c = O.cov_conv2d(t.double(), (ks, ks), (st, st), (pd, pd))
+                    want[k] = c if k not in want else want[k] + c
+        hooks.remove()
+        fea = hooks.fea_in
+    finally:
+        pkg.CovarianceHooks.stage_sms = old
+    for k, w in want.items():
+        got = fea[k + ".weight"].double()
+        worst = float((got - w).abs().max() / w.abs().max())
+        assert worst < 1e-4, (k, worst)
+
+
 # ------------------------------------------------------------------ one key, several extents
 def test_covariance_shared_module_five_levels_one_key(pkg):
     """rpn_head.rpn_conv / rpn_cls are applied to the five FPN levels: five hook calls at
