@@ -893,14 +893,22 @@ static inline int tma_box_rows(int B) {
   if (4 * B <= 48) return 4;
   return 48 / B > 0 ? 48 / B : 1;
 }
-// ring slots: as many stages as fit 192 KB (<= kTmaStages)
+constexpr int kTmaMeanBytes = kTmaMaxRows * 1024;    // one buffer of means
+constexpr int kTmaMeansBytes = 2 * kTmaGroups * kTmaMeanBytes;
+// The sliding-window routine needs the next float4's means.  Template instances with a
+// compile-time batch <= 8 take them from the next lane (lane 31 recomputes them from the raw
+// chunk): no mean buffers, the ring gets their 32 KB (7 x 32 KB stages at B = 8).  Larger or
+// run-time batches exchange the means through shared memory (lane 31's serial recompute of
+// B loads costs more than the group barrier there: configs[4] 5.58 vs 5.75 ms per step).
+static inline bool tma_shuffle_variant(int B) { return B == 8 || B == 4 || B == 2 || B == 1; }
+// ring slots: as many stages as fit the ring (<= kTmaStages)
 static inline int tma_ring_stages(int B) {
-  const int n = kTmaRingBytes / (B * tma_box_rows(B) * 1024);
+  const int ring = kTmaRingBytes + (tma_shuffle_variant(B) ? kTmaMeansBytes : 0);
+  const int n = ring / (B * tma_box_rows(B) * 1024);
   return n >= kTmaStages ? kTmaStages : n;
 }
-constexpr int kTmaMeanBytes = kTmaMaxRows * 1024;    // one buffer of means
 static inline size_t stage_tma_smem_bytes() {
-  return (size_t)kTmaRingBytes + 2 * kTmaGroups * kTmaMeanBytes + 128 /* alignment slack */;
+  return (size_t)kTmaRingBytes + kTmaMeansBytes + 128 /* alignment slack */;
 }
 
 // cvt.rna.tf32.f32 is lowered to integer add + mask + an inf / NaN guard on sm_100a; the
@@ -994,6 +1002,7 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       st += kTmaGroups;
       while (st >= (uint32_t)n_stages) { st -= n_stages; ++lap; }
     };
+    constexpr bool kShuffle = KB == 8 || KB == 4 || KB == 2 || KB == 1;   // tma_shuffle_variant
     float4* const mean_s = reinterpret_cast<float4*>(smem + kTmaRingBytes +
                                                      gid * 2 * kTmaMeanBytes);
     int mbuf = 0;
@@ -1017,6 +1026,18 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
       if (pow2) { s4.x *= inv; s4.y *= inv; s4.z *= inv; s4.w *= inv; }
       else { s4.x /= fb; s4.y /= fb; s4.z /= fb; s4.w /= fb; }
       return s4;
+    };
+    // first two elements of the batch mean of float4 f (same summation order as mean4)
+    auto mean2 = [&](const float4* raw, int f) {
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < (KB > 0 ? KB : 1); ++b) {
+        const float2 v = *reinterpret_cast<const float2*>(raw + b * E4 + f);
+        s2.x += v.x; s2.y += v.y;
+      }
+      if (pow2) { s2.x *= inv; s2.y *= inv; }
+      else { s2.x /= fb; s2.y /= fb; }
+      return s2;
     };
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const StageItem it = items[w];
@@ -1177,27 +1198,37 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
         const long long q0 = it.lo + (long long)k * E4;
         wait_chunk();
         const float4* raw = reinterpret_cast<const float4*>(smem + st * stage_tx);
-        // means into shared memory (the raw chunk is then consumed), then the stores
         float4* ms = mean_s + mbuf * (kTmaMeanBytes / 16);
-        mbuf ^= 1;
-        for (int f = tid; f < E4; f += kTmaGroupThreads) ms[f] = mean4(raw, f);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-        next_chunk();
-        switch (gid) {                               // the group's own named barrier
-          case 0: asm volatile("bar.sync 1, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
-          case 1: asm volatile("bar.sync 2, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
-          case 2: asm volatile("bar.sync 3, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
-          default: asm volatile("bar.sync 4, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+        if (!kShuffle) {
+          // means into shared memory (the raw chunk is then consumed), then the stores
+          mbuf ^= 1;
+          for (int f = tid; f < E4; f += kTmaGroupThreads) ms[f] = mean4(raw, f);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+          switch (gid) {                             // the group's own named barrier
+            case 0: asm volatile("bar.sync 1, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+            case 1: asm volatile("bar.sync 2, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+            case 2: asm volatile("bar.sync 3, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+            default: asm volatile("bar.sync 4, %0;" ::"n"(kTmaGroupThreads) : "memory"); break;
+          }
         }
         int c = c0, r = r0, x4 = x0;
         for (int f = tid; f < E4; f += kTmaGroupThreads, radix_add(c, r, x4, dcU, drU, dxU, H, W4)) {
-          if (q0 + f >= it.hi) break;
-          const float4 mm = ms[f];
+          if (q0 + f >= it.hi) break;                // warp-uniform: hi is a multiple of 64
           const bool next_data = x4 + 1 < W4;
-          const bool in_stage = f + 1 < E4;          // the next float4's means are in `ms`
+          const bool in_stage = f + 1 < E4;          // the next float4 belongs to this chunk
+          float4 mm;
           float2 nx = make_float2(0.f, 0.f);
-          if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(ms + f + 1);
+          if (kShuffle) {
+            // the next float4's two means from the next lane; lane 31 recomputes them
+            mm = mean4(raw, f);
+            const float sx = __shfl_down_sync(0xffffffffu, mm.x, 1);
+            const float sy = __shfl_down_sync(0xffffffffu, mm.y, 1);
+            if (next_data && in_stage) nx = lane == 31 ? mean2(raw, f + 1) : make_float2(sx, sy);
+          } else {
+            mm = ms[f];
+            if (next_data && in_stage) nx = *reinterpret_cast<const float2*>(ms + f + 1);
+          }
           const bool defer = next_data && !in_stage;
           float h[6], l[6];
           tf32_split_finite(mm.x, h[0], l[0]); tf32_split_finite(mm.y, h[1], l[1]);
@@ -1280,6 +1311,11 @@ stage_tma_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __restri
           }
         }
         radix_add(c0, r0, x0, dcC, drC, dxC, H, W4);
+        if (kShuffle) {                              // the raw chunk was read until here
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        next_chunk();
       }
     }
   }
