@@ -858,9 +858,9 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
 // The register routines keep their loads in flight in registers - ~128 KB per SM at most,
 // fine when all 148 SMs stage, not when the staging only gets a slice of the GPU next to the
 // sliding-window contraction.  Here ONE 3-D tensor-map box (256 floats x rows x B images,
-// <= 32 KB) brings the same chunk of all B images into shared memory and six of them are
-// in flight per SM (scripts/tma3d_probe.py: the loads alone reach 149 GB/s per SM).
-//   warp 0        producer: cp.async.bulk.tensor.3d into a 6-stage ring, mbarrier complete_tx
+// <= 32 KB) brings the same chunk of all B images into shared memory and six or seven of
+// them are in flight per SM (scripts/tma3d_probe.py: the loads alone reach 149 GB/s per SM).
+//   warp 0        producer: cp.async.bulk.tensor.3d into a 6- or 7-stage ring, mbarrier tx
 //   warps 1..16   kTmaGroups consumer groups; group g takes the chunks g, g + G, ... of the
 //                 CTA's chunk sequence: batch mean out of shared memory, tf32 split, layout
 //                 stores.  A group does not see every lap of a ring slot, so before the
@@ -871,8 +871,8 @@ stage_group_kernel(const StageJobDev* __restrict__ jobs, const StageItem* __rest
 //                 the sliding-window kernel the phase is HBM-bound from ~56 SMs on.
 // Index space = float4s of the per-image tensor (every routine's input is contiguous).
 // Autocorrelation layout: the two column-shifted copies need the NEXT float4's first two
-// means; the means go through a (double-buffered, per group) shared array, so inside a stage
-// they come from there; at a stage end the owner writes only the words it knows and the
+// means; inside a stage they come from the next lane (compile-time batch <= 8) or through a
+// double-buffered, per-group shared array; at a stage end the owner writes only the words it knows and the
 // first thread of the next stage (maybe in another CTA) writes the rest - disjoint words, no
 // ordering needed.  The threads that hold the first / last float4 of an image row also write
 // the edge-column and corner-pixel buffers of the boundary corrections.  Padding of the tiled
